@@ -1,0 +1,173 @@
+"""Float64 coordinate oracle (TEST INFRASTRUCTURE -- see oracle/__init__.py).
+
+Restates, in float64 NumPy, the geometry the reference uses to go from an
+output (perspective) pixel to a source pixel position:
+
+* panorama (ERP) source -- gs360_GUI.py:342-395 (normalise, pitch about X, yaw
+  about Y, lon = atan2(x, z), lat = asin(y)) and gs360_GUI.py:419-424
+  (lon/lat -> ERP pixel position, edge origin).  Output pixel centres follow
+  cli_tools/gs360_DualFisheyeDistortionCalibration.py:1771-1778
+  (``((i + 0.5) / w) * 2 - 1``), which is also what FFmpeg's v360 filter uses
+  for its rectilinear output.
+* dual-fisheye source -- gs360_DualFisheyeDistortionCalibration.py:1759-1823
+  (equisolid projection, Brown distortion :975-1005, affinity b1/b2, validity
+  by lens half-FOV and image bounds) and the lens choice of :1857-1907.
+
+Two ERP pixel conventions are exposed because the replaced filter and the
+in-repo code disagree by up to half a pixel:
+
+``halfpixel``  x = (lon/2pi + 0.5) * W - 0.5      y = (0.5 - lat/pi) * H - 0.5
+``v360``       x = (lon/2pi + 0.5) * (W - 1)      y = (0.5 - lat/pi) * (H - 1)
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Dict, Mapping, Sequence, Tuple
+
+import numpy as np
+
+CONVENTIONS = ("halfpixel", "v360")
+
+
+def view_rotation(yaw_deg: float, pitch_deg: float, roll_deg: float = 0.0) -> np.ndarray:
+    """World-from-camera rotation: roll about the view axis, then pitch about X,
+    then yaw about Y, with the signs of gs360_GUI.py:351-374.
+
+    The reference never rolls (``roll=0`` at gs360_360PerspCut.py:312); roll is
+    defined here as a right-handed turn about +z in the y-up camera frame.
+    """
+    cy, sy = math.cos(math.radians(yaw_deg)), math.sin(math.radians(yaw_deg))
+    cp, sp = math.cos(math.radians(pitch_deg)), math.sin(math.radians(pitch_deg))
+    cr, sr = math.cos(math.radians(roll_deg)), math.sin(math.radians(roll_deg))
+    r_yaw = np.array([[cy, 0.0, sy], [0.0, 1.0, 0.0], [-sy, 0.0, cy]])
+    r_pitch = np.array([[1.0, 0.0, 0.0], [0.0, cp, sp], [0.0, -sp, cp]])
+    r_roll = np.array([[cr, -sr, 0.0], [sr, cr, 0.0], [0.0, 0.0, 1.0]])
+    return r_yaw @ r_pitch @ r_roll
+
+
+def _clamped_fov_rad(fov_deg: float) -> float:
+    # gs360_GUI.py:437-438 and DF:1781-1782 clamp to [1e-3, 179.9] degrees.
+    return math.radians(min(max(float(fov_deg), 1e-3), 179.9))
+
+
+def camera_rays(out_w: int, out_h: int, hfov_deg: float, vfov_deg: float,
+                yaw_deg: float, pitch_deg: float, roll_deg: float = 0.0) -> np.ndarray:
+    """Unit rays (h, w, 3), y up, after the view rotation (float64)."""
+    u = ((np.arange(out_w, dtype=np.float64) + 0.5) / float(out_w)) * 2.0 - 1.0
+    v = ((np.arange(out_h, dtype=np.float64) + 0.5) / float(out_h)) * 2.0 - 1.0
+    uu, vv = np.meshgrid(u, v)
+    rays = np.empty((out_h, out_w, 3), dtype=np.float64)
+    rays[..., 0] = math.tan(_clamped_fov_rad(hfov_deg) * 0.5) * uu
+    rays[..., 1] = math.tan(_clamped_fov_rad(vfov_deg) * 0.5) * (-vv)
+    rays[..., 2] = 1.0
+    rays /= np.linalg.norm(rays, axis=2, keepdims=True)
+    if roll_deg:
+        rays = rays @ view_rotation(0.0, 0.0, roll_deg).T
+    # pitch then yaw, written out as in gs360_GUI.py:351-374 / DF:1310-1339
+    cp, sp = math.cos(math.radians(pitch_deg)), math.sin(math.radians(pitch_deg))
+    cy, sy = math.cos(math.radians(yaw_deg)), math.sin(math.radians(yaw_deg))
+    x, y, z = rays[..., 0], rays[..., 1], rays[..., 2]
+    y1 = cp * y + sp * z
+    z1 = -sp * y + cp * z
+    x2 = cy * x + sy * z1
+    z2 = -sy * x + cy * z1
+    return np.stack([x2, y1, z2], axis=-1)
+
+
+def erp_map64(src_w: int, src_h: int, out_w: int, out_h: int,
+              yaw_deg: float, pitch_deg: float, hfov_deg: float, vfov_deg: float,
+              convention: str = "halfpixel", roll_deg: float = 0.0
+              ) -> Tuple[np.ndarray, np.ndarray]:
+    """Source pixel position (x, y) in an ERP of size src_w x src_h for every
+    output pixel.  x is NOT wrapped into [0, W): it lies in [-0.5, W - 0.5) for
+    ``halfpixel`` and [0, W - 1] for ``v360``; the sampler wraps taps."""
+    if convention not in CONVENTIONS:
+        raise ValueError("unknown convention: %r" % (convention,))
+    rays = camera_rays(out_w, out_h, hfov_deg, vfov_deg, yaw_deg, pitch_deg, roll_deg)
+    lon = np.arctan2(rays[..., 0], rays[..., 2])
+    lat = np.arcsin(np.clip(rays[..., 1], -1.0, 1.0))
+    if convention == "halfpixel":
+        mx = (lon / (2.0 * math.pi) + 0.5) * src_w - 0.5
+        my = (0.5 - lat / math.pi) * src_h - 0.5
+    else:
+        mx = (lon / (2.0 * math.pi) + 0.5) * (src_w - 1)
+        my = (0.5 - lat / math.pi) * (src_h - 1)
+    return mx, my
+
+
+# --------------------------------------------------------------------------
+# dual fisheye (equisolid + Brown), DF:1759-1823
+# --------------------------------------------------------------------------
+
+CALIB_KEYS = ("width", "height", "f", "cx", "cy", "k1", "k2", "k3", "k4",
+              "p1", "p2", "b1", "b2")
+
+
+def brown_distort(x: np.ndarray, y: np.ndarray, c: Mapping[str, float]):
+    """DF:975-1005."""
+    r2 = x * x + y * y
+    r4 = r2 * r2
+    radial = 1.0 + c["k1"] * r2 + c["k2"] * r4 + c["k3"] * (r4 * r2) + c["k4"] * (r4 * r4)
+    xd, yd = x * radial, y * radial
+    if c["p1"] != 0.0 or c["p2"] != 0.0:
+        xy = x * y
+        xd = xd + c["p1"] * (r2 + 2.0 * x * x) + 2.0 * c["p2"] * xy
+        yd = yd + c["p2"] * (r2 + 2.0 * y * y) + 2.0 * c["p1"] * xy
+    return xd, yd
+
+
+def fisheye_map64(calib: Mapping[str, float], yaw_rel_deg: float, pitch_deg: float,
+                  hfov_deg: float, vfov_deg: float, out_w: int, out_h: int,
+                  lens_fov_deg: float) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(map_x, map_y, valid) for one lens, float64 restatement of DF:1759-1823."""
+    rays = camera_rays(out_w, out_h, hfov_deg, vfov_deg, yaw_rel_deg, pitch_deg)
+    rx, ry, rz = rays[..., 0], rays[..., 1], rays[..., 2]
+    theta = np.arccos(np.clip(rz, -1.0, 1.0))
+    theta_max = math.radians(max(1.0, min(360.0, float(lens_fov_deg))) * 0.5)
+    rho = np.sqrt(rx * rx + ry * ry)
+    scale = np.zeros_like(rho)
+    nz = rho > 1e-12
+    scale[nz] = 2.0 * np.sin(theta[nz] * 0.5) / rho[nz]
+    xn = rx * scale
+    yn = -ry * scale
+    xd, yd = brown_distort(xn, yn, calib)
+    cx0 = calib["width"] * 0.5 + calib["cx"]
+    cy0 = calib["height"] * 0.5 + calib["cy"]
+    mx = cx0 + xd * calib["f"] + xd * calib["b1"] + yd * calib["b2"]
+    my = cy0 + yd * calib["f"]
+    valid = theta <= theta_max
+    valid &= (mx >= 0.0) & (mx <= calib["width"] - 1)
+    valid &= (my >= 0.0) & (my <= calib["height"] - 1)
+    return mx, my, valid
+
+
+def wrap_angle_deg(a: float) -> float:
+    """DF:1342-1345: wrap to [-180, 180)."""
+    return ((float(a) + 180.0) % 360.0) - 180.0
+
+
+def dualfisheye_view_maps(calib_x: Mapping[str, float], calib_y: Mapping[str, float],
+                          specs: Sequence[Mapping[str, object]],
+                          lens_x_yaw_deg: float = 0.0, lens_y_yaw_deg: float = 180.0,
+                          lens_fov_deg: float = 190.0) -> Dict[str, Dict[str, object]]:
+    """Per view: maps for both lenses, keep the one with the larger valid ratio,
+    ties broken by smaller |relative yaw| (DF:1857-1907)."""
+    out: Dict[str, Dict[str, object]] = {}
+    for spec in specs:
+        best = None
+        for lens_key, lens_yaw, calib in (("X", lens_x_yaw_deg, calib_x),
+                                          ("Y", lens_y_yaw_deg, calib_y)):
+            yaw_rel = wrap_angle_deg(float(spec["yaw_deg"]) - lens_yaw)
+            mx, my, valid = fisheye_map64(
+                calib, yaw_rel, float(spec["pitch_deg"]), float(spec["hfov_deg"]),
+                float(spec["vfov_deg"]), int(spec["width"]), int(spec["height"]),
+                lens_fov_deg)
+            key = (float(np.mean(valid)), -abs(yaw_rel))
+            if best is None or key > best[0]:
+                best = (key, lens_key, yaw_rel, mx, my, valid)
+        out[str(spec["view_id"])] = {
+            "lens_key": best[1], "yaw_rel_deg": best[2],
+            "map_x": best[3], "map_y": best[4], "valid": best[5],
+        }
+    return out

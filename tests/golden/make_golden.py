@@ -1,0 +1,237 @@
+#!/usr/bin/env python3
+"""Regenerate the fixtures in tests/golden/ by RUNNING THE REFERENCE.
+
+Only works where the reference checkout exists (this build container):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [/root/reference]
+
+It imports the reference's own modules (nothing is copied) and records their
+outputs; the tests then check the oracle and the product against those files,
+so the reference does not need to exist where the tests run (the GPU box).
+
+Files written
+-------------
+perspcut_views.json     ``gs360_360PerspCut.build_view_jobs`` for every preset and
+                        a set of --addcam/--setcam/--delcam/--size/... variants
+                        (jobs argv, names, ViewSpecs, FOVs, the four log lines)
+perspcut_helpers.json   small pure helpers (fov_from_focal_mm, v_fov_from_hfov,
+                        letter_tag, normalize_angle_deg, extra_suffix, parse_*)
+dualfisheye.json        template calibration as parsed by the reference,
+                        ``build_sfm10_specs`` output, lens choice + valid ratio
+                        of ``build_perspective_spec_maps`` at 1750 px
+dualfisheye_maps.npz    reference float32 maps: all views x both lenses at 96 px,
+                        a strided sample (every 25th pixel) of the chosen-lens
+                        maps at 1750 px, and 64 px maps for a synthetic
+                        calibration with every Brown/affinity term non-zero
+cv2_remap.npz           ``cv2.remap`` outputs (the routine the reference calls,
+                        DF:2001-2008) for small random sources x dtypes x
+                        interpolations x borders
+"""
+
+import argparse
+import json
+import math
+import pathlib
+import sys
+
+import numpy as np
+
+HERE = pathlib.Path(__file__).resolve().parent
+
+
+def _args_for(pc, argv, video=False, bit_depth=8):
+    ap = pc.create_arg_parser()
+    args = ap.parse_args(argv)
+    for name in ("size", "hfov", "focal_mm"):
+        setattr(args, name + "_explicit", getattr(args, name + "_explicit", False))
+    args.input_is_video = video
+    args.video_bit_depth = bit_depth
+    return args
+
+
+PERSPCUT_CASES = [
+    # (name, argv after "-i IN", files, video, bit_depth)
+    ("default", [], ["pano0001.jpg"], False, 8),
+    ("fisheyelike", ["--preset", "fisheyelike"], ["pano0001.jpg"], False, 8),
+    ("full360coverage", ["--preset", "full360coverage"], ["pano0001.jpg"], False, 8),
+    ("2views", ["--preset", "2views"], ["pano0001.jpg"], False, 8),
+    ("evenMinus30", ["--preset", "evenMinus30"], ["pano0001.jpg"], False, 8),
+    ("evenPlus30", ["--preset", "evenPlus30"], ["pano0001.jpg"], False, 8),
+    ("fisheyeXY", ["--preset", "fisheyeXY"], ["pano0001.jpg"], False, 8),
+    ("fisheyeXY_sized", ["--preset", "fisheyeXY", "--size", "2000", "--hfov", "170"],
+     ["pano0001.jpg"], False, 8),
+    ("two_files_png", ["--ext", "png"], ["a.tif", "b.png"], False, 8),
+    ("count4_topbottom", ["--count", "4", "--hfov", "105", "--add-top", "--add-bottom"],
+     ["p.jpg"], False, 8),
+    ("topdown_hidden", ["--add-topdown", "--count", "6"], ["p.jpg"], False, 8),
+    ("addcam_mix", ["--addcam", "B,D:U,F:D20,H:U12.5", "--addcam-deg", "25"], ["p.jpg"], False, 8),
+    ("delcam_setcam", ["--delcam", "B,d,8", "--setcam", "A=30,C:-10,E=U,G=D15"], ["p.jpg"], False, 8),
+    ("setcam_extra", ["--addcam", "A,C", "--setcam", "A_U=50,A_D:+5,C:+10,C_U:-5"], ["p.jpg"], False, 8),
+    ("setcam_clamp", ["--setcam", "A=120,B=-95"], ["p.jpg"], False, 8),
+    ("count30", ["--count", "30", "--size", "800"], ["p.jpg"], False, 8),
+    ("focal_sensor", ["--focal-mm", "18", "--sensor-mm", "36x24", "--size", "1200"], ["p.jpg"], False, 8),
+    ("sensor_apsc", ["--focal-mm", "10", "--sensor-mm", "23.5 15.6"], ["p.jpg"], False, 8),
+    ("hfov_explicit", ["--hfov", "90", "--size", "1024"], ["p.jpg"], False, 8),
+    ("preset_override", ["--preset", "full360coverage", "--focal-mm", "16", "--size", "1800"],
+     ["p.jpg"], False, 8),
+    ("fisheyelike_user_del", ["--preset", "fisheyelike", "--delcam", "B", "--addcam", "C:U10"],
+     ["p.jpg"], False, 8),
+    ("jpeg95", ["--jpeg-quality-95"], ["p.jpg"], False, 8),
+    ("video_jpg", ["--preset", "fisheyelike", "-f", "2"], ["vid.mp4"], True, 8),
+    ("video_png10", ["--preset", "fisheyelike", "-f", "2", "--ext", "png"], ["vid.mp4"], True, 10),
+    ("video_tif_keep709", ["-f", "0.5", "--ext", "tif", "--keep-rec709", "--start", "3", "--end", "12.5"],
+     ["clip.mov"], True, 8),
+    ("video_fisheyeXY", ["--preset", "fisheyeXY", "-f", "1"], ["vid.mp4"], True, 8),
+]
+
+
+def dump_perspcut(pc):
+    out = {}
+    for name, extra, files, video, depth in PERSPCUT_CASES:
+        argv = ["-i", "/tmp/in"] + list(extra)
+        args = _args_for(pc, argv, video, depth)
+        paths = [pathlib.Path("/tmp/in") / f for f in files]
+        res = pc.build_view_jobs(args, paths, pathlib.Path("/tmp/out"))
+        out[name] = {
+            "argv": argv, "files": files, "video": video, "bit_depth": depth,
+            "jobs": [[list(cmd), src, dst] for cmd, src, dst in res.jobs],
+            "view_specs": [
+                {"source_path": str(v.source_path), "output_name": v.output_name,
+                 "view_id": v.view_id, "yaw_deg": v.yaw_deg, "pitch_deg": v.pitch_deg,
+                 "hfov_deg": v.hfov_deg, "vfov_deg": v.vfov_deg, "width": v.width,
+                 "height": v.height, "projection": v.projection}
+                for v in res.view_specs],
+            "focal_used_mm": res.focal_used_mm, "focal_35mm_equiv": res.focal_35mm_equiv,
+            "hfov_deg": res.hfov_deg, "vfov_deg": res.vfov_deg,
+            "preview_views_line": res.preview_views_line, "sensor_line": res.sensor_line,
+            "realityscan_line": res.realityscan_line, "metashape_line": res.metashape_line,
+            "args_after": {k: getattr(args, k) for k in ("count", "size", "focal_mm", "add_top", "add_bottom")},
+        }
+    (HERE / "perspcut_views.json").write_text(json.dumps(out, indent=1, sort_keys=True) + "\n")
+
+    helpers = {
+        "fov_from_focal_mm": [[f, s, pc.fov_from_focal_mm(f, s)]
+                              for f, s in ((12, 36), (14, 36), (17, 36), (6, 36), (10, 23.5), (50, 36))],
+        "focal_from_hfov_deg": [[a, s, pc.focal_from_hfov_deg(a, s)] for a, s in ((90, 36), (105, 36), (60, 24))],
+        "v_fov_from_hfov": [[a, w, h, pc.v_fov_from_hfov(a, w, h)] for a, w, h in ((90, 1600, 1600), (100, 1920, 1080), (70, 800, 1200))],
+        "letter_tag": [[i, pc.letter_tag(i)] for i in (0, 1, 7, 25, 26, 27, 40)],
+        "letter_to_index1": [[s, pc.letter_to_index1(s)] for s in ("A", "b", " h ", "12", "Z")],
+        "normalize_angle_deg": [[a, pc.normalize_angle_deg(a)] for a in (0, 45, 180, -180, 181, 359.5, 540, -181, 179.9999999)],
+        "extra_suffix": [[d, dd, pc.extra_suffix(d, dd)] for d, dd in ((30, 30), (-30, 30), (20, 30), (-12.5, 30), (25, 25), (-40, 25))],
+        "parse_jobs": [[s, pc.parse_jobs(s)] for s in ("1", "7", "0", "-3")],
+        "parse_sensor": [[s, pc.parse_sensor(s)] for s in ("36 36", "36x24", "23.5,15.6", "24")],
+        "parse_addcam_spec": [[s, d, {str(k): v for k, v in pc.parse_addcam_spec(s, d).items()}]
+                              for s, d in (("B", 30.0), ("B:U,D:D20", 30.0), ("A=u15, C", 20.0), ("", 30.0))],
+        "parse_delcam_spec": [[s, sorted(pc.parse_delcam_spec(s))] for s in ("B,D", "a, 3 ,H", "")],
+    }
+    setcam = []
+    for s, d in (("A=30,B:-5", 30.0), ("A=U,B=D20,C:U15", 30.0), ("A_U=5,A_D:+5", 30.0), ("", 30.0)):
+        a, b, c, e = pc.parse_setcam_spec(s, d)
+        setcam.append([s, d, {str(k): v for k, v in a.items()}, {str(k): v for k, v in b.items()},
+                       {"%d%s" % k: v for k, v in c.items()}, {"%d%s" % k: v for k, v in e.items()}])
+    helpers["parse_setcam_spec"] = setcam
+    (HERE / "perspcut_helpers.json").write_text(json.dumps(helpers, indent=1, sort_keys=True) + "\n")
+
+
+def _calib_dict(c):
+    return {k: getattr(c, k) for k in ("sensor_id", "model_type", "width", "height", "f", "cx", "cy",
+                                       "k1", "k2", "k3", "k4", "p1", "p2", "b1", "b2")}
+
+
+def dump_dualfisheye(df):
+    sensor_map, cam_to_sensor = df.load_metashape_calibration(df.DEFAULT_CAMERA_XML)
+    calib = sensor_map[sorted(sensor_map)[0]]
+    meta = {
+        "template_xml": "cli_tools/templates/Osmo360-Fisheye-Distortion.xml",
+        "sensors": {k: _calib_dict(v) for k, v in sensor_map.items()},
+        "n_camera_labels": len(cam_to_sensor),
+        "camera_to_sensor_sample": dict(sorted(cam_to_sensor.items())[:6]),
+        "compute_view_fov_deg": [[f, s, list(df.compute_view_fov_deg(f, s))]
+                                 for f, s in ((14.0, "36 36"), (12.0, "36x24"), (0.05, "36 36"), (4000.0, "36 36"))],
+        "wrap_angle_deg": [[a, df.wrap_angle_deg(a)] for a in (0, 180, -180, 220, 320, 539, -181)],
+    }
+    specs = df.build_sfm10_specs(1750, 14.0, "36 36", 40.0, 40.0)
+    meta["sfm10_default"] = specs
+    meta["sfm10_alt"] = df.build_sfm10_specs(1200, 12.0, "36x24", 35.0, 25.0)
+
+    arrays = {}
+    # (1) default layout at 1750 px: lens choice, valid ratio, strided sample
+    maps = df.build_perspective_spec_maps(sensor_map, calib.sensor_id, calib.sensor_id, specs, 0.0, 180.0, 190.0)
+    stride = 25
+    meta["maps_1750"] = {"stride": stride, "views": {}}
+    for vid, m in maps.items():
+        meta["maps_1750"]["views"][vid] = {"lens_key": m["lens_key"], "valid_ratio": float(np.mean(m["valid"]))}
+        arrays["s1750_%s_x" % vid] = m["map_x"][::stride, ::stride].copy()
+        arrays["s1750_%s_y" % vid] = m["map_y"][::stride, ::stride].copy()
+        arrays["s1750_%s_v" % vid] = m["valid"][::stride, ::stride].copy()
+    # (2) every view x both lenses at 96 px, full maps (includes invalid regions)
+    small = df.build_sfm10_specs(96, 14.0, "36 36", 40.0, 40.0)
+    for spec in small:
+        for lens_key, lens_yaw in (("X", 0.0), ("Y", 180.0)):
+            yaw_rel = df.wrap_angle_deg(spec["yaw_deg"] - lens_yaw)
+            mx, my, valid = df.build_direct_perspective_map_for_lens(
+                calib, yaw_rel, spec["pitch_deg"], spec["hfov_deg"], spec["vfov_deg"], 96, 96, 190.0)
+            key = "m96_%s_%s" % (spec["view_id"], lens_key)
+            arrays[key + "_x"], arrays[key + "_y"], arrays[key + "_v"] = mx, my, valid
+    # (3) synthetic calibration exercising k4, p1, p2, b1, b2 and a non-square sensor
+    syn = df.SensorCalibration(sensor_id="9", model_type="equisolid_fisheye", width=3000, height=2800,
+                               f=820.5, cx=12.25, cy=-7.5, k1=0.08, k2=-0.011, k3=0.0021, k4=-0.0003,
+                               p1=0.0007, p2=-0.0004, b1=1.75, b2=-0.6)
+    meta["synthetic_calibration"] = _calib_dict(syn)
+    syn_views = [(0.0, 0.0), (35.0, 20.0), (-60.0, -35.0), (95.0, 5.0)]
+    meta["synthetic_views"] = syn_views
+    for n, (yaw, pitch) in enumerate(syn_views):
+        mx, my, valid = df.build_direct_perspective_map_for_lens(syn, yaw, pitch, 100.0, 80.0, 80, 64, 185.0)
+        arrays["syn%d_x" % n], arrays["syn%d_y" % n], arrays["syn%d_v" % n] = mx, my, valid
+    np.savez_compressed(HERE / "dualfisheye_maps.npz", **arrays)
+    (HERE / "dualfisheye.json").write_text(json.dumps(meta, indent=1, sort_keys=True) + "\n")
+
+
+def dump_cv2():
+    import cv2
+    rng = np.random.default_rng(20261017)
+    arrays = {}
+    h, w, n = 40, 56, 48
+    flags = {"nearest": cv2.INTER_NEAREST, "linear": cv2.INTER_LINEAR, "cubic": cv2.INTER_CUBIC}
+    mx = (rng.random((n, n)) * (w + 8) - 4).astype(np.float32)
+    my = (rng.random((n, n)) * (h + 8) - 4).astype(np.float32)
+    # exact bin centres / boundaries and integer positions too
+    mx[0, :] = np.arange(n, dtype=np.float32) + np.float32(1.0 / 64)
+    my[0, :] = 7.0
+    mx[1, :] = np.arange(n, dtype=np.float32)
+    my[1, :] = np.arange(n, dtype=np.float32) * np.float32(0.5) + np.float32(0.5)
+    arrays["map_x"], arrays["map_y"] = mx, my
+    for dt in ("uint8", "uint16", "float32"):
+        for ch in (1, 3):
+            if dt == "float32":
+                src = rng.random((h, w, ch), dtype=np.float32)
+            else:
+                src = rng.integers(0, np.iinfo(dt).max + 1, (h, w, ch)).astype(dt)
+            if ch == 1:
+                src = src[..., 0]
+            arrays["src_%s_c%d" % (dt, ch)] = src
+            for interp, flag in flags.items():
+                for bv in (0, 37):
+                    arrays["out_%s_c%d_%s_b%d" % (dt, ch, interp, bv)] = cv2.remap(
+                        src, mx, my, flag, borderMode=cv2.BORDER_CONSTANT, borderValue=(float(bv),) * 4)
+    arrays["cv2_version"] = np.array(cv2.__version__)
+    np.savez_compressed(HERE / "cv2_remap.npz", **arrays)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("reference", nargs="?", default="/root/reference")
+    ns = ap.parse_args()
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, str(pathlib.Path(ns.reference) / "cli_tools"))
+    import gs360_360PerspCut as pc
+    import gs360_DualFisheyeDistortionCalibration as df
+    dump_perspcut(pc)
+    dump_dualfisheye(df)
+    dump_cv2()
+    for p in sorted(HERE.glob("*.json")) + sorted(HERE.glob("*.npz")):
+        print("%9d  %s" % (p.stat().st_size, p.name))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,141 @@
+"""Float64 coordinate oracle (oracle/geometry.py) against reference-derived fixtures
+and against a literal scalar restatement of gs360_GUI.py:342-424."""
+
+import math
+
+import numpy as np
+import pytest
+
+from oracle import geometry as g
+
+
+# --- scalar restatement of the GUI functions (gs360_GUI.py:342-395, :419-424) -------------
+
+def _gui_lonlat(u, v, hfov, vfov, yaw, pitch):
+    x, y, z = math.tan(hfov / 2.0) * u, math.tan(vfov / 2.0) * (-v), 1.0
+    n = math.sqrt(x * x + y * y + z * z)
+    x, y, z = x / n, y / n, z / n
+    cp, sp = math.cos(pitch), math.sin(pitch)
+    x, y, z = x, cp * y + sp * z, -sp * y + cp * z
+    cy, sy = math.cos(yaw), math.sin(yaw)
+    x, y, z = cy * x + sy * z, y, -sy * x + cy * z
+    return math.atan2(x, z), math.asin(max(-1.0, min(1.0, y)))
+
+
+@pytest.mark.parametrize("yaw,pitch", [(0, 0), (45, 30), (180, 0), (-135, -30), (0, 90), (0, -90), (179.9, 60)])
+def test_erp_map_matches_gui_scalar_math(yaw, pitch):
+    W, H, w, h, fov = 7680, 3840, 64, 48, 104.2500326978036
+    vf = 90.0
+    mx, my = g.erp_map64(W, H, w, h, yaw, pitch, fov, vf, "halfpixel")
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        i, j = int(rng.integers(0, w)), int(rng.integers(0, h))
+        u, v = (i + 0.5) / w * 2 - 1, (j + 0.5) / h * 2 - 1
+        lon, lat = _gui_lonlat(u, v, math.radians(fov), math.radians(vf), math.radians(yaw), math.radians(pitch))
+        # gs360_GUI.py:419-424 is edge-origin; the halfpixel convention is that minus 0.5
+        ex = (lon / (2 * math.pi) + 0.5) * W - 0.5
+        ey = (0.5 - lat / math.pi) * H - 0.5
+        assert abs(mx[j, i] - ex) < 1e-8 and abs(my[j, i] - ey) < 1e-8
+
+
+def test_view_centre_lands_on_yaw_pitch():
+    W, H = 3840, 1920
+    for yaw, pitch in [(0, 0), (90, 0), (-45, 30), (135, -30)]:
+        mx, my = g.erp_map64(W, H, 2, 2, yaw, pitch, 1e-3, 1e-3)   # vanishing FOV -> centre ray
+        assert abs(mx.mean() - ((yaw / 360 + 0.5) * W - 0.5)) < 1e-3
+        assert abs(my.mean() - ((0.5 - pitch / 180) * H - 0.5)) < 1e-3
+
+
+def test_conventions_differ_by_at_most_half_a_pixel():
+    a = g.erp_map64(7680, 3840, 40, 40, 30, 10, 100, 100, "halfpixel")
+    b = g.erp_map64(7680, 3840, 40, 40, 30, 10, 100, 100, "v360")
+    assert np.abs(a[0] - b[0]).max() <= 0.5 + 1e-9 and np.abs(a[1] - b[1]).max() <= 0.5 + 1e-9
+    with pytest.raises(ValueError):
+        g.erp_map64(8, 4, 2, 2, 0, 0, 90, 90, "nope")
+
+
+def test_seam_and_pole_ranges():
+    W, H = 7680, 3840
+    mx, my = g.erp_map64(W, H, 200, 200, 180.0, 0.0, 112.6, 112.6)
+    assert mx.min() >= -0.5 and mx.max() < W - 0.5
+    assert (mx[:, :100] > W / 2).all() and (mx[:, 100:] < W / 2).all()      # seam splits the view
+    mx, my = g.erp_map64(W, H, 200, 200, 0.0, 90.0, 112.6, 112.6)
+    assert my.min() >= -0.5 and my.min() < 20                               # reaches the pole rows
+    mx, my = g.erp_map64(W, H, 200, 200, 0.0, -90.0, 112.6, 112.6)
+    assert my.max() <= H - 0.5 and my.max() > H - 20
+
+
+def test_rotation_describes_the_camera_the_pose_exporter_writes():
+    """cli_tools/gs360_MS360xmlToPersCams.py:292-353: R_gl = Ry(-yaw) . Rx(pitch) in GL axes
+    (x right, y up, z backwards).  Flipping z on both sides gives the y-up / z-forward
+    rotation the remap uses."""
+    def rot_x(d):
+        c, s = math.cos(math.radians(d)), math.sin(math.radians(d))
+        return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+
+    def rot_y(d):
+        c, s = math.cos(math.radians(d)), math.sin(math.radians(d))
+        return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+    flip = np.diag([1.0, 1.0, -1.0])
+    for yaw, pitch in [(0, 0), (45, 30), (-135, -30), (180, 0), (10, 90)]:
+        r_gl = rot_y(-yaw) @ rot_x(pitch)
+        assert np.allclose(flip @ r_gl @ flip, g.view_rotation(yaw, pitch), atol=1e-12)
+
+
+def test_roll_is_a_rotation_about_the_view_axis():
+    r = g.view_rotation(20, 10, 33)
+    assert np.allclose(r @ r.T, np.eye(3), atol=1e-12)
+    assert np.allclose(r[:, 2], g.view_rotation(20, 10, 0)[:, 2], atol=1e-12)
+    a = g.camera_rays(8, 8, 90, 90, 20, 10, 33)
+    b = (g.camera_rays(8, 8, 90, 90, 0, 0, 0) @ r.T)
+    assert np.allclose(a, b, atol=1e-12)
+
+
+# --- dual fisheye against maps produced by the reference ----------------------------------
+
+def test_fisheye_maps_match_reference_float32_maps(golden_df, golden_df_maps):
+    calib = golden_df["sensors"]["0"]
+    worst_valid = 0.0
+    for spec in golden_df["sfm10_default"]:
+        for lens_key, lens_yaw in (("X", 0.0), ("Y", 180.0)):
+            yaw_rel = g.wrap_angle_deg(spec["yaw_deg"] - lens_yaw)
+            mx, my, valid = g.fisheye_map64(calib, yaw_rel, spec["pitch_deg"], spec["hfov_deg"],
+                                            spec["vfov_deg"], 96, 96, 190.0)
+            key = "m96_%s_%s" % (spec["view_id"], lens_key)
+            assert np.array_equal(valid, golden_df_maps[key + "_v"])
+            ref_x, ref_y = golden_df_maps[key + "_x"], golden_df_maps[key + "_y"]
+            # the reference computes in float32 (arccos near the axis costs it ~1e-2 px)
+            assert np.abs(mx - ref_x).max() < 0.03 and np.abs(my - ref_y).max() < 0.03
+            if valid.any():
+                worst_valid = max(worst_valid, np.abs(mx - ref_x)[valid].max(), np.abs(my - ref_y)[valid].max())
+    assert worst_valid < 0.01
+
+
+def test_lens_choice_and_full_size_samples(golden_df, golden_df_maps):
+    calib = golden_df["sensors"]["0"]
+    maps = g.dualfisheye_view_maps(calib, calib, golden_df["sfm10_default"])
+    info = golden_df["maps_1750"]
+    s = info["stride"]
+    for vid, m in maps.items():
+        assert m["lens_key"] == info["views"][vid]["lens_key"]
+        assert float(np.mean(m["valid"])) == info["views"][vid]["valid_ratio"] == 1.0
+        assert np.abs(m["map_x"][::s, ::s] - golden_df_maps["s1750_%s_x" % vid]).max() < 0.06
+        assert np.abs(m["map_y"][::s, ::s] - golden_df_maps["s1750_%s_y" % vid]).max() < 0.06
+        # ... and tight away from the optical axis, where float32 arccos is well conditioned
+        far = np.hypot(m["map_x"][::s, ::s] - 1920, m["map_y"][::s, ::s] - 1920) > 300
+        assert np.abs(m["map_x"][::s, ::s] - golden_df_maps["s1750_%s_x" % vid])[far].max() < 2e-3
+
+
+def test_every_distortion_term(golden_df, golden_df_maps):
+    calib = golden_df["synthetic_calibration"]
+    for n, (yaw, pitch) in enumerate(golden_df["synthetic_views"]):
+        mx, my, valid = g.fisheye_map64(calib, yaw, pitch, 100.0, 80.0, 80, 64, 185.0)
+        assert np.array_equal(valid, golden_df_maps["syn%d_v" % n])
+        assert np.abs(mx - golden_df_maps["syn%d_x" % n])[valid].max() < 6e-3
+        assert np.abs(my - golden_df_maps["syn%d_y" % n])[valid].max() < 6e-3
+
+
+def test_wrap_angle(golden_df):
+    for a, want in golden_df["wrap_angle_deg"]:
+        assert g.wrap_angle_deg(a) == want
