@@ -1,0 +1,175 @@
+// Shared device/host definitions of the remap360 kernels (sm_100a).
+//
+// Projection math follows gs360_GUI.py:342-424 (ERP) and
+// cli_tools/gs360_DualFisheyeDistortionCalibration.py:975-1005, :1759-1823 (equisolid + Brown);
+// sampling arithmetic is cv2.remap's (the call at DF:2001-2008), see weights.cpp.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "r360_tables.h"
+
+namespace r360 {
+
+constexpr int kMaxViewsPerLaunch = 16;
+constexpr int kMaxLenses = 4;
+
+enum Proj : int { kProjErp = 0, kProjFisheye = 1 };
+enum Interp : int { kNearest = 0, kLinear = 1, kCubic = 2 };
+
+// A view is a linear map from output pixel indices to an (unnormalised) world ray:
+//   d(i, j) = c0 + i * ci + j * cj
+// with d = R * (tan(hfov/2) * ((2i+1)/w - 1), -tan(vfov/2) * ((2j+1)/h - 1), 1).
+struct ViewDev {
+    double c0[3];
+    double ci[3];
+    double cj[3];
+    int32_t slot;
+    int32_t pad;
+};
+
+struct ErpDev {          // x = (lon/2pi + 0.5) * su + ou ;  y = (0.5 - lat/pi) * sv + ov
+    double su, ou, sv, ov;
+};
+
+struct LensDev {         // one fisheye calibration
+    double cx0, cy0;     // width/2 + cx, height/2 + cy
+    double f, b1, b2;
+    double k1, k2, k3, k4, p1, p2;
+    double xmax, ymax;   // width - 1, height - 1
+    double cos_theta_max;
+};
+
+struct ImageSetDev {
+    unsigned char* data;
+    long long pitch;
+    long long image_stride;
+    int width, height;
+};
+
+struct LaunchParams {
+    ImageSetDev src;
+    ImageSetDev dst;
+    int channels;
+    int n_views;          // views in this launch (<= kMaxViewsPerLaunch)
+    int view_base;        // index of views[0] within the call's view list
+    int n_views_total;    // dst images per source group
+    int n_lenses;         // source images per group
+    int n_groups;
+    int fill_invalid;
+    float border_value;
+    ErpDev erp;
+    LensDev lens[kMaxLenses];
+    ViewDev views[kMaxViewsPerLaunch];
+};
+
+struct CoordParams {
+    int out_w, out_h, n_views;
+    ErpDev erp;
+    LensDev lens[kMaxLenses];
+    ViewDev views[kMaxViewsPerLaunch];
+    float* x32; float* y32; double* x64; double* y64; unsigned char* valid;
+    long long view_base;
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void ray_at(const ViewDev& v, int i, int j, double& dx, double& dy, double& dz) {
+    const double fi = (double)i, fj = (double)j;
+    dx = fma(fi, v.ci[0], fma(fj, v.cj[0], v.c0[0]));
+    dy = fma(fi, v.ci[1], fma(fj, v.cj[1], v.c0[1]));
+    dz = fma(fi, v.ci[2], fma(fj, v.cj[2], v.c0[2]));
+}
+
+// Continuous (i, j) variant for the tile fitter.
+__device__ __forceinline__ void ray_at(const ViewDev& v, double fi, double fj, double& dx, double& dy, double& dz) {
+    dx = fma(fi, v.ci[0], fma(fj, v.cj[0], v.c0[0]));
+    dy = fma(fi, v.ci[1], fma(fj, v.cj[1], v.c0[1]));
+    dz = fma(fi, v.ci[2], fma(fj, v.cj[2], v.c0[2]));
+}
+
+// ERP: lon = atan2(x, z), lat = asin(y / |d|) written as atan2(y, hypot(x, z)).
+// Returns longitude / latitude in radians.
+__device__ __forceinline__ void erp_lonlat(double dx, double dy, double dz, double& lon, double& lat) {
+    lon = atan2(dx, dz);
+    lat = atan2(dy, sqrt(fma(dx, dx, dz * dz)));
+}
+
+__device__ __forceinline__ void erp_xy(const ErpDev& e, double lon, double lat, double& x, double& y) {
+    const double inv_2pi = 0.15915494309189533577;
+    const double inv_pi = 0.31830988618379067154;
+    x = fma(fma(lon, inv_2pi, 0.5), e.su, e.ou);
+    y = fma(fma(-lat, inv_pi, 0.5), e.sv, e.ov);
+}
+
+// Equisolid fisheye with Brown distortion.  With n = |d|:
+//   2 sin(theta/2) / rho = sqrt(2 / (n (n + dz)))   (theta from +z, rho = hypot(dx, dy) / n)
+// so no trigonometry is needed.  valid = theta <= theta_max and inside the sensor.
+__device__ __forceinline__ bool fisheye_xy(const LensDev& L, double dx, double dy, double dz,
+                                           double& x, double& y) {
+    const double n2 = fma(dx, dx, fma(dy, dy, dz * dz));
+    const double n = sqrt(n2);
+    const double den = n * (n + dz);
+    const double s = den > 1e-24 * n2 ? sqrt(2.0 / den) : 0.0;
+    const double xn = dx * s;
+    const double yn = -dy * s;
+    const double r2 = fma(xn, xn, yn * yn);
+    const double r4 = r2 * r2;
+    const double radial = 1.0 + L.k1 * r2 + L.k2 * r4 + L.k3 * (r4 * r2) + L.k4 * (r4 * r4);
+    double xd = xn * radial, yd = yn * radial;
+    if (L.p1 != 0.0 || L.p2 != 0.0) {
+        const double xy = xn * yn;
+        xd += L.p1 * (r2 + 2.0 * xn * xn) + 2.0 * L.p2 * xy;
+        yd += L.p2 * (r2 + 2.0 * yn * yn) + 2.0 * L.p1 * xy;
+    }
+    x = L.cx0 + xd * L.f + xd * L.b1 + yd * L.b2;
+    y = L.cy0 + yd * L.f;
+    const bool in_fov = dz >= L.cos_theta_max * n;
+    return in_fov && x >= 0.0 && x <= L.xmax && y >= 0.0 && y <= L.ymax;
+}
+
+// ---- element I/O -------------------------------------------------------------------------
+
+template <typename T> struct Elem;
+template <> struct Elem<uint8_t> {
+    static __device__ __forceinline__ float to_float(uint8_t v) { return (float)v; }
+};
+template <> struct Elem<uint16_t> {
+    static __device__ __forceinline__ float to_float(uint16_t v) { return (float)v; }
+};
+template <> struct Elem<__half> {
+    static __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+};
+template <> struct Elem<float> {
+    static __device__ __forceinline__ float to_float(float v) { return v; }
+};
+
+// float accumulator -> output element, cv2 saturate_cast semantics for integers
+template <typename TIn, typename TOut> struct Finish;
+template <> struct Finish<uint16_t, uint16_t> {
+    static __device__ __forceinline__ uint16_t run(float a) {
+        return (uint16_t)min(max(__float2int_rn(a), 0), 65535);
+    }
+};
+template <> struct Finish<uint16_t, __half> {
+    static __device__ __forceinline__ __half run(float a) {
+        return __float2half_rn(__fmul_rn(a, 1.0f / 65535.0f));
+    }
+};
+template <> struct Finish<__half, __half> {
+    static __device__ __forceinline__ __half run(float a) { return __float2half_rn(a); }
+};
+template <> struct Finish<float, float> {
+    static __device__ __forceinline__ float run(float a) { return a; }
+};
+template <> struct Finish<uint8_t, uint8_t> {
+    static __device__ __forceinline__ uint8_t run(float a) {
+        return (uint8_t)min(max(__float2int_rn(a), 0), 255);
+    }
+};
+
+#endif  // __CUDACC__
+
+}  // namespace r360

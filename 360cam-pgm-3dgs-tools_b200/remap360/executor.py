@@ -1,0 +1,190 @@
+"""Runs planner jobs on the GPU.
+
+A job is the ffmpeg-style argv that ``perspcut.build_view_jobs`` emits (and that the GUI may
+have edited, gs360_GUI.py:19092-19147).  The reference hands each argv to an ffmpeg process
+(gs360_360PerspCut.py:569-590); here the argv is parsed back into (source, view, output) and
+executed with the CUDA remap.  Jobs that share a source are grouped so the source is decoded and
+uploaded once."""
+
+from __future__ import annotations
+
+import pathlib
+import threading
+import traceback
+from collections import OrderedDict
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+
+
+@dataclass
+class ParsedJob:
+    source: pathlib.Path
+    output: pathlib.Path
+    projection: str            # "rectilinear" | "fisheye"
+    width: int
+    height: int
+    yaw: float
+    pitch: float
+    roll: float
+    hfov: float
+    vfov: float
+    interp: str
+    video: bool
+    fps: Optional[float]
+    start: Optional[float]
+    end: Optional[float]
+    jpeg_quality: int
+    pix_fmt: Optional[str]
+
+
+class JobError(RuntimeError):
+    pass
+
+
+def parse_job_argv(argv: Sequence[str]) -> ParsedJob:
+    """Recover the job from the argv of gs360_360PerspCut.py:286-414."""
+    argv = list(argv)
+
+    def opt(flag: str) -> Optional[str]:
+        return argv[argv.index(flag) + 1] if flag in argv and argv.index(flag) + 1 < len(argv) else None
+
+    source, vf = opt("-i"), opt("-vf")
+    if source is None or vf is None or len(argv) < 2:
+        raise JobError("not a view job: missing -i / -vf")
+    v360 = next((f for f in vf.split(",") if f.startswith("v360=")), None)
+    if v360 is None:
+        raise JobError("not a view job: no v360 filter in -vf")
+    kv = dict(item.split("=", 1) for item in v360[len("v360="):].split(":") if "=" in item)
+    if kv.get("input") != "equirect":
+        raise JobError("unsupported v360 input: %s" % kv.get("input"))
+    fps = next((float(f.split("=", 1)[1]) for f in vf.split(",") if f.startswith("fps=")), None)
+    q = opt("-q:v")
+    proj = kv.get("output", "rectilinear")
+    if proj == "fisheye":
+        hfov = vfov = float(kv["d_fov"])
+    else:
+        hfov, vfov = float(kv["h_fov"]), float(kv["v_fov"])
+    return ParsedJob(source=pathlib.Path(source), output=pathlib.Path(argv[-1]), projection=proj,
+                     width=int(kv["w"]), height=int(kv["h"]), yaw=float(kv.get("yaw", 0.0)),
+                     pitch=float(kv.get("pitch", 0.0)), roll=float(kv.get("roll", 0.0)), hfov=hfov, vfov=vfov,
+                     interp=kv.get("interp", "cubic"), video=fps is not None, fps=fps,
+                     start=float(opt("-ss")) if opt("-ss") else None, end=float(opt("-to")) if opt("-to") else None,
+                     jpeg_quality=95 if q == "2" else 100, pix_fmt=opt("-pix_fmt"))
+
+
+_INTERP = {"cubic": "cubic", "linear": "linear", "nearest": "nearest", "near": "nearest"}
+_gpu_lock = threading.Lock()
+
+
+def _write_image(path: pathlib.Path, image, jpeg_quality: int) -> None:
+    import cv2
+    path.parent.mkdir(parents=True, exist_ok=True)
+    params: List[int] = []
+    if path.suffix.lower() in (".jpg", ".jpeg"):
+        params = [int(cv2.IMWRITE_JPEG_QUALITY), int(jpeg_quality)]
+        if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):      # yuvj444p, as the reference asks of ffmpeg
+            params += [int(cv2.IMWRITE_JPEG_SAMPLING_FACTOR), int(cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444)]
+    if not cv2.imwrite(str(path), image, params):
+        raise JobError("failed to write %s" % path)
+
+
+def _run_still_group(source: pathlib.Path, jobs: List[ParsedJob], stop_event) -> List[Tuple[int, str]]:
+    """All views of one still image: one decode, one upload, one batched launch per output size."""
+    import cv2
+    import numpy as np
+    import torch
+    from . import api
+
+    image = cv2.imread(str(source), cv2.IMREAD_UNCHANGED)
+    if image is None:
+        return [(1, "failed to read %s" % source)] * len(jobs)
+    if image.ndim == 2:
+        image = image[..., None]
+    if image.dtype not in (np.uint8, np.uint16):
+        return [(1, "unsupported sample type %s in %s" % (image.dtype, source))] * len(jobs)
+    results: List[Optional[Tuple[int, str]]] = [None] * len(jobs)
+    buckets: Dict[Tuple[int, int, str], List[int]] = OrderedDict()
+    for k, job in enumerate(jobs):
+        if job.projection != "rectilinear":
+            results[k] = (1, "v360 output=%s is not available in the CUDA backend yet" % job.projection)
+            continue
+        if job.interp not in _INTERP:
+            results[k] = (1, "interp=%s is not available in the CUDA backend" % job.interp)
+            continue
+        buckets.setdefault((job.width, job.height, _INTERP[job.interp]), []).append(k)
+    host = np.ascontiguousarray(image)
+    for (w, h, interp), idxs in buckets.items():
+        if stop_event is not None and stop_event.is_set():
+            for k in idxs:
+                results[k] = (130, "")
+            continue
+        views = [api.PerspectiveView(jobs[k].yaw, jobs[k].pitch, jobs[k].hfov, jobs[k].vfov, roll_deg=jobs[k].roll)
+                 for k in idxs]
+        try:
+            with _gpu_lock:
+                if host.dtype == np.uint16:
+                    dev = torch.from_numpy(host.view(np.int16)).cuda().view(torch.uint16)
+                else:
+                    dev = torch.from_numpy(host).cuda()
+                out = api.remap_erp(dev[None], views, (w, h), interp=interp)[0]
+                if out.dtype == torch.uint16:
+                    out_host = out.view(torch.int16).cpu().numpy().view(np.uint16)
+                else:
+                    out_host = out.cpu().numpy()
+            for n, k in enumerate(idxs):
+                img = out_host[n]
+                _write_image(jobs[k].output, img[..., 0] if img.shape[2] == 1 else img, jobs[k].jpeg_quality)
+                results[k] = (0, "")
+        except Exception as exc:  # report per job, like a failing ffmpeg process would
+            text = "%s: %s" % (type(exc).__name__, exc)
+            for k in idxs:
+                if results[k] is None:
+                    results[k] = (1, text)
+    return [r if r is not None else (1, "job skipped") for r in results]
+
+
+def run_job_argv(cmd: Sequence[str], stop_event=None) -> Tuple[int, str]:
+    """One job (the ``run_one`` contract): returns (rc, stderr_text)."""
+    try:
+        job = parse_job_argv(cmd)
+    except Exception as exc:
+        return 1, str(exc)
+    if job.video:
+        from . import video
+        return video.run_video_jobs(job.source, [job], stop_event)[0]
+    return _run_still_group(job.source, [job], stop_event)[0]
+
+
+def run_jobs(jobs, stop_event=None, workers: int = 1) -> Iterator[Tuple[tuple, Tuple[int, str]]]:
+    """Run planner jobs grouped by source; yields (job, (rc, err)) for every job as groups finish."""
+    groups: "OrderedDict[str, List[int]]" = OrderedDict()
+    parsed: List[Optional[ParsedJob]] = []
+    early: Dict[int, Tuple[int, str]] = {}
+    for n, (cmd, _src, _dst) in enumerate(jobs):
+        try:
+            pj = parse_job_argv(cmd)
+            parsed.append(pj)
+            groups.setdefault(str(pj.source) + ("|video" if pj.video else ""), []).append(n)
+        except Exception as exc:
+            parsed.append(None)
+            early[n] = (1, str(exc))
+    for n, res in early.items():
+        yield jobs[n], res
+
+    def run_group(idxs: List[int]):
+        if stop_event is not None and stop_event.is_set():
+            return idxs, [(130, "")] * len(idxs)
+        pjs = [parsed[n] for n in idxs]
+        try:
+            if pjs[0].video:
+                from . import video
+                return idxs, video.run_video_jobs(pjs[0].source, pjs, stop_event)
+            return idxs, _run_still_group(pjs[0].source, pjs, stop_event)
+        except Exception:
+            return idxs, [(1, traceback.format_exc())] * len(idxs)
+
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+        for idxs, results in pool.map(run_group, list(groups.values())):
+            for n, res in zip(idxs, results):
+                yield jobs[n], res

@@ -1,0 +1,342 @@
+#!/usr/bin/env python3
+"""Throughput of the panorama -> perspective remap hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--interp cubic|linear] [--frames B] [--preset full360coverage]
+
+One step = one pass of the hot path over one batch of B synthetic 8K ERP frames: every frame is
+cut into the preset's views (full360coverage: 12 x 1600^2, 14 mm).  BASELINE.json's metric is
+output Mpix/s (and views/s) per GPU plus the fraction of the HBM roofline, next to the
+reference's CPU remap (cv2.remap, cli_tools/gs360_DualFisheyeDistortionCalibration.py:2001-2014)
+timed on this box's host cores.
+
+  value      kernel throughput with the frames already resident in HBM (CUDA events)
+  e2e        the same frames pushed through the public streaming API from pinned host memory,
+             H2D of every frame and D2H of every view inside the timed region
+  roofline   algorithmic bytes of the dominant kernel / its measured duration vs MEASURED_PEAKS
+  cpu_baseline  cv2.remap + prebuilt float32 maps on the host cores, bounded sample (rank 0, N=1)
+
+`--impl reference` times only that CPU arm and prints the same line with "impl": "reference".
+Multi-GPU (torchrun): frames are sharded across ranks, no data-path collective; weak scaling.
+"""
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "360cam-pgm-3dgs-tools_b200"))
+sys.path.insert(0, str(ROOT))
+
+ERP_W, ERP_H, CHANNELS = 7680, 3840, 3
+
+# Distinct source pixels touched by one frame's view set (U) -- computed by `python -m
+# oracle.footprint` with the float64 oracle maps; O = views * size^2.  Algorithmic bytes per
+# frame = (U + O) * channels * sizeof(u8)  (DESIGN.md section 5).
+FOOTPRINT_PX = {
+    ("full360coverage", "linear"): 24_335_997,
+    ("full360coverage", "cubic"): 26_463_848,
+    ("fisheyelike", "linear"): 19_305_992,
+    ("fisheyelike", "cubic"): 19_998_440,
+    ("default", "linear"): 18_073_800,
+    ("default", "cubic"): 18_250_224,
+}
+
+
+def preset_views(preset, size):
+    """(views, hfov) of a gs360_360PerspCut preset through the drop-in planner."""
+    from remap360 import perspcut
+    ap = perspcut.create_arg_parser()
+    args = ap.parse_args(["-i", "/nonexistent", "--preset", preset, "--size", str(size)])
+    args.size_explicit = False if size == 1600 else True
+    args.input_is_video = False
+    res = perspcut.build_view_jobs(args, [pathlib.Path("/nonexistent/frame.png")], pathlib.Path("/nonexistent/out"))
+    return [(v.view_id, v.yaw_deg, v.pitch_deg, v.hfov_deg, v.vfov_deg) for v in res.view_specs
+            if v.projection == "perspective"]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's remap (cv2.remap on prebuilt float32 maps, DF:2001-2014)
+# --------------------------------------------------------------------------------------------
+
+def cpu_reference_arm(views, size, interp, seconds_budget, steps=None, warmup=1):
+    """Returns (Mpix/s, info).  One CPU 'step' = ONE frame cut into all views (a bounded sample of
+    the GPU step, which is B such frames); maps are built once outside the timed region exactly
+    as the reference does (DF:1857-1907 builds maps once, DF:1996-2014 applies them per frame)."""
+    import cv2
+    import numpy as np
+    from oracle import geometry as geo
+    cores = os.cpu_count() or 1
+    cv2.setNumThreads(cores)
+    rng = np.random.default_rng(1234)
+    frame = rng.integers(0, 256, (ERP_H, ERP_W, CHANNELS), dtype=np.uint8)
+    pad = 4
+    padded = np.concatenate([frame[:, -pad:], frame, frame[:, :pad]], axis=1)
+    padded = np.ascontiguousarray(np.concatenate([padded[:1].repeat(pad, 0), padded, padded[-1:].repeat(pad, 0)], 0))
+    t0 = time.perf_counter()
+    maps = []
+    for _, yaw, pitch, hfov, vfov in views:
+        mx, my = geo.erp_map64(ERP_W, ERP_H, size, size, yaw, pitch, hfov, vfov)
+        maps.append(((mx + pad).astype(np.float32), (my + pad).astype(np.float32)))
+    map_build_s = time.perf_counter() - t0
+    flag = {"linear": cv2.INTER_LINEAR, "cubic": cv2.INTER_CUBIC, "nearest": cv2.INTER_NEAREST}[interp]
+
+    def one_frame():
+        for mx, my in maps:
+            cv2.remap(padded, mx, my, flag, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+
+    for _ in range(max(1, warmup)):
+        one_frame()
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t = time.perf_counter()
+        one_frame()
+        times.append(time.perf_counter() - t)
+        if steps is not None and len(times) >= steps:
+            break
+        if steps is None and (time.perf_counter() - t_start) > seconds_budget and len(times) >= 3:
+            break
+    pix = len(views) * size * size
+    mean_t = sum(times) / len(times)
+    info = {"cores": cv2.getNumThreads(), "host_cpus": cores, "frames_timed": len(times),
+            "s_per_frame": mean_t, "map_build_s_once": map_build_s, "cv2": cv2.__version__,
+            "cv2_threads": cv2.getNumThreads()}
+    return pix / mean_t / 1e6, info
+
+
+# --------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--interp", choices=["cubic", "linear"], default="cubic",
+                    help="cubic is the reference's hard-wired default (PC:730, DF:232)")
+    ap.add_argument("--preset", default="full360coverage")
+    ap.add_argument("--frames", type=int, default=16, help="8K frames per GPU per step")
+    ap.add_argument("--size", type=int, default=1600)
+    ap.add_argument("--path", default="auto")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ns = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if ns.warmup < 3 and ns.impl == "ours":
+        ns.warmup = 3
+    views = preset_views(ns.preset, ns.size)
+    n_views = len(views)
+    workload = "%dx%d u8x3 ERP x%d frames/GPU -> %s preset %d views %dx%d, %s" % (
+        ERP_W, ERP_H, ns.frames, ns.preset, n_views, ns.size, ns.size, ns.interp)
+    config = {"workload": workload, "preset": ns.preset, "views": n_views, "out_size": ns.size,
+              "interp": ns.interp, "frames_per_gpu_per_step": ns.frames, "convention": "halfpixel",
+              "content": "uniform noise (seeded)", "l2_policy": "inputs (1.4 GB/step) larger than L2"}
+
+    # ------------------------------------------------------------------ reference arm
+    if ns.impl == "reference":
+        if rank != 0:
+            return
+        value, info = cpu_reference_arm(views, ns.size, ns.interp, ns.cpu_seconds, steps=ns.steps, warmup=ns.warmup)
+        sample = "1 frame (all %d views) per step, cv2.remap %s on prebuilt float32 maps, %d cv2 threads" % (
+            n_views, ns.interp, info["cv2_threads"])
+        line = {"impl": "reference", "metric": "output Mpix/s", "value": value, "unit": "Mpix/s",
+                "n_gpus": ns.gpus, "steps": ns.steps, "warmup": ns.warmup, "ms_per_step": info["s_per_frame"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic", "config": config,
+                "views_per_s": value * 1e6 / (ns.size * ns.size),
+                "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": info["cores"], "kind": "reference",
+                                 "sample": sample, "detail": info},
+                "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import remap360
+    from remap360.stream import StreamingRemapper
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    pviews = [remap360.PerspectiveView(y, p, hf, vf, view_id=vid) for vid, y, p, hf, vf in views]
+    # frames are sharded by index: rank r owns global frames [r*B, (r+1)*B); seeded per frame
+    frames = torch.empty((ns.frames, ERP_H, ERP_W, CHANNELS), dtype=torch.uint8, device=dev)
+    for f in range(ns.frames):
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank * ns.frames + f)
+        frames[f] = torch.randint(0, 256, (ERP_H, ERP_W, CHANNELS), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty((ns.frames, n_views, ns.size, ns.size, CHANNELS), dtype=torch.uint8, device=dev)
+
+    def step():
+        remap360.remap_erp(frames, pviews, (ns.size, ns.size), interp=ns.interp, out=out, path=ns.path)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(ns.warmup):
+        step()
+    barrier()
+    launches0 = remap360.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(ns.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record()
+        for k in range(ns.steps):
+            step()
+            ev[k + 1].record()
+        barrier()
+    launches = remap360.launch_count() - launches0
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(ns.steps)]
+    total_ms = ev[0].elapsed_time(ev[ns.steps])
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / ns.steps
+    out_pix_step = ns.frames * n_views * ns.size * ns.size
+    value = out_pix_step * world / (ms_per_step * 1e-3) / 1e6          # Mpix/s, whole job
+
+    # roofline of the dominant kernel: one launch per step (<=16 views) -> launch time = step time
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    u_px = FOOTPRINT_PX.get((ns.preset, ns.interp))
+    launches_per_step = max(1, launches // ns.steps)
+    roofline = None
+    if u_px is not None and ns.size == 1600:
+        bytes_per_frame = (u_px + n_views * ns.size * ns.size) * CHANNELS
+        bytes_per_launch = bytes_per_frame * ns.frames / launches_per_step
+        kernel_ms = statistics.median(step_ms) / launches_per_step
+        achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "kernel_ms": kernel_ms, "launches_per_step": launches_per_step}
+
+    # ------------------------------------------------------------------ end to end (host buffers)
+    e2e = None
+    if not ns.no_e2e:
+        remapper = StreamingRemapper(pviews, (ns.size, ns.size), (ERP_H, ERP_W, CHANNELS), torch.uint8,
+                                     interp=ns.interp, device=dev, path=ns.path)
+        host_frames = [torch.empty((ERP_H, ERP_W, CHANNELS), dtype=torch.uint8).pin_memory() for _ in range(min(ns.frames, 4))]
+        for k, hf in enumerate(host_frames):
+            hf.copy_(frames[k].cpu())
+        e2e_steps = max(2, min(ns.steps, 5))
+
+        def e2e_step():
+            sink = 0
+            for f in range(ns.frames):
+                remapper.submit(host_frames[f % len(host_frames)])
+            for res in remapper.drain():
+                sink += int(res[0, 0, 0, 0])      # touch the host copy of every result
+            return sink
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": out_pix_step * world / e2e_s / 1e6, "unit": "Mpix/s",
+               "h2d_bytes_per_step": ns.frames * ERP_H * ERP_W * CHANNELS,
+               "d2h_bytes_per_step": out_pix_step * CHANNELS, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "api": "remap360.stream.StreamingRemapper (pinned ring, H2D / kernel / D2H on three streams)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not ns.no_cpu_baseline:
+        v, info = cpu_reference_arm(views, ns.size, ns.interp, ns.cpu_seconds)
+        cpu_baseline = {"value": v, "unit": "Mpix/s", "cores": info["cores"], "kind": "reference",
+                        "sample": "%d frames x %d views, cv2.remap %s (%s) on prebuilt float32 maps, %d threads of %d host CPUs"
+                                  % (info["frames_timed"], n_views, ns.interp, info["cv2"], info["cv2_threads"], info["host_cpus"]),
+                        "detail": info}
+
+    if rank == 0:
+        line = {"metric": "output Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": ns.steps,
+                "warmup": ns.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "views_per_s": value * 1e6 / (ns.size * ns.size), "frames_per_s": value * 1e6 / (n_views * ns.size * ns.size),
+                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

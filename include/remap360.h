@@ -1,0 +1,177 @@
+/*
+ * remap360 -- C ABI of the B200 panorama / dual-fisheye -> perspective remap library.
+ *
+ * The reference project (Mistral-Yu/360Cam-PGM-3DGS-Tools) has no FFI: its hot path is
+ * reached either by spawning `ffmpeg -vf v360=...` (cli_tools/gs360_360PerspCut.py:310-314,
+ * executed at :572) or by `cv2.remap` on NumPy maps
+ * (cli_tools/gs360_DualFisheyeDistortionCalibration.py:1759-1823 build, :2001-2014 apply).
+ * The entry points below are what a Python binding for those two call sites needs; each one
+ * names the reference code it stands in for.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer called "device" is CUDA device memory owned by the caller (e.g. a torch
+ *     tensor); the library never allocates, frees or retains caller memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
+ *     stream-ordered, no call synchronises the device;
+ *   - every function returns R360_OK (0) or a negative R360_E_* code and never throws;
+ *   - calls are re-entrant and thread-safe (the only global state is an immutable weight
+ *     table uploaded once per device under a lock).
+ *   - images are interleaved (HWC), 1..4 channels, rows `pitch_bytes` apart.
+ */
+#ifndef REMAP360_H
+#define REMAP360_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R360_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------- */
+enum {
+    R360_OK = 0,
+    R360_E_INVALID_ARG = -1,   /* null pointer, non-positive size, bad enum                */
+    R360_E_UNSUPPORTED = -2,   /* dtype / channel / interpolation combination not built    */
+    R360_E_CUDA = -3,          /* a CUDA runtime call failed; see r360_last_cuda_error()   */
+    R360_E_NO_DEVICE = -4,     /* no CUDA device / wrong architecture (needs sm_100)       */
+    R360_E_TOO_MANY = -5       /* more than R360_MAX_LENSES source slots                   */
+};
+
+/* ---- enums --------------------------------------------------------------------------- */
+enum { R360_U8 = 0, R360_U16 = 1, R360_F16 = 2, R360_F32 = 3 };
+
+/* cv2 names at gs360_DualFisheyeDistortionCalibration.py:59-64; ffmpeg `interp=` at
+ * gs360_360PerspCut.py:107-109.  Arithmetic is cv2.remap's (1/32-px fractions, A = -0.75). */
+enum { R360_NEAREST = 0, R360_LINEAR = 1, R360_CUBIC = 2 };
+
+/* ERP pixel convention: HALFPIXEL x = (lon/2pi+.5)*W - .5 (in-repo
+ * geometry, gs360_GUI.py:419-424 with pixel centres); V360 x = (lon/2pi+.5)*(W-1) (the
+ * replaced ffmpeg filter). */
+enum { R360_CONV_HALFPIXEL = 0, R360_CONV_V360 = 1 };
+
+/* which device code path to use; AUTO picks TILED when the layout allows it */
+enum { R360_PATH_AUTO = 0, R360_PATH_DIRECT = 1, R360_PATH_TILED = 2 };
+
+#define R360_MAX_LENSES 4
+
+/* ---- plain-data descriptors ------------------------------------------------------------ */
+
+/* A batch of equally sized interleaved images in device memory. */
+typedef struct r360_images {
+    void*   data;            /* device pointer to image 0                                   */
+    int32_t width;           /* pixels                                                      */
+    int32_t height;
+    int32_t channels;        /* 1..4                                                        */
+    int32_t dtype;           /* R360_U8 ...                                                 */
+    int64_t pitch_bytes;     /* row stride                                                  */
+    int64_t image_stride_bytes; /* distance between consecutive images of the batch         */
+    int32_t count;           /* number of images                                            */
+    int32_t reserved;
+} r360_images;
+
+/* One perspective (rectilinear) view.  Replaces the `w:h:yaw:pitch:roll:h_fov:v_fov` options
+ * of the v360 filter string (gs360_360PerspCut.py:310-314) and one entry of
+ * build_sfm10_specs (gs360_DualFisheyeDistortionCalibration.py:1258-1307).
+ * Rotation order and signs: gs360_GUI.py:351-374 (pitch about X, then yaw about Y; +yaw looks
+ * right, +pitch looks up); roll is about the view axis.  All views of one call share the
+ * output size of `dst`. */
+typedef struct r360_view {
+    double  yaw_deg;
+    double  pitch_deg;
+    double  roll_deg;
+    double  hfov_deg;
+    double  vfov_deg;
+    int32_t src_slot;        /* which image of a source group feeds this view (ERP: 0;
+                                dual fisheye: 0 = X lens, 1 = Y lens)                        */
+    int32_t reserved;
+} r360_view;
+
+/* Metashape equisolid-fisheye calibration, the fields of SensorCalibration
+ * (gs360_DualFisheyeDistortionCalibration.py:67-85) that the projection uses. */
+typedef struct r360_fisheye_calib {
+    double width, height;    /* sensor resolution the calibration refers to                 */
+    double f, cx, cy;
+    double k1, k2, k3, k4;
+    double p1, p2;
+    double b1, b2;
+    double lens_fov_deg;     /* usable lens FOV (DF --lens-fov-deg, default 190)            */
+} r360_fisheye_calib;
+
+typedef struct r360_options {
+    int32_t interp;          /* R360_NEAREST / LINEAR / CUBIC                               */
+    int32_t convention;      /* ERP only: R360_CONV_*                                       */
+    int32_t path;            /* R360_PATH_*                                                 */
+    int32_t fill_invalid;    /* fisheye only: 1 = write border_value where the ray is outside
+                                the lens model or the sensor (DF:2009-2014)                 */
+    double  border_value;    /* fisheye only: per-tap constant border (cv2 BORDER_CONSTANT) */
+    int32_t out_dtype;       /* -1 = same as source; R360_F16 with a U16 source writes
+                                value/65535 as half                                         */
+    int32_t reserved;
+} r360_options;
+
+/* ---- entry points --------------------------------------------------------------------------- */
+
+int         r360_abi_version(void);
+const char* r360_error_string(int code);
+const char* r360_last_cuda_error(void);   /* thread-local text of the last CUDA failure       */
+void        r360_default_options(r360_options* opt);
+
+/* Number of SMs of the current device and whether the library's kernels can run on it. */
+int r360_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * Panorama -> perspective views.  Replaces one `ffmpeg -vf v360=input=equirect:
+ * output=rectilinear...` process per (source, view) (gs360_360PerspCut.py:286-349, :569-590).
+ *
+ *   src   `count` ERP frames;
+ *   dst   src->count * n_views images, frame-major: image (f * n_views + v) is view v of
+ *         frame f; dst->count must equal that product;
+ *   x taps wrap at the seam, y taps clamp at the poles.
+ */
+int r360_remap_erp(const r360_images* src, const r360_images* dst,
+                   const r360_view* views, int32_t n_views,
+                   const r360_options* opt, void* stream);
+
+/*
+ * Dual (or n-) fisheye -> perspective views.  Replaces map build + cv2.remap + mask fill
+ * (gs360_DualFisheyeDistortionCalibration.py:1759-1823, :2001-2014; masks :2031-2043 with
+ * interp = NEAREST and border_value = 0).
+ *
+ *   src      groups of `n_lenses` images: image (g * n_lenses + slot); src->count must be a
+ *            multiple of n_lenses;
+ *   calib    one calibration per slot;
+ *   views    yaw is RELATIVE to the lens of views[v].src_slot (DF:1883);
+ *   dst      (src->count / n_lenses) * n_views images, group-major.
+ */
+int r360_remap_fisheye(const r360_images* src, const r360_images* dst,
+                       const r360_fisheye_calib* calib, int32_t n_lenses,
+                       const r360_view* views, int32_t n_views,
+                       const r360_options* opt, void* stream);
+
+/*
+ * Test/debug: the source coordinates the kernels sample at, without sampling.  Writes, for
+ * view v and output pixel (j, i), element [(v * out_h + j) * out_w + i] of each non-null
+ * device array:
+ *   map_x32 / map_y32   float   the value handed to the 1/32-px quantiser (what cv2.remap
+ *                               would receive as its map);
+ *   map_x64 / map_y64   double  the same coordinate before the float32 rounding;
+ *   valid               uint8   fisheye only: inside lens FOV and sensor bounds.
+ * `calib == NULL` selects the ERP projection of a src_w x src_h panorama.
+ */
+int r360_coords(int32_t src_w, int32_t src_h,
+                const r360_fisheye_calib* calib, int32_t n_lenses,
+                const r360_view* views, int32_t n_views,
+                int32_t out_w, int32_t out_h, const r360_options* opt,
+                float* map_x32, float* map_y32, double* map_x64, double* map_y64,
+                uint8_t* valid, void* stream);
+
+/* Count of kernels this library has launched in the calling process (all threads). */
+int64_t r360_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REMAP360_H */
