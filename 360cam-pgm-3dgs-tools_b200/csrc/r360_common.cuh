@@ -76,14 +76,7 @@ struct CoordParams {
 
 #ifdef __CUDACC__
 
-__device__ __forceinline__ void ray_at(const ViewDev& v, int i, int j, double& dx, double& dy, double& dz) {
-    const double fi = (double)i, fj = (double)j;
-    dx = fma(fi, v.ci[0], fma(fj, v.cj[0], v.c0[0]));
-    dy = fma(fi, v.ci[1], fma(fj, v.cj[1], v.c0[1]));
-    dz = fma(fi, v.ci[2], fma(fj, v.cj[2], v.c0[2]));
-}
-
-// Continuous (i, j) variant for the tile fitter.
+// (fi, fj) may be fractional: the tile fitter samples between pixel centres.
 __device__ __forceinline__ void ray_at(const ViewDev& v, double fi, double fj, double& dx, double& dy, double& dz) {
     dx = fma(fi, v.ci[0], fma(fj, v.cj[0], v.c0[0]));
     dy = fma(fi, v.ci[1], fma(fj, v.cj[1], v.c0[1]));

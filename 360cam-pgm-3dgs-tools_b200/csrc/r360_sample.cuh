@@ -1,0 +1,195 @@
+// Per-pixel sampling with cv2.remap's arithmetic (the call the reference makes at
+// cli_tools/gs360_DualFisheyeDistortionCalibration.py:2001-2008), parameterised on where the
+// taps come from (global memory with border rules, or a staged shared-memory patch).
+//
+//   float32 map value -> s = rint(m * 32); integer part s >> 5 (saturated to int16), fraction s & 31
+//   uint8 : 15-bit fixed-point 2-D weights, (sum + 16384) >> 15, saturate
+//   others: float32 weights wy[k]*wx[k], products and sums rounded one by one in cv2's order
+#pragma once
+
+#include <type_traits>
+
+#include "r360_common.cuh"
+
+namespace r360 {
+
+__device__ WeightTables g_tables;
+
+__device__ __forceinline__ int sat_short(int v) { return min(max(v, -32768), 32767); }
+
+// ---- tap sources -------------------------------------------------------------------------------
+
+// Global memory, panorama border: columns wrap at the seam, rows clamp at the poles.
+template <typename TIn>
+struct ErpGlobalTaps {
+    const unsigned char* img; long long pitch; int w, h, channels;
+    static constexpr bool kConstantBorder = false;
+    __device__ __forceinline__ bool exists(int, int) const { return true; }
+    __device__ __forceinline__ void load(int x, int y, float* out) const {
+        x = x % w;
+        if (x < 0) x += w;
+        y = min(max(y, 0), h - 1);
+        const TIn* p = reinterpret_cast<const TIn*>(img + (long long)y * pitch) + (long long)x * channels;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < channels) out[c] = Elem<TIn>::to_float(__ldg(p + c));
+    }
+};
+
+// Global memory, cv2 BORDER_CONSTANT applied tap by tap.
+template <typename TIn>
+struct ConstBorderGlobalTaps {
+    const unsigned char* img; long long pitch; int w, h, channels; float border;
+    static constexpr bool kConstantBorder = true;
+    __device__ __forceinline__ bool exists(int x, int y) const {
+        return (unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h;
+    }
+    __device__ __forceinline__ void load(int x, int y, float* out) const {
+        if (exists(x, y)) {
+            const TIn* p = reinterpret_cast<const TIn*>(img + (long long)y * pitch) + (long long)x * channels;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < channels) out[c] = Elem<TIn>::to_float(__ldg(p + c));
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out[c] = border;
+        }
+    }
+};
+
+// A staged patch in shared memory that already contains every tap (seam unwrapped, pole rows
+// replicated): no border logic at all.  (x, y) are source pixel indices; x may be unwrapped.
+template <typename TIn>
+struct PatchTaps {
+    const unsigned char* base;   // address of byte column xb0 of source row y0
+    int pitch;                   // bytes between patch rows
+    int xb0;                     // unwrapped source byte column of patch byte 0
+    int y0;                      // source row (unclamped index) of patch row 0
+    int channels;
+    static constexpr bool kConstantBorder = false;
+    __device__ __forceinline__ bool exists(int, int) const { return true; }
+    __device__ __forceinline__ void load(int x, int y, float* out) const {
+        const TIn* p = reinterpret_cast<const TIn*>(base + (y - y0) * pitch + (x * channels * (int)sizeof(TIn) - xb0));
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < channels) out[c] = Elem<TIn>::to_float(p[c]);
+    }
+};
+
+// ---- the sampler ---------------------------------------------------------------------------------
+
+template <int INTERP, typename TIn, typename TOut, typename Taps>
+__device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int src_w, int src_h, float border,
+                                             float x32, float y32, TOut* dst) {
+    if constexpr (INTERP == kNearest) {
+        float v[4];
+        taps.load(sat_short(__float2int_rn(x32)), sat_short(__float2int_rn(y32)), v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (c < channels) dst[c] = Finish<TIn, TOut>::run(v[c]);   // exact: every element fits a float
+        return;
+    } else {
+        const int sx = __float2int_rn(x32 * 32.0f);
+        const int sy = __float2int_rn(y32 * 32.0f);
+        const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
+        const int fx = sx & 31, fy = sy & 31;
+        float t[4];
+
+        if constexpr (std::is_same<TIn, uint8_t>::value) {
+            int acc[4] = {0, 0, 0, 0};
+            if constexpr (INTERP == kLinear) {
+                // (32-fx)(32-fy) ... in units of 1/1024: cv2's 15-bit table divided by 32, exactly
+                const int wx[2] = {32 - fx, fx}, wy[2] = {32 - fy, fy};
+#pragma unroll
+                for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 2; ++kx) {
+                        taps.load(ix + kx, iy + ky, t);
+                        const int wgt = wx[kx] * wy[ky];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[c] += wgt * (int)t[c];
+                    }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < channels) dst[c] = Finish<uint8_t, TOut>::run((float)((acc[c] + 512) >> 10));
+            } else {
+                const short* wt = g_tables.cubic_fixed + (fy * 32 + fx) * 16;
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 4; ++kx) {
+                        taps.load(ix - 1 + kx, iy - 1 + ky, t);
+                        const int wgt = wt[ky * 4 + kx];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[c] += wgt * (int)t[c];
+                    }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < channels) dst[c] = Finish<uint8_t, TOut>::run((float)min(max((acc[c] + 16384) >> 15, 0), 255));
+            }
+        } else {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if constexpr (INTERP == kLinear) {
+                const float tx = (float)fx * (1.0f / 32.0f), ty = (float)fy * (1.0f / 32.0f);
+                const float wx[2] = {1.0f - tx, tx}, wy[2] = {1.0f - ty, ty};
+#pragma unroll
+                for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 2; ++kx) {
+                        taps.load(ix + kx, iy + ky, t);
+                        const float wgt = __fmul_rn(wy[ky], wx[kx]);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float term = __fmul_rn(t[c], wgt);
+                            acc[c] = (ky == 0 && kx == 0) ? term : __fadd_rn(acc[c], term);
+                        }
+                    }
+            } else {
+                const float* wx = g_tables.cubic_1d + 4 * fx;
+                const float* wy = g_tables.cubic_1d + 4 * fy;
+                const int x0 = ix - 1, y0 = iy - 1;
+                bool interior = true;
+                if constexpr (Taps::kConstantBorder)
+                    interior = x0 >= 0 && x0 < max(src_w - 3, 0) && y0 >= 0 && y0 < max(src_h - 3, 0);
+                if (interior) {
+                    // each row summed left to right, rows added to a running sum that starts at zero
+#pragma unroll
+                    for (int ky = 0; ky < 4; ++ky) {
+                        float row[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int kx = 0; kx < 4; ++kx) {
+                            taps.load(x0 + kx, y0 + ky, t);
+                            const float wgt = __fmul_rn(wy[ky], wx[kx]);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float term = __fmul_rn(t[c], wgt);
+                                row[c] = kx == 0 ? term : __fadd_rn(row[c], term);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[c] = __fadd_rn(acc[c], row[c]);
+                    }
+                } else {
+                    // near the sensor edge cv2 starts from the border value and adds
+                    // (tap - border) * w for the taps that exist
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[c] = border;
+                    for (int ky = 0; ky < 4; ++ky)
+                        for (int kx = 0; kx < 4; ++kx) {
+                            if (!taps.exists(x0 + kx, y0 + ky)) continue;
+                            taps.load(x0 + kx, y0 + ky, t);
+                            const float wgt = __fmul_rn(wy[ky], wx[kx]);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                acc[c] = __fadd_rn(acc[c], __fmul_rn(__fsub_rn(t[c], border), wgt));
+                        }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < channels) dst[c] = Finish<TIn, TOut>::run(acc[c]);
+        }
+    }
+}
+
+}  // namespace r360

@@ -11,6 +11,7 @@
 
 #include "r360_common.cuh"
 #include "r360_direct.cuh"
+#include "r360_tiled.cuh"
 
 using namespace r360;
 
@@ -34,6 +35,37 @@ int cuda_fail(cudaError_t e, const char* what) {
 std::mutex g_init_mutex;
 bool g_device_ready[64] = {};
 
+// Chebyshev nodes, the inverse monomial Vandermonde matrix at those nodes (Gauss-Jordan in long
+// double) and the check points of the tile fitter (r360_tiled.cuh).
+void make_fit_constants(FitConstants* f) {
+    const int n = kFitN;
+    long double v[kFitN][2 * kFitN];
+    for (int k = 0; k < n; ++k) {
+        const long double t = cosl(M_PIl * (k + 0.5L) / n);
+        f->node[k] = (double)t;
+        long double pw = 1.0L;
+        for (int m = 0; m < n; ++m) { v[k][m] = pw; pw *= t; }
+        for (int m = 0; m < n; ++m) v[k][n + m] = (k == m) ? 1.0L : 0.0L;
+    }
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r) if (fabsl(v[r][c]) > fabsl(v[piv][c])) piv = r;
+        for (int m = 0; m < 2 * n; ++m) { const long double tmp = v[c][m]; v[c][m] = v[piv][m]; v[piv][m] = tmp; }
+        const long double d = v[c][c];
+        for (int m = 0; m < 2 * n; ++m) v[c][m] /= d;
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const long double fct = v[r][c];
+            for (int m = 0; m < 2 * n; ++m) v[r][m] -= fct * v[c][m];
+        }
+    }
+    for (int m = 0; m < n; ++m)
+        for (int k = 0; k < n; ++k) f->minv[m * n + k] = (double)v[m][n + k];
+    const double cp[kFitChecks][2] = {{-1, -1}, {1, -1}, {-1, 1}, {1, 1}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {0, 0},
+                                      {-.5, -.5}, {.5, -.5}, {-.5, .5}, {.5, .5}};
+    for (int q = 0; q < kFitChecks; ++q) { f->check[q][0] = cp[q][0]; f->check[q][1] = cp[q][1]; }
+}
+
 int ensure_device_ready() {
     int dev = 0;
     R360_CUDA(cudaGetDevice(&dev));
@@ -54,6 +86,9 @@ int ensure_device_ready() {
         built = true;
     }
     R360_CUDA(cudaMemcpyToSymbol(g_tables, &host_tables, sizeof(WeightTables)));
+    static FitConstants fit;
+    make_fit_constants(&fit);
+    R360_CUDA(cudaMemcpyToSymbol(c_fit, &fit, sizeof(FitConstants)));
     g_device_ready[dev] = true;
     return R360_OK;
 }
@@ -163,23 +198,67 @@ int launch_direct(const LaunchParams& p, cudaStream_t stream) {
     return R360_OK;
 }
 
+// Shared memory per block for the tiled kernel: aim for 4 resident blocks per SM.
+constexpr int kSmemPerBlockTarget = 56 * 1024 - 1024;
+constexpr int kTiledFixedSmem = 2048;
+
+template <int PROJ, int INTERP, typename TIn, typename TOut>
+int launch_tiled(const LaunchParams& p, cudaStream_t stream, const CoordParams* dbg = nullptr) {
+    TiledParams T;
+    std::memset(&T, 0, sizeof(T));
+    T.lp = p;
+    T.tiles_x = (p.dst.width + kTile - 1) / kTile;
+    T.tiles_y = (p.dst.height + kTile - 1) / kTile;
+    T.out_stage_bytes = kTile * kTile * p.channels * (int)sizeof(TOut);
+    const int stage = (T.out_stage_bytes + 127) & ~127;
+    T.patch_budget = kSmemPerBlockTarget - kTiledFixedSmem - stage;
+    if (T.patch_budget < 8192) T.patch_budget = 8192;
+    const int smem = kTiledFixedSmem + stage + T.patch_budget;
+    auto aligned16 = [](const ImageSetDev& im) {
+        return (reinterpret_cast<uintptr_t>(im.data) % 16 == 0) && im.pitch % 16 == 0 && im.image_stride % 16 == 0;
+    };
+    T.bulk_load_ok = aligned16(p.src) && ((long long)p.src.width * p.channels * sizeof(TIn)) % 16 == 0;
+    T.bulk_store_ok = aligned16(p.dst);
+    if (dbg) { T.dbg_x32 = dbg->x32; T.dbg_y32 = dbg->y32; T.dbg_x64 = dbg->x64; T.dbg_y64 = dbg->y64; T.dbg_valid = dbg->valid; }
+    auto kernel = remap_tiled_kernel<PROJ, INTERP, TIn, TOut>;
+    static thread_local const void* configured = nullptr;   // per instantiation (static in a template)
+    if (configured != (const void*)kernel) {
+        R360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = (const void*)kernel;
+    }
+    const int n_tiles = T.tiles_x * T.tiles_y;
+    const int max_groups = 65535 / p.n_views;
+    for (int g0 = 0; g0 < p.n_groups; g0 += max_groups) {
+        TiledParams Q = T;
+        const int ng = p.n_groups - g0 < max_groups ? p.n_groups - g0 : max_groups;
+        Q.lp.src.data += (long long)g0 * p.n_lenses * p.src.image_stride;
+        Q.lp.dst.data += (long long)g0 * p.n_views_total * p.dst.image_stride;
+        Q.lp.n_groups = ng;
+        dim3 grid(n_tiles, ng * p.n_views, 1);
+        kernel<<<grid, 256, smem, stream>>>(Q);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        R360_CUDA(cudaGetLastError());
+    }
+    return R360_OK;
+}
+
 template <int PROJ, typename TIn, typename TOut>
-int dispatch_interp(const LaunchParams& p, int interp, cudaStream_t s) {
+int dispatch_interp(const LaunchParams& p, int interp, bool tiled, cudaStream_t s) {
     switch (interp) {
-        case R360_NEAREST: return launch_direct<PROJ, kNearest, TIn, TOut>(p, s);
-        case R360_LINEAR: return launch_direct<PROJ, kLinear, TIn, TOut>(p, s);
-        case R360_CUBIC: return launch_direct<PROJ, kCubic, TIn, TOut>(p, s);
+        case R360_NEAREST: return tiled ? launch_tiled<PROJ, kNearest, TIn, TOut>(p, s) : launch_direct<PROJ, kNearest, TIn, TOut>(p, s);
+        case R360_LINEAR: return tiled ? launch_tiled<PROJ, kLinear, TIn, TOut>(p, s) : launch_direct<PROJ, kLinear, TIn, TOut>(p, s);
+        case R360_CUBIC: return tiled ? launch_tiled<PROJ, kCubic, TIn, TOut>(p, s) : launch_direct<PROJ, kCubic, TIn, TOut>(p, s);
         default: return R360_E_INVALID_ARG;
     }
 }
 
 template <int PROJ>
-int dispatch_types(const LaunchParams& p, int in_dt, int out_dt, int interp, cudaStream_t s) {
-    if (in_dt == R360_U8 && out_dt == R360_U8) return dispatch_interp<PROJ, uint8_t, uint8_t>(p, interp, s);
-    if (in_dt == R360_U16 && out_dt == R360_U16) return dispatch_interp<PROJ, uint16_t, uint16_t>(p, interp, s);
-    if (in_dt == R360_U16 && out_dt == R360_F16) return dispatch_interp<PROJ, uint16_t, __half>(p, interp, s);
-    if (in_dt == R360_F16 && out_dt == R360_F16) return dispatch_interp<PROJ, __half, __half>(p, interp, s);
-    if (in_dt == R360_F32 && out_dt == R360_F32) return dispatch_interp<PROJ, float, float>(p, interp, s);
+int dispatch_types(const LaunchParams& p, int in_dt, int out_dt, int interp, bool tiled, cudaStream_t s) {
+    if (in_dt == R360_U8 && out_dt == R360_U8) return dispatch_interp<PROJ, uint8_t, uint8_t>(p, interp, tiled, s);
+    if (in_dt == R360_U16 && out_dt == R360_U16) return dispatch_interp<PROJ, uint16_t, uint16_t>(p, interp, tiled, s);
+    if (in_dt == R360_U16 && out_dt == R360_F16) return dispatch_interp<PROJ, uint16_t, __half>(p, interp, tiled, s);
+    if (in_dt == R360_F16 && out_dt == R360_F16) return dispatch_interp<PROJ, __half, __half>(p, interp, tiled, s);
+    if (in_dt == R360_F32 && out_dt == R360_F32) return dispatch_interp<PROJ, float, float>(p, interp, tiled, s);
     return R360_E_UNSUPPORTED;
 }
 
@@ -229,8 +308,9 @@ int remap_common(int proj, const r360_images* src, const r360_images* dst,
         p.view_base = v0;
         p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
         for (int v = 0; v < p.n_views; ++v) make_view(views[v0 + v], dst->width, dst->height, &p.views[v]);
-        rc = proj == kProjErp ? dispatch_types<kProjErp>(p, src->dtype, out_dt, opt.interp, s)
-                              : dispatch_types<kProjFisheye>(p, src->dtype, out_dt, opt.interp, s);
+        const bool tiled = opt.path != R360_PATH_DIRECT;
+        rc = proj == kProjErp ? dispatch_types<kProjErp>(p, src->dtype, out_dt, opt.interp, tiled, s)
+                              : dispatch_types<kProjFisheye>(p, src->dtype, out_dt, opt.interp, tiled, s);
         if (rc != R360_OK) return rc;
     }
     return R360_OK;
@@ -312,10 +392,29 @@ int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, i
     for (int v = 0; v < n_views; ++v)
         if (calib && (views[v].src_slot < 0 || views[v].src_slot >= n_lenses)) return R360_E_INVALID_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (opt.path != R360_PATH_DIRECT && (!map_x32 || !map_y32 || !map_x64 || !map_y64)) return R360_E_INVALID_ARG;
     for (int v0 = 0; v0 < n_views; v0 += kMaxViewsPerLaunch) {
         p.view_base = v0;
         p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
         for (int v = 0; v < p.n_views; ++v) make_view(views[v0 + v], out_w, out_h, &p.views[v]);
+        if (opt.path != R360_PATH_DIRECT) {
+            // what the tiled kernels would sample for an 8-bit 3-channel source of this size
+            LaunchParams lp;
+            std::memset(&lp, 0, sizeof(lp));
+            lp.src.width = calib ? (int)calib[0].width : src_w;
+            lp.src.height = calib ? (int)calib[0].height : src_h;
+            lp.src.pitch = (long long)lp.src.width * 3;
+            lp.dst.width = out_w; lp.dst.height = out_h;
+            lp.channels = 3; lp.n_views = p.n_views; lp.view_base = v0; lp.n_views_total = n_views;
+            lp.n_lenses = calib ? n_lenses : 1; lp.n_groups = 1; lp.fill_invalid = opt.fill_invalid != 0;
+            lp.erp = p.erp;
+            std::memcpy(lp.lens, p.lens, sizeof(lp.lens));
+            std::memcpy(lp.views, p.views, sizeof(lp.views));
+            rc = proj == kProjErp ? launch_tiled<kProjErp, kLinear, uint8_t, uint8_t>(lp, s, &p)
+                                  : launch_tiled<kProjFisheye, kLinear, uint8_t, uint8_t>(lp, s, &p);
+            if (rc != R360_OK) return rc;
+            continue;
+        }
         dim3 grid((out_w + 31) / 32, (out_h + 7) / 8, p.n_views);
         coords_kernel<<<grid, 256, 0, s>>>(p, proj);
         g_launches.fetch_add(1, std::memory_order_relaxed);

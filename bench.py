@@ -296,9 +296,7 @@ def main():
 
         def e2e_step():
             sink = 0
-            for f in range(ns.frames):
-                remapper.submit(host_frames[f % len(host_frames)])
-            for res in remapper.drain():
+            for res in remapper.run(host_frames[f % len(host_frames)] for f in range(ns.frames)):
                 sink += int(res[0, 0, 0, 0])      # touch the host copy of every result
             return sink
 
