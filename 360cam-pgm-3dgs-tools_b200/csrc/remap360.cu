@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <new>
+#include <vector>
 
 #include "r360_common.cuh"
 #include "r360_direct.cuh"
@@ -178,6 +180,12 @@ int check_images(const r360_images* im) {
 
 // ---- dispatch ------------------------------------------------------------------------------------
 
+struct Prepared {          // everything the kernels need, derived from the ABI arguments
+    int proj, n_lenses, n_views, interp, in_dt, out_dt;
+    LaunchParams lp;       // views[] filled per launch chunk
+    r360_options opt;
+};
+
 template <int PROJ, int INTERP, typename TIn, typename TOut>
 int launch_direct(const LaunchParams& p, cudaStream_t stream) {
     dim3 block(256);
@@ -198,76 +206,53 @@ int launch_direct(const LaunchParams& p, cudaStream_t stream) {
     return R360_OK;
 }
 
-// Shared memory per block for the tiled kernel: aim for 4 resident blocks per SM.
-constexpr int kSmemPerBlockTarget = 56 * 1024 - 1024;
-constexpr int kTiledFixedSmem = 2048;
-
-template <int PROJ, int INTERP, typename TIn, typename TOut>
-int launch_tiled(const LaunchParams& p, cudaStream_t stream, const CoordParams* dbg = nullptr) {
-    TiledParams T;
-    std::memset(&T, 0, sizeof(T));
-    T.lp = p;
-    T.tiles_x = (p.dst.width + kTile - 1) / kTile;
-    T.tiles_y = (p.dst.height + kTile - 1) / kTile;
-    T.out_stage_bytes = kTile * kTile * p.channels * (int)sizeof(TOut);
-    const int stage = (T.out_stage_bytes + 127) & ~127;
-    T.patch_budget = kSmemPerBlockTarget - kTiledFixedSmem - stage;
-    if (T.patch_budget < 8192) T.patch_budget = 8192;
-    const int smem = kTiledFixedSmem + stage + T.patch_budget;
-    auto aligned16 = [](const ImageSetDev& im) {
-        return (reinterpret_cast<uintptr_t>(im.data) % 16 == 0) && im.pitch % 16 == 0 && im.image_stride % 16 == 0;
-    };
-    T.bulk_load_ok = aligned16(p.src) && ((long long)p.src.width * p.channels * sizeof(TIn)) % 16 == 0;
-    T.bulk_store_ok = aligned16(p.dst);
-    if (dbg) { T.dbg_x32 = dbg->x32; T.dbg_y32 = dbg->y32; T.dbg_x64 = dbg->x64; T.dbg_y64 = dbg->y64; T.dbg_valid = dbg->valid; }
-    auto kernel = remap_tiled_kernel<PROJ, INTERP, TIn, TOut>;
-    static thread_local const void* configured = nullptr;   // per instantiation (static in a template)
-    if (configured != (const void*)kernel) {
-        R360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = (const void*)kernel;
-    }
-    const int n_tiles = T.tiles_x * T.tiles_y;
-    const int max_groups = 65535 / p.n_views;
-    for (int g0 = 0; g0 < p.n_groups; g0 += max_groups) {
-        TiledParams Q = T;
-        const int ng = p.n_groups - g0 < max_groups ? p.n_groups - g0 : max_groups;
-        Q.lp.src.data += (long long)g0 * p.n_lenses * p.src.image_stride;
-        Q.lp.dst.data += (long long)g0 * p.n_views_total * p.dst.image_stride;
-        Q.lp.n_groups = ng;
-        dim3 grid(n_tiles, ng * p.n_views, 1);
-        kernel<<<grid, 256, smem, stream>>>(Q);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        R360_CUDA(cudaGetLastError());
-    }
-    return R360_OK;
-}
-
-template <int PROJ, typename TIn, typename TOut>
-int dispatch_interp(const LaunchParams& p, int interp, bool tiled, cudaStream_t s) {
-    switch (interp) {
-        case R360_NEAREST: return tiled ? launch_tiled<PROJ, kNearest, TIn, TOut>(p, s) : launch_direct<PROJ, kNearest, TIn, TOut>(p, s);
-        case R360_LINEAR: return tiled ? launch_tiled<PROJ, kLinear, TIn, TOut>(p, s) : launch_direct<PROJ, kLinear, TIn, TOut>(p, s);
-        case R360_CUBIC: return tiled ? launch_tiled<PROJ, kCubic, TIn, TOut>(p, s) : launch_direct<PROJ, kCubic, TIn, TOut>(p, s);
-        default: return R360_E_INVALID_ARG;
-    }
-}
-
-template <int PROJ>
-int dispatch_types(const LaunchParams& p, int in_dt, int out_dt, int interp, bool tiled, cudaStream_t s) {
-    if (in_dt == R360_U8 && out_dt == R360_U8) return dispatch_interp<PROJ, uint8_t, uint8_t>(p, interp, tiled, s);
-    if (in_dt == R360_U16 && out_dt == R360_U16) return dispatch_interp<PROJ, uint16_t, uint16_t>(p, interp, tiled, s);
-    if (in_dt == R360_U16 && out_dt == R360_F16) return dispatch_interp<PROJ, uint16_t, __half>(p, interp, tiled, s);
-    if (in_dt == R360_F16 && out_dt == R360_F16) return dispatch_interp<PROJ, __half, __half>(p, interp, tiled, s);
-    if (in_dt == R360_F32 && out_dt == R360_F32) return dispatch_interp<PROJ, float, float>(p, interp, tiled, s);
+// type / interpolation / projection switchboard: calls f.template run<PROJ, INTERP, TIn, TOut>()
+template <typename F>
+int dispatch(int proj, int interp, int in_dt, int out_dt, F&& f) {
+#define R360_CASE_T(TIN, TOUT)                                                                              \
+    do {                                                                                                    \
+        if (proj == kProjErp) {                                                                             \
+            if (interp == R360_NEAREST) return f.template run<kProjErp, kNearest, TIN, TOUT>();             \
+            if (interp == R360_LINEAR) return f.template run<kProjErp, kLinear, TIN, TOUT>();               \
+            if (interp == R360_CUBIC) return f.template run<kProjErp, kCubic, TIN, TOUT>();                 \
+        } else {                                                                                            \
+            if (interp == R360_NEAREST) return f.template run<kProjFisheye, kNearest, TIN, TOUT>();         \
+            if (interp == R360_LINEAR) return f.template run<kProjFisheye, kLinear, TIN, TOUT>();           \
+            if (interp == R360_CUBIC) return f.template run<kProjFisheye, kCubic, TIN, TOUT>();             \
+        }                                                                                                   \
+        return R360_E_INVALID_ARG;                                                                          \
+    } while (0)
+    if (in_dt == R360_U8 && out_dt == R360_U8) R360_CASE_T(uint8_t, uint8_t);
+    if (in_dt == R360_U16 && out_dt == R360_U16) R360_CASE_T(uint16_t, uint16_t);
+    if (in_dt == R360_U16 && out_dt == R360_F16) R360_CASE_T(uint16_t, __half);
+    if (in_dt == R360_F16 && out_dt == R360_F16) R360_CASE_T(__half, __half);
+    if (in_dt == R360_F32 && out_dt == R360_F32) R360_CASE_T(float, float);
+#undef R360_CASE_T
     return R360_E_UNSUPPORTED;
 }
 
-int remap_common(int proj, const r360_images* src, const r360_images* dst,
-                 const r360_fisheye_calib* calib, int n_lenses,
-                 const r360_view* views, int n_views, const r360_options* opt_in, void* stream) {
+bool supported_types(int in_dt, int out_dt) {
+    return (in_dt == R360_U8 && out_dt == R360_U8) || (in_dt == R360_U16 && out_dt == R360_U16) ||
+           (in_dt == R360_U16 && out_dt == R360_F16) || (in_dt == R360_F16 && out_dt == R360_F16) ||
+           (in_dt == R360_F32 && out_dt == R360_F32);
+}
+
+// Validates the arguments shared by the plan-less and planned entry points and fills `out`.
+// With `layout_only` the data pointers and counts are not looked at.
+int prepare(int proj, const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
+            int n_lenses, const r360_view* views, int n_views, const r360_options* opt_in, bool layout_only,
+            Prepared* out) {
     int rc;
-    if ((rc = check_images(src)) != R360_OK) return rc;
-    if ((rc = check_images(dst)) != R360_OK) return rc;
+    r360_images s_chk, d_chk;
+    if (!src || !dst) return R360_E_INVALID_ARG;
+    s_chk = *src; d_chk = *dst;
+    if (layout_only) {
+        s_chk.data = d_chk.data = reinterpret_cast<void*>(16);
+        s_chk.count = n_lenses > 0 ? n_lenses : 1;
+        d_chk.count = n_views > 0 ? n_views : 1;
+    }
+    if ((rc = check_images(&s_chk)) != R360_OK) return rc;
+    if ((rc = check_images(&d_chk)) != R360_OK) return rc;
     if (!views || n_views <= 0) return R360_E_INVALID_ARG;
     if (n_lenses < 1) return R360_E_INVALID_ARG;
     if (n_lenses > R360_MAX_LENSES) return R360_E_TOO_MANY;
@@ -277,17 +262,19 @@ int remap_common(int proj, const r360_images* src, const r360_images* dst,
     if (opt.interp < R360_NEAREST || opt.interp > R360_CUBIC) return R360_E_INVALID_ARG;
     if (opt.convention != R360_CONV_HALFPIXEL && opt.convention != R360_CONV_V360) return R360_E_INVALID_ARG;
     if (opt.path < R360_PATH_AUTO || opt.path > R360_PATH_TILED) return R360_E_INVALID_ARG;
-    if (src->channels != dst->channels) return R360_E_INVALID_ARG;
-    if (src->count % n_lenses) return R360_E_INVALID_ARG;
-    const int n_groups = src->count / n_lenses;
-    if ((int64_t)dst->count != (int64_t)n_groups * n_views) return R360_E_INVALID_ARG;
+    if (s_chk.channels != d_chk.channels) return R360_E_INVALID_ARG;
+    if (s_chk.count % n_lenses) return R360_E_INVALID_ARG;
+    const int n_groups = s_chk.count / n_lenses;
+    if ((int64_t)d_chk.count != (int64_t)n_groups * n_views) return R360_E_INVALID_ARG;
     const int out_dt = opt.out_dtype < 0 ? src->dtype : opt.out_dtype;
     if (out_dt != dst->dtype) return R360_E_INVALID_ARG;
+    if (!supported_types(src->dtype, out_dt)) return R360_E_UNSUPPORTED;
     for (int v = 0; v < n_views; ++v)
         if (views[v].src_slot < 0 || views[v].src_slot >= n_lenses) return R360_E_INVALID_ARG;
-    if ((rc = ensure_device_ready()) != R360_OK) return rc;
 
-    LaunchParams p;
+    out->proj = proj; out->n_lenses = n_lenses; out->n_views = n_views; out->interp = opt.interp;
+    out->in_dt = src->dtype; out->out_dt = out_dt; out->opt = opt;
+    LaunchParams& p = out->lp;
     std::memset(&p, 0, sizeof(p));
     p.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
     p.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
@@ -302,18 +289,202 @@ int remap_common(int proj, const r360_images* src, const r360_images* dst,
     p.border_value = (float)bv;
     if (proj == kProjErp) make_erp(src->width, src->height, opt.convention, &p.erp);
     else for (int l = 0; l < n_lenses; ++l) make_lens(calib[l], &p.lens[l]);
+    return R360_OK;
+}
 
+struct DirectLauncher {
+    const LaunchParams& p; cudaStream_t s;
+    template <int PROJ, int INTERP, typename TIn, typename TOut> int run() { return launch_direct<PROJ, INTERP, TIn, TOut>(p, s); }
+};
+
+int remap_direct(int proj, const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
+                 int n_lenses, const r360_view* views, int n_views, const r360_options* opt_in, void* stream) {
+    Prepared pr;
+    int rc = prepare(proj, src, dst, calib, n_lenses, views, n_views, opt_in, false, &pr);
+    if (rc != R360_OK) return rc;
+    if (pr.opt.path == R360_PATH_TILED) return R360_E_INVALID_ARG;      // needs a plan
+    if ((rc = ensure_device_ready()) != R360_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LaunchParams& p = pr.lp;
     for (int v0 = 0; v0 < n_views; v0 += kMaxViewsPerLaunch) {
         p.view_base = v0;
         p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
         for (int v = 0; v < p.n_views; ++v) make_view(views[v0 + v], dst->width, dst->height, &p.views[v]);
-        const bool tiled = opt.path != R360_PATH_DIRECT;
-        rc = proj == kProjErp ? dispatch_types<kProjErp>(p, src->dtype, out_dt, opt.interp, tiled, s)
-                              : dispatch_types<kProjFisheye>(p, src->dtype, out_dt, opt.interp, tiled, s);
+        rc = dispatch(proj, pr.interp, pr.in_dt, pr.out_dt, DirectLauncher{p, s});
         if (rc != R360_OK) return rc;
     }
     return R360_OK;
+}
+
+// ---- plans ------------------------------------------------------------------------------------------
+
+// Shared memory per block for the tiled kernel: aim for 4 resident blocks per SM.
+constexpr int kSmemPerBlockTarget = 56 * 1024 - 1024;
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WorkspaceLayout { size_t header, views, plans, fallback, total; };
+
+WorkspaceLayout workspace_layout(int n_views, int out_w, int out_h) {
+    const size_t tiles = (size_t)((out_w + kTile - 1) / kTile) * ((out_h + kTile - 1) / kTile);
+    WorkspaceLayout w;
+    w.header = 0;
+    w.views = align_up(sizeof(PlanHeader), 256);
+    w.plans = w.views + align_up(sizeof(ViewDev) * n_views, 256);
+    w.fallback = w.plans + align_up(sizeof(TilePlan) * n_views * tiles, 256);
+    w.total = w.fallback + align_up(sizeof(int2) * n_views * tiles, 256);
+    return w;
+}
+
+}  // namespace
+
+struct r360_plan {
+    Prepared pr;
+    r360_images src_layout, dst_layout;
+    std::vector<ViewDev> views;
+    int tiles_x, tiles_y, n_tiles, n_fallback;
+    int out_stage_bytes, patch_budget, smem_bytes;
+    bool bulk_load_ok, bulk_store_ok;
+    unsigned char* ws;
+    PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback;
+};
+
+namespace {
+
+bool aligned16(const void* p, int64_t pitch, int64_t stride) {
+    return reinterpret_cast<uintptr_t>(p) % 16 == 0 && pitch % 16 == 0 && stride % 16 == 0;
+}
+
+int plan_create(int proj, const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
+                int n_lenses, const r360_view* views, int n_views, const r360_options* opt_in,
+                void* workspace, size_t workspace_bytes, void* stream, r360_plan** plan_out) {
+    if (!plan_out || !workspace) return R360_E_INVALID_ARG;
+    *plan_out = nullptr;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256) return R360_E_INVALID_ARG;
+    r360_plan* pl = new (std::nothrow) r360_plan();
+    if (!pl) return R360_E_INVALID_ARG;
+    int rc = prepare(proj, src, dst, calib, n_lenses, views, n_views, opt_in, true, &pl->pr);
+    if (rc == R360_OK) rc = ensure_device_ready();
+    const WorkspaceLayout wl = workspace_layout(n_views > 0 ? n_views : 1, dst ? dst->width : 1, dst ? dst->height : 1);
+    if (rc == R360_OK && workspace_bytes < wl.total) rc = R360_E_INVALID_ARG;
+    if (rc != R360_OK) { delete pl; return rc; }
+
+    pl->src_layout = *src; pl->dst_layout = *dst;
+    pl->tiles_x = (dst->width + kTile - 1) / kTile;
+    pl->tiles_y = (dst->height + kTile - 1) / kTile;
+    pl->n_tiles = pl->tiles_x * pl->tiles_y;
+    pl->views.resize(n_views);
+    for (int v = 0; v < n_views; ++v) make_view(views[v], dst->width, dst->height, &pl->views[v]);
+    const int out_es = elem_size(pl->pr.out_dt), in_es = elem_size(pl->pr.in_dt);
+    pl->out_stage_bytes = (int)align_up((size_t)kTile * kTile * dst->channels * out_es, 128);
+    pl->patch_budget = kSmemPerBlockTarget - kTiledFixedSmem - pl->out_stage_bytes;
+    if (pl->patch_budget < 8192) pl->patch_budget = 8192;
+    pl->smem_bytes = kTiledFixedSmem + pl->out_stage_bytes + pl->patch_budget;
+    // the data pointers are not known yet: assume 16-byte aligned bases (checked at remap time)
+    pl->bulk_load_ok = src->pitch_bytes % 16 == 0 && src->image_stride_bytes % 16 == 0 &&
+                       ((int64_t)src->width * src->channels * in_es) % 16 == 0;
+    pl->bulk_store_ok = dst->pitch_bytes % 16 == 0 && dst->image_stride_bytes % 16 == 0;
+    pl->ws = static_cast<unsigned char*>(workspace);
+    pl->d_header = reinterpret_cast<PlanHeader*>(pl->ws + wl.header);
+    pl->d_views = reinterpret_cast<ViewDev*>(pl->ws + wl.views);
+    pl->d_plans = reinterpret_cast<TilePlan*>(pl->ws + wl.plans);
+    pl->d_fallback = reinterpret_cast<int2*>(pl->ws + wl.fallback);
+
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    auto fail = [&](cudaError_t e, const char* what) { delete pl; return cuda_fail(e, what); };
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(pl->d_header, 0, sizeof(PlanHeader), s)) != cudaSuccess) return fail(e, "cudaMemsetAsync");
+    if ((e = cudaMemcpyAsync(pl->d_views, pl->views.data(), sizeof(ViewDev) * n_views, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+        return fail(e, "cudaMemcpyAsync(views)");
+    PlanParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.proj = proj; P.out_w = dst->width; P.out_h = dst->height; P.tiles_x = pl->tiles_x; P.tiles_y = pl->tiles_y;
+    P.n_views = n_views; P.src_w = src->width; P.src_h = src->height; P.px_bytes = src->channels * in_es;
+    P.patch_budget = pl->patch_budget; P.bulk_load_ok = pl->bulk_load_ok; P.fill_invalid = pl->pr.lp.fill_invalid;
+    P.erp = pl->pr.lp.erp;
+    std::memcpy(P.lens, pl->pr.lp.lens, sizeof(P.lens));
+    P.views = pl->d_views; P.plans = pl->d_plans; P.header = pl->d_header; P.fallback = pl->d_fallback;
+    for (int v0 = 0; v0 < n_views; v0 += 65535) {
+        PlanParams Q = P;
+        const int nv = n_views - v0 < 65535 ? n_views - v0 : 65535;
+        Q.views = pl->d_views + v0; Q.plans = pl->d_plans + (size_t)v0 * pl->n_tiles; Q.n_views = nv;
+        // the fallback list stores view indices relative to Q.views: only one chunk is ever needed in practice
+        if (v0 != 0) { delete pl; return R360_E_TOO_MANY; }
+        plan_kernel<<<dim3(pl->n_tiles, nv), 64, 0, s>>>(Q);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "plan_kernel launch");
+    }
+    PlanHeader h;
+    if ((e = cudaMemcpyAsync(&h, pl->d_header, sizeof(h), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "cudaMemcpyAsync(header)");
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
+    pl->n_fallback = h.n_fallback;
+    *plan_out = pl;
+    return R360_OK;
+}
+
+struct TiledLauncher {
+    const r360_plan* pl; const r360_images* src; const r360_images* dst; cudaStream_t s;
+    float* dx32; float* dy32; double* dx64; double* dy64; unsigned char* dvalid;
+
+    template <int PROJ, int INTERP, typename TIn, typename TOut> int run() {
+        const bool debug = dx32 != nullptr;
+        const LaunchParams& lp = pl->pr.lp;
+        const int n_groups = debug ? 1 : src->count / pl->pr.n_lenses;
+        TiledParams T;
+        std::memset(&T, 0, sizeof(T));
+        if (!debug) {
+            T.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
+            T.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
+        } else {
+            T.src = lp.src; T.dst = lp.dst;
+        }
+        T.channels = lp.channels; T.n_views = pl->pr.n_views; T.view_base = 0; T.n_views_total = pl->pr.n_views;
+        T.n_lenses = pl->pr.n_lenses; T.tiles_x = pl->tiles_x; T.tiles_y = pl->tiles_y;
+        T.out_stage_bytes = pl->out_stage_bytes; T.bulk_store_ok = pl->bulk_store_ok; T.border_value = lp.border_value;
+        T.plans = pl->d_plans;
+        T.dbg_x32 = dx32; T.dbg_y32 = dy32; T.dbg_x64 = dx64; T.dbg_y64 = dy64; T.dbg_valid = dvalid;
+
+        auto kernel = remap_tiled_kernel<INTERP, TIn, TOut>;
+        static thread_local int configured_smem = -1;     // per instantiation and thread
+        if (configured_smem < pl->smem_bytes) {
+            R360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
+            configured_smem = pl->smem_bytes;
+        }
+        const int max_groups = 65535 / pl->pr.n_views > 0 ? 65535 / pl->pr.n_views : 1;
+        for (int g0 = 0; g0 < n_groups; g0 += max_groups) {
+            TiledParams Q = T;
+            const int ng = n_groups - g0 < max_groups ? n_groups - g0 : max_groups;
+            if (!debug) {
+                Q.src.data += (long long)g0 * pl->pr.n_lenses * Q.src.image_stride;
+                Q.dst.data += (long long)g0 * pl->pr.n_views * Q.dst.image_stride;
+            }
+            kernel<<<dim3(pl->n_tiles, ng * pl->pr.n_views), 256, pl->smem_bytes, s>>>(Q);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            R360_CUDA(cudaGetLastError());
+        }
+        if (pl->n_fallback > 0 && !debug) {
+            FallbackParams F;
+            std::memset(&F, 0, sizeof(F));
+            F.lp = lp;
+            F.lp.src = T.src; F.lp.dst = T.dst; F.lp.view_base = 0; F.lp.n_views = pl->pr.n_views;
+            F.views = pl->d_views; F.list = pl->d_fallback; F.tiles_x = pl->tiles_x;
+            for (int g0 = 0; g0 < n_groups; g0 += 65535) {
+                FallbackParams G = F;
+                const int ng = n_groups - g0 < 65535 ? n_groups - g0 : 65535;
+                G.lp.src.data += (long long)g0 * pl->pr.n_lenses * G.lp.src.image_stride;
+                G.lp.dst.data += (long long)g0 * pl->pr.n_views * G.lp.dst.image_stride;
+                remap_fallback_kernel<PROJ, INTERP, TIn, TOut><<<dim3(pl->n_fallback, ng), 256, 0, s>>>(G);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                R360_CUDA(cudaGetLastError());
+            }
+        }
+        return R360_OK;
+    }
+};
+
+bool same_layout(const r360_images& a, const r360_images& b, bool check_stride) {
+    return a.width == b.width && a.height == b.height && a.channels == b.channels && a.dtype == b.dtype &&
+           a.pitch_bytes == b.pitch_bytes && (!check_stride || a.image_stride_bytes == b.image_stride_bytes);
 }
 
 }  // namespace
@@ -362,13 +533,13 @@ int r360_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int r360_remap_erp(const r360_images* src, const r360_images* dst, const r360_view* views, int32_t n_views,
                    const r360_options* opt, void* stream) {
-    return remap_common(kProjErp, src, dst, nullptr, 1, views, n_views, opt, stream);
+    return remap_direct(kProjErp, src, dst, nullptr, 1, views, n_views, opt, stream);
 }
 
 int r360_remap_fisheye(const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
                        int32_t n_lenses, const r360_view* views, int32_t n_views, const r360_options* opt,
                        void* stream) {
-    return remap_common(kProjFisheye, src, dst, calib, n_lenses, views, n_views, opt, stream);
+    return remap_direct(kProjFisheye, src, dst, calib, n_lenses, views, n_views, opt, stream);
 }
 
 int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, int32_t n_lenses,
@@ -377,7 +548,8 @@ int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, i
                 uint8_t* valid, void* stream) {
     if (!views || n_views <= 0 || out_w <= 0 || out_h <= 0) return R360_E_INVALID_ARG;
     if (!calib && (src_w <= 0 || src_h <= 0)) return R360_E_INVALID_ARG;
-    if (calib && (n_lenses < 1 || n_lenses > R360_MAX_LENSES)) return calib && n_lenses > R360_MAX_LENSES ? R360_E_TOO_MANY : R360_E_INVALID_ARG;
+    if (calib && n_lenses > R360_MAX_LENSES) return R360_E_TOO_MANY;
+    if (calib && n_lenses < 1) return R360_E_INVALID_ARG;
     r360_options opt;
     if (opt_in) opt = *opt_in; else r360_default_options(&opt);
     int rc;
@@ -392,29 +564,10 @@ int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, i
     for (int v = 0; v < n_views; ++v)
         if (calib && (views[v].src_slot < 0 || views[v].src_slot >= n_lenses)) return R360_E_INVALID_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (opt.path != R360_PATH_DIRECT && (!map_x32 || !map_y32 || !map_x64 || !map_y64)) return R360_E_INVALID_ARG;
     for (int v0 = 0; v0 < n_views; v0 += kMaxViewsPerLaunch) {
         p.view_base = v0;
         p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
         for (int v = 0; v < p.n_views; ++v) make_view(views[v0 + v], out_w, out_h, &p.views[v]);
-        if (opt.path != R360_PATH_DIRECT) {
-            // what the tiled kernels would sample for an 8-bit 3-channel source of this size
-            LaunchParams lp;
-            std::memset(&lp, 0, sizeof(lp));
-            lp.src.width = calib ? (int)calib[0].width : src_w;
-            lp.src.height = calib ? (int)calib[0].height : src_h;
-            lp.src.pitch = (long long)lp.src.width * 3;
-            lp.dst.width = out_w; lp.dst.height = out_h;
-            lp.channels = 3; lp.n_views = p.n_views; lp.view_base = v0; lp.n_views_total = n_views;
-            lp.n_lenses = calib ? n_lenses : 1; lp.n_groups = 1; lp.fill_invalid = opt.fill_invalid != 0;
-            lp.erp = p.erp;
-            std::memcpy(lp.lens, p.lens, sizeof(lp.lens));
-            std::memcpy(lp.views, p.views, sizeof(lp.views));
-            rc = proj == kProjErp ? launch_tiled<kProjErp, kLinear, uint8_t, uint8_t>(lp, s, &p)
-                                  : launch_tiled<kProjFisheye, kLinear, uint8_t, uint8_t>(lp, s, &p);
-            if (rc != R360_OK) return rc;
-            continue;
-        }
         dim3 grid((out_w + 31) / 32, (out_h + 7) / 8, p.n_views);
         coords_kernel<<<grid, 256, 0, s>>>(p, proj);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -422,6 +575,82 @@ int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, i
     }
     return R360_OK;
 }
+
+size_t r360_plan_workspace_bytes(int32_t n_views, int32_t out_w, int32_t out_h) {
+    if (n_views <= 0 || out_w <= 0 || out_h <= 0) return 0;
+    return workspace_layout(n_views, out_w, out_h).total;
+}
+
+int r360_plan_create_erp(const r360_images* src_layout, const r360_images* dst_layout, const r360_view* views,
+                         int32_t n_views, const r360_options* opt, void* workspace_device, size_t workspace_bytes,
+                         void* stream, r360_plan** plan_out) {
+    return plan_create(kProjErp, src_layout, dst_layout, nullptr, 1, views, n_views, opt, workspace_device,
+                       workspace_bytes, stream, plan_out);
+}
+
+int r360_plan_create_fisheye(const r360_images* src_layout, const r360_images* dst_layout,
+                             const r360_fisheye_calib* calib, int32_t n_lenses, const r360_view* views,
+                             int32_t n_views, const r360_options* opt, void* workspace_device,
+                             size_t workspace_bytes, void* stream, r360_plan** plan_out) {
+    return plan_create(kProjFisheye, src_layout, dst_layout, calib, n_lenses, views, n_views, opt,
+                       workspace_device, workspace_bytes, stream, plan_out);
+}
+
+int r360_plan_info(const r360_plan* plan, int32_t* tiles_per_view, int32_t* n_fallback_tiles) {
+    if (!plan) return R360_E_INVALID_ARG;
+    if (tiles_per_view) *tiles_per_view = plan->n_tiles;
+    if (n_fallback_tiles) *n_fallback_tiles = plan->n_fallback;
+    return R360_OK;
+}
+
+int r360_remap_planned(const r360_plan* plan, const r360_images* src, const r360_images* dst, void* stream) {
+    if (!plan) return R360_E_INVALID_ARG;
+    int rc;
+    if ((rc = check_images(src)) != R360_OK) return rc;
+    if ((rc = check_images(dst)) != R360_OK) return rc;
+    if (!same_layout(*src, plan->src_layout, src->count > 1) || !same_layout(*dst, plan->dst_layout, dst->count > 1))
+        return R360_E_INVALID_ARG;
+    if (src->count % plan->pr.n_lenses) return R360_E_INVALID_ARG;
+    if ((int64_t)dst->count != (int64_t)(src->count / plan->pr.n_lenses) * plan->pr.n_views) return R360_E_INVALID_ARG;
+    // the plan assumed 16-byte aligned bases wherever it chose bulk copies
+    if (plan->bulk_load_ok && !aligned16(src->data, src->pitch_bytes, src->count > 1 ? src->image_stride_bytes : 0))
+        return R360_E_INVALID_ARG;
+    if (plan->bulk_store_ok && !aligned16(dst->data, dst->pitch_bytes, dst->count > 1 ? dst->image_stride_bytes : 0))
+        return R360_E_INVALID_ARG;
+    TiledLauncher L{plan, src, dst, static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, nullptr, nullptr};
+    return dispatch(plan->pr.proj, plan->pr.interp, plan->pr.in_dt, plan->pr.out_dt, L);
+}
+
+int r360_plan_coords(const r360_plan* plan, float* map_x32, float* map_y32, double* map_x64, double* map_y64,
+                     uint8_t* valid, void* stream) {
+    if (!plan || !map_x32 || !map_y32 || !map_x64 || !map_y64) return R360_E_INVALID_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // every pixel from the direct projection first, then the fast tiles overwrite theirs with
+    // what the polynomial path computes
+    CoordParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.out_w = plan->dst_layout.width; p.out_h = plan->dst_layout.height;
+    p.x32 = map_x32; p.y32 = map_y32; p.x64 = map_x64; p.y64 = map_y64; p.valid = valid;
+    p.erp = plan->pr.lp.erp;
+    std::memcpy(p.lens, plan->pr.lp.lens, sizeof(p.lens));
+    const int n_views = plan->pr.n_views;
+    for (int v0 = 0; v0 < n_views; v0 += kMaxViewsPerLaunch) {
+        p.view_base = v0;
+        p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
+        for (int v = 0; v < p.n_views; ++v) p.views[v] = plan->views[v0 + v];
+        dim3 grid((p.out_w + 31) / 32, (p.out_h + 7) / 8, p.n_views);
+        coords_kernel<<<grid, 256, 0, s>>>(p, plan->pr.proj);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        R360_CUDA(cudaGetLastError());
+    }
+    r360_plan dbg = *plan;      // shallow copy: give the launcher a destination size to index with
+    dbg.pr.lp.dst.width = p.out_w; dbg.pr.lp.dst.height = p.out_h;
+    dbg.pr.lp.src.width = plan->src_layout.width; dbg.pr.lp.src.height = plan->src_layout.height;
+    TiledLauncher L{&dbg, nullptr, nullptr, s, map_x32, map_y32, map_x64, map_y64, valid};
+    return dispatch(plan->pr.proj, plan->pr.interp, plan->pr.in_dt, plan->pr.out_dt, L);
+}
+
+void r360_plan_destroy(r360_plan* plan) { delete plan; }
 
 int64_t r360_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -50,7 +50,9 @@ _lib = None
 
 # every symbol include/remap360.h declares (tests check the .so exports exactly these)
 EXPORTS = ("r360_abi_version", "r360_error_string", "r360_last_cuda_error", "r360_default_options",
-           "r360_device_info", "r360_remap_erp", "r360_remap_fisheye", "r360_coords", "r360_launch_count")
+           "r360_device_info", "r360_remap_erp", "r360_remap_fisheye", "r360_coords", "r360_launch_count",
+           "r360_plan_workspace_bytes", "r360_plan_create_erp", "r360_plan_create_fisheye", "r360_plan_info",
+           "r360_remap_planned", "r360_plan_coords", "r360_plan_destroy")
 
 
 def load() -> ctypes.CDLL:
@@ -77,6 +79,18 @@ def load() -> ctypes.CDLL:
                                 c_int32, c_int32, POINTER(Options), c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]
     lib.r360_launch_count.restype = c_int64
+    lib.r360_plan_workspace_bytes.restype = ctypes.c_size_t
+    lib.r360_plan_workspace_bytes.argtypes = [c_int32, c_int32, c_int32]
+    lib.r360_plan_create_erp.argtypes = [POINTER(Images), POINTER(Images), POINTER(View), c_int32, POINTER(Options),
+                                         c_void_p, ctypes.c_size_t, c_void_p, POINTER(c_void_p)]
+    lib.r360_plan_create_fisheye.argtypes = [POINTER(Images), POINTER(Images), POINTER(FisheyeCalib), c_int32,
+                                             POINTER(View), c_int32, POINTER(Options), c_void_p, ctypes.c_size_t,
+                                             c_void_p, POINTER(c_void_p)]
+    lib.r360_plan_info.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32)]
+    lib.r360_remap_planned.argtypes = [c_void_p, POINTER(Images), POINTER(Images), c_void_p]
+    lib.r360_plan_coords.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.r360_plan_destroy.argtypes = [c_void_p]
+    lib.r360_plan_destroy.restype = None
     lib.r360_debug_weight_tables.argtypes = [c_void_p, c_void_p]
     if lib.r360_abi_version() != 1:
         raise ImportError("libremap360.so has ABI version %d, expected 1" % lib.r360_abi_version())

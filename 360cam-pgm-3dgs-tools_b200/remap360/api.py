@@ -7,11 +7,16 @@ library provides the kernels.
 The two calls stand in for the reference's two remap back ends: one ffmpeg ``v360`` process per
 (frame, view) (cli_tools/gs360_360PerspCut.py:286-349, :569-590) and NumPy map build +
 ``cv2.remap`` + mask fill (cli_tools/gs360_DualFisheyeDistortionCalibration.py:1759-1823,
-:2001-2014)."""
+:2001-2014).
+
+``path="auto"`` (default) uses the tiled kernels through a cached *plan* -- the counterpart of
+the reference building its maps once and applying them to every frame (DF:1857-1907 /
+:1996-2014); ``path="direct"`` runs the per-pixel float64 path with no plan."""
 
 from __future__ import annotations
 
 import ctypes
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence, Tuple
 
@@ -56,7 +61,6 @@ class FisheyeCalibration:
 
 _TORCH_TO_R360 = {torch.uint8: _lib.DTYPE_U8, torch.uint16: _lib.DTYPE_U16,
                   torch.float16: _lib.DTYPE_F16, torch.float32: _lib.DTYPE_F32}
-_R360_TO_TORCH = {v: k for k, v in _TORCH_TO_R360.items()}
 
 
 def _dtype_code(dt) -> int:
@@ -115,12 +119,107 @@ def _stream_handle(stream: Optional[torch.cuda.Stream], device) -> int:
     return (stream or torch.cuda.current_stream(device)).cuda_stream
 
 
+# ---- plans --------------------------------------------------------------------------------------
+
+class Plan:
+    """A built tile plan (r360_plan) plus the device workspace it lives in."""
+
+    def __init__(self, handle: int, workspace: torch.Tensor, tiles_per_view: int, n_fallback: int, n_views: int):
+        self.handle, self.workspace = handle, workspace
+        self.tiles_per_view, self.n_fallback, self.n_views = tiles_per_view, n_fallback, n_views
+
+    @property
+    def fallback_fraction(self) -> float:
+        return self.n_fallback / float(self.tiles_per_view * self.n_views)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().r360_plan_destroy(self.handle)
+                self.handle = 0
+        except Exception:
+            pass
+
+
+_PLAN_CACHE: "OrderedDict[tuple, Plan]" = OrderedDict()
+_PLAN_CACHE_SIZE = 32
+
+
+def _layout_key(im: Images, aligned: bool):
+    return (im.width, im.height, im.channels, im.dtype, im.pitch_bytes,
+            im.image_stride_bytes if im.count > 1 else 0, aligned)
+
+
+def get_plan(src: Images, dst: Images, views: Sequence[PerspectiveView], opt: Options, device,
+             calibs: Optional[Sequence[FisheyeCalibration]] = None,
+             stream: Optional[torch.cuda.Stream] = None) -> Plan:
+    """Build (or fetch from the cache) the plan for this layout / view set / option set."""
+    lib = _lib.load()
+    device = torch.device(device)
+    key = (device.index, _layout_key(src, src.data % 16 == 0 if src.data else True),
+           _layout_key(dst, dst.data % 16 == 0 if dst.data else True),
+           tuple((v.yaw_deg, v.pitch_deg, v.roll_deg, v.hfov_deg, v.vfov_deg, v.src_slot) for v in views),
+           None if calibs is None else tuple(tuple(getattr(c, n) for n, _ in FisheyeCalib._fields_) for c in calibs),
+           (opt.interp, opt.convention, opt.fill_invalid, opt.border_value, opt.out_dtype))
+    plan = _PLAN_CACHE.get(key)
+    if plan is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return plan
+    nbytes = lib.r360_plan_workspace_bytes(len(views), dst.width, dst.height)
+    workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    handle = ctypes.c_void_p()
+    popt = Options.from_buffer_copy(opt)
+    popt.path = _lib.PATH["tiled"]
+    with torch.cuda.device(device):
+        if calibs is None:
+            rc = lib.r360_plan_create_erp(ctypes.byref(src), ctypes.byref(dst), _views_array(views), len(views),
+                                          ctypes.byref(popt), workspace.data_ptr(), nbytes,
+                                          _stream_handle(stream, device), ctypes.byref(handle))
+        else:
+            rc = lib.r360_plan_create_fisheye(ctypes.byref(src), ctypes.byref(dst), _calib_array(calibs), len(calibs),
+                                              _views_array(views), len(views), ctypes.byref(popt),
+                                              workspace.data_ptr(), nbytes, _stream_handle(stream, device),
+                                              ctypes.byref(handle))
+    _lib.check(rc)
+    tiles, nfb = ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(lib.r360_plan_info(handle, ctypes.byref(tiles), ctypes.byref(nfb)))
+    plan = Plan(handle.value, workspace, tiles.value, nfb.value, len(views))
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def clear_plan_cache() -> None:
+    _PLAN_CACHE.clear()
+
+
+def _run(src: Images, dst: Images, views, opt: Options, path: str, device, stream, calibs=None) -> None:
+    lib = _lib.load()
+    if path == "direct":
+        with torch.cuda.device(device):
+            if calibs is None:
+                rc = lib.r360_remap_erp(ctypes.byref(src), ctypes.byref(dst), _views_array(views), len(views),
+                                        ctypes.byref(opt), _stream_handle(stream, device))
+            else:
+                rc = lib.r360_remap_fisheye(ctypes.byref(src), ctypes.byref(dst), _calib_array(calibs), len(calibs),
+                                            _views_array(views), len(views), ctypes.byref(opt),
+                                            _stream_handle(stream, device))
+        _lib.check(rc)
+        return
+    if len(views) == 0:
+        raise _lib.Remap360Error(-1, "invalid argument (no views)")
+    plan = get_plan(src, dst, views, opt, device, calibs, stream)
+    with torch.cuda.device(device):
+        _lib.check(lib.r360_remap_planned(plan.handle, ctypes.byref(src), ctypes.byref(dst),
+                                          _stream_handle(stream, device)))
+
+
 def remap_erp(frames: torch.Tensor, views: Sequence[PerspectiveView], size: Tuple[int, int], *,
               interp: str = "cubic", convention: str = "halfpixel", out: Optional[torch.Tensor] = None,
               out_dtype: Optional[torch.dtype] = None, path: str = "auto",
               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
     """ERP frames [B, H, W, C] -> views [B, V, h, w, C] (size = (w, h))."""
-    lib = _lib.load()
     if frames.dim() == 3:
         frames = frames.unsqueeze(0)
     b, _, _, c = frames.shape
@@ -131,11 +230,9 @@ def remap_erp(frames: torch.Tensor, views: Sequence[PerspectiveView], size: Tupl
     elif tuple(out.shape) != (b, len(views), h, w, c) or out.dtype != dt:
         raise ValueError("out must be %s %s" % ((b, len(views), h, w, c), dt))
     src = _describe(frames, "frames")
-    dst = _describe(out.view(b * len(views), h, w, c), "out")
+    dst = _describe(out.view(b * max(len(views), 1), h, w, c) if len(views) else out.view(0, h, w, c), "out")
     opt = _options(interp, convention, path, out_dtype=None if dt == frames.dtype else dt)
-    with torch.cuda.device(frames.device):
-        _lib.check(lib.r360_remap_erp(ctypes.byref(src), ctypes.byref(dst), _views_array(views), len(views),
-                                      ctypes.byref(opt), _stream_handle(stream, frames.device)))
+    _run(src, dst, views, opt, path, frames.device, stream)
     return out
 
 
@@ -146,7 +243,6 @@ def remap_fisheye(images: torch.Tensor, calibs: Sequence[FisheyeCalibration],
                   stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
     """Fisheye groups [G, L, H, W, C] (L lens images per group) -> views [G, V, h, w, C].
     View yaw is relative to the lens named by ``src_slot`` (DF:1883)."""
-    lib = _lib.load()
     if images.dim() != 5:
         raise ValueError("images must be [G, L, H, W, C]")
     g, nl, hh, ww, c = images.shape
@@ -162,12 +258,8 @@ def remap_fisheye(images: torch.Tensor, calibs: Sequence[FisheyeCalibration],
         raise ValueError("images must be contiguous")
     src = _describe(images.view(g * nl, hh, ww, c), "images")
     dst = _describe(out.view(g * len(views), h, w, c), "out")
-    opt = _options(interp, "halfpixel", path, fill_invalid, border_value,
-                   None if dt == images.dtype else dt)
-    with torch.cuda.device(images.device):
-        _lib.check(lib.r360_remap_fisheye(ctypes.byref(src), ctypes.byref(dst), _calib_array(calibs), nl,
-                                          _views_array(views), len(views), ctypes.byref(opt),
-                                          _stream_handle(stream, images.device)))
+    opt = _options(interp, "halfpixel", path, fill_invalid, border_value, None if dt == images.dtype else dt)
+    _run(src, dst, views, opt, path, images.device, stream, calibs)
     return out
 
 
@@ -177,10 +269,13 @@ def sample_coordinates(views: Sequence[PerspectiveView], size: Tuple[int, int], 
                        convention: str = "halfpixel", path: str = "auto", device="cuda",
                        stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
     """The source coordinates the kernels sample at (test/debug): float32 maps as cv2.remap would
-    receive them, their float64 pre-images, and (fisheye) the validity mask; each [V, h, w]."""
+    receive them, their float64 pre-images, and (fisheye) the validity mask; each [V, h, w].
+    With a tiled path the plan is the one an 8-bit 3-channel contiguous source would get."""
     lib = _lib.load()
     w, h = int(size[0]), int(size[1])
     device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     n = len(views)
     res = {"x32": torch.empty((n, h, w), dtype=torch.float32, device=device),
            "y32": torch.empty((n, h, w), dtype=torch.float32, device=device),
@@ -190,14 +285,27 @@ def sample_coordinates(views: Sequence[PerspectiveView], size: Tuple[int, int], 
     if calibs is not None:
         res["valid"] = torch.empty((n, h, w), dtype=torch.uint8, device=device)
         valid_ptr = res["valid"].data_ptr()
-        cal, nl, sw, sh = _calib_array(calibs), len(calibs), 0, 0
+        cal, nl, sw, sh = _calib_array(calibs), len(calibs), int(calibs[0].width), int(calibs[0].height)
     else:
         if erp_size is None:
             raise ValueError("erp_size or calibs is required")
         cal, nl, sw, sh = None, 1, int(erp_size[0]), int(erp_size[1])
     opt = _options("cubic", convention, path)
+    if path == "direct":
+        with torch.cuda.device(device):
+            _lib.check(lib.r360_coords(sw if calibs is None else 0, sh if calibs is None else 0, cal, nl,
+                                       _views_array(views), n, w, h, ctypes.byref(opt),
+                                       res["x32"].data_ptr(), res["y32"].data_ptr(), res["x64"].data_ptr(),
+                                       res["y64"].data_ptr(), valid_ptr, _stream_handle(stream, device)))
+        return res
+    src = Images(data=None, width=sw, height=sh, channels=3, dtype=_lib.DTYPE_U8, pitch_bytes=sw * 3,
+                 image_stride_bytes=sw * sh * 3, count=nl, reserved=0)
+    dst = Images(data=None, width=w, height=h, channels=3, dtype=_lib.DTYPE_U8, pitch_bytes=w * 3,
+                 image_stride_bytes=w * h * 3, count=n, reserved=0)
+    plan = get_plan(src, dst, views, opt, device, calibs, stream)
     with torch.cuda.device(device):
-        _lib.check(lib.r360_coords(sw, sh, cal, nl, _views_array(views), n, w, h, ctypes.byref(opt),
-                                   res["x32"].data_ptr(), res["y32"].data_ptr(), res["x64"].data_ptr(),
-                                   res["y64"].data_ptr(), valid_ptr, _stream_handle(stream, device)))
+        _lib.check(lib.r360_plan_coords(plan.handle, res["x32"].data_ptr(), res["y32"].data_ptr(),
+                                        res["x64"].data_ptr(), res["y64"].data_ptr(), valid_ptr,
+                                        _stream_handle(stream, device)))
+    res["fallback_fraction"] = torch.tensor(plan.fallback_fraction)
     return res

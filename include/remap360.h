@@ -52,7 +52,9 @@ enum { R360_NEAREST = 0, R360_LINEAR = 1, R360_CUBIC = 2 };
  * replaced ffmpeg filter). */
 enum { R360_CONV_HALFPIXEL = 0, R360_CONV_V360 = 1 };
 
-/* which device code path to use; AUTO picks TILED when the layout allows it */
+/* r360_options.path: r360_remap_erp / r360_remap_fisheye always run the direct per-pixel path
+ * (AUTO == DIRECT there); the tiled path needs a plan, see r360_plan_create_*.  TILED is
+ * rejected by the plan-less entry points. */
 enum { R360_PATH_AUTO = 0, R360_PATH_DIRECT = 1, R360_PATH_TILED = 2 };
 
 #define R360_MAX_LENSES 4
@@ -167,6 +169,51 @@ int r360_coords(int32_t src_w, int32_t src_h,
                 int32_t out_w, int32_t out_h, const r360_options* opt,
                 float* map_x32, float* map_y32, double* map_x64, double* map_y64,
                 uint8_t* valid, void* stream);
+
+/* ---- planned (tiled) execution -------------------------------------------------------------------
+ *
+ * The reference builds its remap tables once per view set and applies them to every frame
+ * (gs360_DualFisheyeDistortionCalibration.py:1857-1907 build, :1996-2014 apply; ffmpeg's v360
+ * does the same inside each process).  A plan is this library's equivalent: per 32x32 output
+ * tile, polynomial coordinates fitted in float64 plus the source patch to stage -- 328 bytes per
+ * tile in a caller-provided device workspace, built on the device by r360_plan_create_*.
+ * r360_remap_planned then runs the tiled fast kernels (bulk-async staging to shared memory),
+ * falling back to the direct path tile by tile where the plan says so.  Results are the same as
+ * r360_remap_erp / r360_remap_fisheye up to 1/32-px bin flips from ~1e-5 px coordinate noise.
+ *
+ * A plan is tied to the source/destination LAYOUT (size, channels, dtype, pitches, 16-byte
+ * alignment of the base pointers), the views, and the options; `data` and `count` of the two
+ * layout descriptors are ignored at creation.  Creating a plan synchronises `stream` once.
+ */
+typedef struct r360_plan r360_plan;    /* opaque host-side handle, owned by the library */
+
+size_t r360_plan_workspace_bytes(int32_t n_views, int32_t out_w, int32_t out_h);
+
+int r360_plan_create_erp(const r360_images* src_layout, const r360_images* dst_layout,
+                         const r360_view* views, int32_t n_views, const r360_options* opt,
+                         void* workspace_device, size_t workspace_bytes, void* stream,
+                         r360_plan** plan_out);
+
+int r360_plan_create_fisheye(const r360_images* src_layout, const r360_images* dst_layout,
+                             const r360_fisheye_calib* calib, int32_t n_lenses,
+                             const r360_view* views, int32_t n_views, const r360_options* opt,
+                             void* workspace_device, size_t workspace_bytes, void* stream,
+                             r360_plan** plan_out);
+
+/* Tiles per view and how many (view, tile) pairs take the direct path. */
+int r360_plan_info(const r360_plan* plan, int32_t* tiles_per_view, int32_t* n_fallback_tiles);
+
+/* Same contract as r360_remap_erp / r360_remap_fisheye for the layout the plan was made for;
+ * R360_E_INVALID_ARG if src/dst do not match that layout. */
+int r360_remap_planned(const r360_plan* plan, const r360_images* src, const r360_images* dst,
+                       void* stream);
+
+/* Test/debug twin of r360_coords for the planned path (all five arrays as in r360_coords;
+ * the four map arrays are required). */
+int r360_plan_coords(const r360_plan* plan, float* map_x32, float* map_y32, double* map_x64,
+                     double* map_y64, uint8_t* valid, void* stream);
+
+void r360_plan_destroy(r360_plan* plan);
 
 /* Count of kernels this library has launched in the calling process (all threads). */
 int64_t r360_launch_count(void);

@@ -266,15 +266,11 @@ def test_row_pitch_and_strided_views_of_larger_buffers(r360, path):
     frames = big[:, :, 5:5 + W, :]                      # row pitch > W * C, unaligned start
     views = _views(r360, [(20, 10), (-160, -30)], fov=80.0)
     outbig = torch.zeros((2, 2, size, size + 8, 3), dtype=torch.uint8, device="cuda")
-    # write into a padded destination through the ABI directly
-    import ctypes
-    from remap360 import _lib, api
-    lib = _lib.load()
+    # write into a padded destination (row pitch > w * C) through the descriptor layer
+    from remap360 import api
     src = api._describe(frames, "frames")
     dst = api._describe(outbig.view(4, size, size + 8, 3)[:, :, :size, :], "out")
-    opt = api._options("linear", path=path)
-    _lib.check(lib.r360_remap_erp(ctypes.byref(src), ctypes.byref(dst), api._views_array(views), 2,
-                                  ctypes.byref(opt), torch.cuda.current_stream().cuda_stream))
+    api._run(src, dst, views, api._options("linear", path=path), path, frames.device, None)
     ref = r360.remap_erp(frames.contiguous(), views, (size, size), interp="linear", path=path)
     assert torch.equal(outbig[:, :, :, :size, :], ref)
     assert int(outbig[:, :, :, size:, :].abs().sum()) == 0     # padding untouched
