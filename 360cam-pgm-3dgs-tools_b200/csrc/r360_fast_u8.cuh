@@ -1,0 +1,114 @@
+// Packed-integer sampling of 8-bit 3-channel pixels from a staged shared-memory patch.
+//
+// Same arithmetic as the generic sampler (cv2.remap, DF:2001-2008) -- bit for bit -- but organised
+// for instruction count: taps are fetched as aligned 32-bit words and funnel-shifted into place,
+// channels are gathered with byte permutes, and the weighted sums run on dp4a / dp2a.
+//
+//   bilinear: weights (32-fx, fx) x (32-fy, fy) in units of 1/1024 (== cv2's 15-bit table / 32):
+//             horizontal pass with dp4a (8-bit weights), vertical pass with two IMAD, (s+512)>>10
+//   bicubic : cv2's 15-bit 4x4 table (shared-memory copy), rows of 4 taps with dp2a
+//             (16-bit weight pairs x 8-bit pixels), (s+16384)>>15, saturate
+#pragma once
+
+#include "r360_common.cuh"
+
+namespace r360 {
+
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ int dp2a_lo_s16_u8(uint32_t w_pair, uint32_t bytes, int acc) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w_pair), "r"(bytes), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_s16_u8(uint32_t w_pair, uint32_t bytes, int acc) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w_pair), "r"(bytes), "r"(acc));
+    return d;
+}
+
+// float (holding 32 * coordinate, |value| < 2^22) -> integer bits: adding 1.5 * 2^23 leaves the
+// round-half-even integer in the low mantissa bits (what cvRound does), on the full-rate FP32
+// pipe instead of the conversion unit.  Result = 0x4B400000 + rint(v).
+constexpr uint32_t kMagicBits = 0x4B400000u;
+__device__ __forceinline__ uint32_t round_bits(float v) { return __float_as_uint(__fadd_rn(v, 12582912.0f)); }
+
+// Address bias that turns (round_bits(x) >> 5, round_bits(y) >> 5) into a shared-memory byte
+// address of the top-left tap: patch + (iy - py0) * pitch + ix * 3 - xb0, with the magic offsets
+// folded in (32-bit wrap-around arithmetic).
+__device__ __forceinline__ uint32_t patch_bias_u8c3(uint32_t patch_saddr, int pitch, int xb0, int py0) {
+    const uint32_t m = kMagicBits >> 5;
+    return patch_saddr - (uint32_t)xb0 - (uint32_t)(py0 * pitch) - 3u * m - (uint32_t)pitch * m;
+}
+
+// One bilinear sample; returns R | G << 8 | B << 16.
+__device__ __forceinline__ uint32_t bilinear_u8c3(uint32_t bias, uint32_t pitch, uint32_t ux, uint32_t uy) {
+    const uint32_t fx = ux & 31u, fy = uy & 31u;
+    const uint32_t addr = (ux >> 5) * 3u + (uy >> 5) * pitch + bias;
+    const uint32_t a4 = addr & ~3u, sh = (addr & 3u) << 3;
+    const uint32_t t0 = lds32(a4), t1 = lds32(a4 + 4), t2 = lds32(a4 + 8);
+    const uint32_t b0 = lds32(a4 + pitch), b1 = lds32(a4 + pitch + 4), b2 = lds32(a4 + pitch + 8);
+    const uint32_t lo_t = __funnelshift_r(t0, t1, sh), hi_t = __funnelshift_r(t1, t2, sh);   // R0 G0 B0 R1 | G1 B1 . .
+    const uint32_t lo_b = __funnelshift_r(b0, b1, sh), hi_b = __funnelshift_r(b1, b2, sh);
+    const uint32_t rr = __byte_perm(lo_t, lo_b, 0x7430);      // R00 R01 R10 R11
+    const uint32_t gb_t = __byte_perm(lo_t, hi_t, 0x5241);    // G00 G01 B00 B01
+    const uint32_t gb_b = __byte_perm(lo_b, hi_b, 0x5241);    // G10 G11 B10 B11
+    const uint32_t w_lo = 32u + 255u * fx;                    // bytes (32 - fx, fx, 0, 0)
+    const uint32_t w_hi = w_lo << 16;                         // bytes (0, 0, 32 - fx, fx)
+    const uint32_t wy0 = 32u - fy;
+    const uint32_t r = (__dp4a(rr, w_lo, 0u) * wy0 + __dp4a(rr, w_hi, 0u) * fy + 512u) >> 10;
+    const uint32_t g = (__dp4a(gb_t, w_lo, 0u) * wy0 + __dp4a(gb_b, w_lo, 0u) * fy + 512u) >> 10;
+    const uint32_t b = (__dp4a(gb_t, w_hi, 0u) * wy0 + __dp4a(gb_b, w_hi, 0u) * fy + 512u) >> 10;
+    return r | (g << 8) | (b << 16);
+}
+
+// One bicubic sample; `table_saddr` is the shared-memory copy of cv2's fixed-point table
+// ([fy][fx][ky][kx] int16).  `bias` must address tap (ix - 1, iy - 1): pass the bilinear bias
+// minus (3 + pitch).  Returns R | G << 8 | B << 16.
+__device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, uint32_t table_saddr,
+                                                 uint32_t ux, uint32_t uy) {
+    const uint32_t fx = ux & 31u, fy = uy & 31u;
+    const uint32_t addr = (ux >> 5) * 3u + (uy >> 5) * pitch + bias;
+    uint32_t a4 = addr & ~3u;
+    const uint32_t sh = (addr & 3u) << 3;
+    const uint32_t wt = table_saddr + ((fy << 5) + fx) * 32u;
+    const uint4 wa = lds128(wt), wb = lds128(wt + 16);          // rows 0,1 | rows 2,3: (w0|w1<<16, w2|w3<<16) each
+    const uint32_t wrow[4][2] = {{wa.x, wa.y}, {wa.z, wa.w}, {wb.x, wb.y}, {wb.z, wb.w}};
+    int r = 16384, g = 16384, b = 16384;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+        const uint32_t q0 = lds32(a4), q1 = lds32(a4 + 4), q2 = lds32(a4 + 8), q3 = lds32(a4 + 12);
+        a4 += pitch;
+        const uint32_t p0 = __funnelshift_r(q0, q1, sh);       // R0 G0 B0 R1
+        const uint32_t p1 = __funnelshift_r(q1, q2, sh);       // G1 B1 R2 G2
+        const uint32_t p2 = __funnelshift_r(q2, q3, sh);       // B2 R3 G3 B3
+        const uint32_t rr = __byte_perm(__byte_perm(p0, p1, 0x0630), p2, 0x5210);   // R0 R1 R2 R3
+        const uint32_t gg = __byte_perm(__byte_perm(p0, p1, 0x0741), p2, 0x6210);   // G0 G1 G2 G3
+        const uint32_t bb = __byte_perm(__byte_perm(p0, p1, 0x0052), p2, 0x7410);   // B0 B1 B2 B3
+        r = dp2a_hi_s16_u8(wrow[ky][1], rr, dp2a_lo_s16_u8(wrow[ky][0], rr, r));
+        g = dp2a_hi_s16_u8(wrow[ky][1], gg, dp2a_lo_s16_u8(wrow[ky][0], gg, g));
+        b = dp2a_hi_s16_u8(wrow[ky][1], bb, dp2a_lo_s16_u8(wrow[ky][0], bb, b));
+    }
+    r = min(max(r >> 15, 0), 255);
+    g = min(max(g >> 15, 0), 255);
+    b = min(max(b >> 15, 0), 255);
+    return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+}
+
+// Four RGB pixels (each R | G<<8 | B<<16) -> three packed words = 12 output bytes.
+__device__ __forceinline__ void pack4_rgb(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3,
+                                          uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+    w0 = __byte_perm(p0, p1, 0x4210);     // R0 G0 B0 R1
+    w1 = __byte_perm(p1, p2, 0x5421);     // G1 B1 R2 G2
+    w2 = __byte_perm(p2, p3, 0x6542);     // B2 R3 G3 B3
+}
+
+}  // namespace r360

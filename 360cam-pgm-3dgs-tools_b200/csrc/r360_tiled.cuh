@@ -26,6 +26,7 @@
 #include "r360_common.cuh"
 #include "r360_direct.cuh"
 #include "r360_sample.cuh"
+#include "r360_fast_u8.cuh"
 
 namespace r360 {
 
@@ -270,136 +271,251 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- the remap kernel -------------------------------------------------------------------------------
+//
+// Persistent, warp-specialised: each block loops over (frame, view, tile) work items with a
+// producer warp that stages the NEXT item (plan record + source patch, bulk-async copies
+// completing on an mbarrier) while eight consumer warps sample the CURRENT one; the output tile
+// is double-buffered in shared memory and leaves as bulk-async row stores.
 
 struct TiledParams {
     ImageSetDev src, dst;
     int channels;
-    int n_views;            // views per source group covered by this launch
-    int view_base;          // first of them within the plan / the destination
-    int n_views_total;      // destination images per group
+    int n_views;            // views per source group
+    int n_groups;           // source groups (frames) in this launch
     int n_lenses;
     int tiles_x, tiles_y;
     int out_stage_bytes;    // kTile * kTile * channels * sizeof(TOut), rounded up to 128
+    int patch_budget;       // bytes per patch buffer (multiple of 128)
     int bulk_store_ok;      // destination layout allows 16-byte aligned row stores
+    int use_table;          // copy the fixed-point cubic table into shared memory
     float border_value;
     const TilePlan* plans;  // whole plan (all views)
-    // debug outputs (r360_plan_coords); all null in production launches
-    float* dbg_x32; float* dbg_y32; double* dbg_x64; double* dbg_y64; unsigned char* dbg_valid;
 };
 
-constexpr int kTiledFixedSmem = 320 + 1536 + 64;    // plan copy, row coefficients, mbarrier (+pad) = 1920
+constexpr int kConsumerThreads = 256;
+constexpr int kTiledThreads = kConsumerThreads + 32;
+constexpr int kTiledFixedSmem = 128 + 1536 + 2 * 320 + 128;     // barriers, row coefficients, 2 plan records, pad = 2432
+constexpr int kTableBytes = 32 * 32 * 16 * 2;
+
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 template <int INTERP, typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) remap_tiled_kernel(const __grid_constant__ TiledParams P) {
+__global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid_constant__ TiledParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
-    TilePlan* plan = reinterpret_cast<TilePlan*>(smem);
-    float* rowc = reinterpret_cast<float*>(smem + 320);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 320 + 1536);
-    unsigned char* out_stage = smem + kTiledFixedSmem;
-    unsigned char* patch = out_stage + P.out_stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [2]
+    uint64_t* empty = full + 2;                                    // [2]
+    float* rowc = reinterpret_cast<float*>(smem + 128);
+    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 128 + 1536);
+    unsigned char* table = smem + kTiledFixedSmem;
+    unsigned char* stage0 = table + (P.use_table ? kTableBytes : 0);
+    unsigned char* patch0 = stage0 + 2 * P.out_stage_bytes;
 
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-    const int v = blockIdx.y % P.n_views, g = blockIdx.y / P.n_views;
-    const int i0 = (tile % P.tiles_x) * kTile, j0 = (tile / P.tiles_x) * kTile;
-    const bool debug = P.dbg_x32 != nullptr;
+    const int n_tiles = P.tiles_x * P.tiles_y;
+    const long long total = (long long)P.n_groups * P.n_views * n_tiles;
 
-    // plan record -> shared memory (20 x 16 bytes)
-    {
-        const int4* gp = reinterpret_cast<const int4*>(P.plans + (long long)(P.view_base + v) * (P.tiles_x * P.tiles_y) + tile);
-        if (tid < 20) reinterpret_cast<int4*>(plan)[tid] = __ldg(gp + tid);
-        if (tid == 32) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (tid == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+        fence_mbar_init();
+    }
+    if (P.use_table) {
+        const int4* src = reinterpret_cast<const int4*>(g_tables.cubic_fixed);
+        for (int q = tid; q < kTableBytes / 16; q += kTiledThreads) reinterpret_cast<int4*>(table)[q] = __ldg(src + q);
     }
     __syncthreads();
-    const int mode = plan->mode_slot & 0xff, slot = plan->mode_slot >> 8;
-    if (mode == kModeFallback) return;                      // remap_fallback_kernel owns this tile
 
-    const int jl = tid >> 3;                 // tile row of this thread
-    const int il0 = (tid & 7) * 4;           // first of its 4 pixels
-    const long long dst_img = (long long)g * P.n_views_total + P.view_base + v;
-    unsigned char* dst_base = P.dst.data + dst_img * P.dst.image_stride;
-    TOut* stage_row = reinterpret_cast<TOut*>(out_stage) + (jl * kTile + il0) * P.channels;
-
-    if (mode == kModeFill) {
-        if (debug) return;     // an all-invalid tile: the debug twin of the fallback kernel reports it
-        for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
-    } else {
-        // ---- stage the source patch (warp 0) --------------------------------------------------
-        if (!debug && tid < 32) {
-            const unsigned char* img = P.src.data + ((long long)g * P.n_lenses + slot) * P.src.image_stride;
-            if (tid == 0) mbar_expect_tx(bar, (uint32_t)(plan->rows * plan->row_bytes));
+    if (tid >= kConsumerThreads) {
+        // ================= producer warp ==========================================================
+        const int lane = tid - kConsumerThreads;
+        int k = 0;
+        for (long long w = blockIdx.x; w < total; w += gridDim.x, ++k) {
+            const int b = k & 1, use = k >> 1;
+            if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);
+            const int tile = (int)(w % n_tiles);
+            const int unit = (int)(w / n_tiles);
+            const int v = unit % P.n_views, g = unit / P.n_views;
+            const TilePlan* gp = P.plans + (long long)v * n_tiles + tile;
+            const int4 geo0 = __ldg(reinterpret_cast<const int4*>(gp) + 18);   // x0 y0 py0 rows
+            const int4 geo1 = __ldg(reinterpret_cast<const int4*>(gp) + 19);   // xb0 row_bytes pitch mode_slot
+            const int mode = geo1.w & 0xff, slot = geo1.w >> 8;
+            const int py0 = geo0.z, rows = mode == kModeFast ? geo0.w : 0;
+            const int xb0 = geo1.x, row_bytes = geo1.y, pitch = geo1.z;
+            if (lane == 0) {
+                mbar_expect_tx(&full[b], (uint32_t)(sizeof(TilePlan) + rows * row_bytes));
+                bulk_g2s(&planbuf[b], gp, (uint32_t)sizeof(TilePlan), &full[b]);
+            }
             __syncwarp();
-            for (int r = tid; r < plan->rows; r += 32) {
-                const int sy = min(max(plan->py0 + r, 0), P.src.height - 1);     // pole rows replicate
-                bulk_g2s(patch + r * plan->pitch, img + (long long)sy * P.src.pitch + plan->xb0,
-                         (uint32_t)plan->row_bytes, bar);
+            const unsigned char* img = P.src.data + ((long long)g * P.n_lenses + slot) * P.src.image_stride;
+            unsigned char* patch = patch0 + b * P.patch_budget;
+            for (int r = lane; r < rows; r += 32) {
+                const int sy = min(max(py0 + r, 0), P.src.height - 1);            // pole rows replicate
+                bulk_g2s(patch + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[b]);
             }
         }
-        // ---- per-row polynomial coefficients (all threads) ----------------------------------
-        for (int task = tid; task < kTile * 12; task += 256) {
-            const int row = task / 12, c = task % 12;
-            const float* K = c < 6 ? plan->kx : plan->ky;
-            const int k = c % 6;
-            const float t = (float)(2 * row - (kTile - 1)) * (1.0f / (kTile - 1));
-            float a = K[5 * 6 + k];
-#pragma unroll
-            for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6 + k]);
-            rowc[row * 12 + c] = a;
-        }
-        __syncthreads();
-        if (!debug) mbar_wait(bar, 0);
-
-        // ---- pixels ---------------------------------------------------------------------------
-        const float X0 = (float)(plan->x0 * 32), Y0 = (float)(plan->y0 * 32);
-        const float* rc = rowc + jl * 12;
-        const PatchTaps<TIn> taps{patch, plan->pitch, plan->xb0, plan->py0, P.channels};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float s = (float)(2 * (il0 + q) - (kTile - 1)) * (1.0f / (kTile - 1));
-            float dx = rc[5], dy = rc[11];
-#pragma unroll
-            for (int k = 4; k >= 0; --k) { dx = fmaf(dx, s, rc[k]); dy = fmaf(dy, s, rc[6 + k]); }
-            // 32 * float32(x): the rounding of this add is the float32 cast cv2.remap's map would see
-            const float sxf = __fadd_rn(dx, X0), syf = __fadd_rn(dy, Y0);
-            if (debug) {
-                const int i = i0 + il0 + q, j = j0 + jl;
-                if (i < P.dst.width && j < P.dst.height) {
-                    const long long o = ((long long)(P.view_base + v) * P.dst.height + j) * P.dst.width + i;
-                    P.dbg_x32[o] = sxf * (1.0f / 32.0f); P.dbg_y32[o] = syf * (1.0f / 32.0f);
-                    P.dbg_x64[o] = (double)plan->x0 + (double)dx * (1.0 / 32.0);
-                    P.dbg_y64[o] = (double)plan->y0 + (double)dy * (1.0 / 32.0);
-                    if (P.dbg_valid) P.dbg_valid[o] = 1;
-                }
-                continue;
-            }
-            sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
-                                            sxf * (1.0f / 32.0f), syf * (1.0f / 32.0f), stage_row + q * P.channels);
-        }
-        if (debug) return;
+        return;
     }
 
-    // ---- store the tile ----------------------------------------------------------------------------
+    // ================= consumer warps ================================================================
+    const int jl = tid >> 3;                 // tile row of this thread
+    const int il0 = (tid & 7) * 4;           // first of its 4 pixels
     const int row_out_bytes = kTile * P.channels * (int)sizeof(TOut);
-    const bool full = i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height;
-    if (full && P.bulk_store_ok) {
-        fence_async_shared();
-        __syncthreads();
-        if (tid < kTile) {
-            bulk_s2g(dst_base + (long long)(j0 + tid) * P.dst.pitch + (long long)i0 * P.channels * sizeof(TOut),
-                     out_stage + tid * row_out_bytes, (uint32_t)row_out_bytes);
-            bulk_commit();
-            bulk_wait_read_all();
+    int k = 0;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x, ++k) {
+        const int b = k & 1, use = k >> 1;
+        const int tile = (int)(w % n_tiles);
+        const int unit = (int)(w / n_tiles);
+        const int i0 = (tile % P.tiles_x) * kTile, j0 = (tile / P.tiles_x) * kTile;
+        mbar_wait(&full[b], use & 1);
+        const TilePlan* plan = &planbuf[b];
+        const int mode = plan->mode_slot & 0xff;
+        unsigned char* stage = stage0 + b * P.out_stage_bytes;
+        const unsigned char* patch = patch0 + b * P.patch_budget;
+
+        if (mode == kModeFast) {
+            for (int task = tid; task < kTile * 12; task += kConsumerThreads) {
+                const int row = task / 12, c = task % 12;
+                const float* K = c < 6 ? plan->kx : plan->ky;
+                const int kk = c % 6;
+                const float t = (float)(2 * row - (kTile - 1)) * (1.0f / (kTile - 1));
+                float a = K[5 * 6 + kk];
+#pragma unroll
+                for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6 + kk]);
+                rowc[row * 12 + c] = a;
+            }
         }
-    } else {
-        __syncthreads();
-        const int nelem = kTile * P.channels;
-        for (int e = tid; e < kTile * nelem; e += 256) {
-            const int r = e / nelem, c = e % nelem;
-            const int i = i0 + c / P.channels, j = j0 + r;
-            if (i < P.dst.width && j < P.dst.height)
-                reinterpret_cast<TOut*>(dst_base + (long long)j * P.dst.pitch)[(long long)i0 * P.channels + c] =
-                    reinterpret_cast<const TOut*>(out_stage)[r * nelem + c];
+        if (tid < kTile) bulk_wait_read_1();       // the stores that last read this stage buffer are done
+        consumer_barrier();
+
+        if (mode != kModeFallback) {
+            TOut* stage_row = reinterpret_cast<TOut*>(stage) + (jl * kTile + il0) * P.channels;
+            if (mode == kModeFill) {
+                for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
+            } else {
+                const float X0 = (float)(plan->x0 * 32), Y0 = (float)(plan->y0 * 32);
+                const float* rc = rowc + jl * 12;
+                float sxf[4], syf[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float s = (float)(2 * (il0 + q) - (kTile - 1)) * (1.0f / (kTile - 1));
+                    float dx = rc[5], dy = rc[11];
+#pragma unroll
+                    for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
+                    // 32 * float32(x): the rounding of this add is the float32 cast cv2.remap's map would see
+                    sxf[q] = __fadd_rn(dx, X0); syf[q] = __fadd_rn(dy, Y0);
+                }
+                bool done = false;
+                if constexpr (std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
+                              INTERP != kNearest) {
+                    if (P.channels == 3) {
+                        uint32_t bias = patch_bias_u8c3(smem_u32(patch), plan->pitch, plan->xb0, plan->py0);
+                        uint32_t px[4];
+                        if constexpr (INTERP == kLinear) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                px[q] = bilinear_u8c3(bias, (uint32_t)plan->pitch, round_bits(sxf[q]), round_bits(syf[q]));
+                        } else {
+                            bias -= 3u + (uint32_t)plan->pitch;
+                            const uint32_t tab = smem_u32(table);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                px[q] = bicubic_u8c3(bias, (uint32_t)plan->pitch, tab, round_bits(sxf[q]), round_bits(syf[q]));
+                        }
+                        uint32_t w0, w1, w2;
+                        pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
+                        uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
+                        o[0] = w0; o[1] = w1; o[2] = w2;
+                        done = true;
+                    }
+                }
+                if (!done) {
+                    const PatchTaps<TIn> taps{patch, plan->pitch, plan->xb0, plan->py0, P.channels};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
+                                                        sxf[q] * (1.0f / 32.0f), syf[q] * (1.0f / 32.0f),
+                                                        stage_row + q * P.channels);
+                }
+            }
+            const int v = unit % P.n_views, g = unit / P.n_views;
+            unsigned char* dst_base = P.dst.data + ((long long)g * P.n_views + v) * P.dst.image_stride;
+            const bool full_tile = i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height;
+            if (full_tile && P.bulk_store_ok) {
+                fence_async_shared();
+                consumer_barrier();
+                if (tid < kTile) {
+                    bulk_s2g(dst_base + (long long)(j0 + tid) * P.dst.pitch + (long long)i0 * P.channels * sizeof(TOut),
+                             stage + tid * row_out_bytes, (uint32_t)row_out_bytes);
+                }
+            } else {
+                consumer_barrier();
+                const int nelem = kTile * P.channels;
+                for (int e = tid; e < kTile * nelem; e += kConsumerThreads) {
+                    const int r = e / nelem, c = e % nelem;
+                    const int i = i0 + c / P.channels, j = j0 + r;
+                    if (i < P.dst.width && j < P.dst.height)
+                        reinterpret_cast<TOut*>(dst_base + (long long)j * P.dst.pitch)[(long long)i0 * P.channels + c] =
+                            reinterpret_cast<const TOut*>(stage)[r * nelem + c];
+                }
+                consumer_barrier();
+            }
+        } else {
+            consumer_barrier();
         }
+        if (tid < kTile) bulk_commit();            // one (possibly empty) group per iteration keeps the count in step
+        if (tid == 0) mbar_arrive(&empty[b]);      // patch / plan buffer b may be refilled
+    }
+    if (tid < kTile) bulk_wait_read_all();
+}
+
+// Debug twin: what the tiled kernel samples at, written as maps (r360_plan_coords).  One block per
+// (tile, view); only fast tiles write (the caller pre-fills everything from the direct path).
+struct TiledCoordParams {
+    int out_w, out_h, tiles_x, tiles_y;
+    const TilePlan* plans;
+    float* x32; float* y32; double* x64; double* y64; unsigned char* valid;
+};
+
+__global__ void __launch_bounds__(256) coords_tiled_kernel(const __grid_constant__ TiledCoordParams P) {
+    __shared__ TilePlan plan;
+    __shared__ float rowc[kTile * 12];
+    const int tid = threadIdx.x, tile = blockIdx.x, v = blockIdx.y;
+    const int i0 = (tile % P.tiles_x) * kTile, j0 = (tile / P.tiles_x) * kTile;
+    const int4* gp = reinterpret_cast<const int4*>(P.plans + (long long)v * (P.tiles_x * P.tiles_y) + tile);
+    if (tid < 20) reinterpret_cast<int4*>(&plan)[tid] = __ldg(gp + tid);
+    __syncthreads();
+    if ((plan.mode_slot & 0xff) != kModeFast) return;
+    for (int task = tid; task < kTile * 12; task += 256) {
+        const int row = task / 12, c = task % 12;
+        const float* K = c < 6 ? plan.kx : plan.ky;
+        const int kk = c % 6;
+        const float t = (float)(2 * row - (kTile - 1)) * (1.0f / (kTile - 1));
+        float a = K[5 * 6 + kk];
+#pragma unroll
+        for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6 + kk]);
+        rowc[row * 12 + c] = a;
+    }
+    __syncthreads();
+    const int jl = tid >> 3, il0 = (tid & 7) * 4;
+    const float X0 = (float)(plan.x0 * 32), Y0 = (float)(plan.y0 * 32);
+    const float* rc = rowc + jl * 12;
+    for (int q = 0; q < 4; ++q) {
+        const int i = i0 + il0 + q, j = j0 + jl;
+        if (i >= P.out_w || j >= P.out_h) continue;
+        const float s = (float)(2 * (il0 + q) - (kTile - 1)) * (1.0f / (kTile - 1));
+        float dx = rc[5], dy = rc[11];
+#pragma unroll
+        for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
+        const float sxf = __fadd_rn(dx, X0), syf = __fadd_rn(dy, Y0);
+        const long long o = ((long long)v * P.out_h + j) * P.out_w + i;
+        P.x32[o] = sxf * (1.0f / 32.0f); P.y32[o] = syf * (1.0f / 32.0f);
+        P.x64[o] = (double)plan.x0 + (double)dx * (1.0 / 32.0);
+        P.y64[o] = (double)plan.y0 + (double)dy * (1.0 / 32.0);
+        if (P.valid) P.valid[o] = 1;
     }
 }
 

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -318,8 +319,6 @@ int remap_direct(int proj, const r360_images* src, const r360_images* dst, const
 
 // ---- plans ------------------------------------------------------------------------------------------
 
-// Shared memory per block for the tiled kernel: aim for 4 resident blocks per SM.
-constexpr int kSmemPerBlockTarget = 56 * 1024 - 1024;
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -343,7 +342,7 @@ struct r360_plan {
     r360_images src_layout, dst_layout;
     std::vector<ViewDev> views;
     int tiles_x, tiles_y, n_tiles, n_fallback;
-    int out_stage_bytes, patch_budget, smem_bytes;
+    int out_stage_bytes, patch_budget, smem_bytes, ctas_per_sm, use_table, sm_count;
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
     PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback;
@@ -377,9 +376,28 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     for (int v = 0; v < n_views; ++v) make_view(views[v], dst->width, dst->height, &pl->views[v]);
     const int out_es = elem_size(pl->pr.out_dt), in_es = elem_size(pl->pr.in_dt);
     pl->out_stage_bytes = (int)align_up((size_t)kTile * kTile * dst->channels * out_es, 128);
-    pl->patch_budget = kSmemPerBlockTarget - kTiledFixedSmem - pl->out_stage_bytes;
-    if (pl->patch_budget < 8192) pl->patch_budget = 8192;
-    pl->smem_bytes = kTiledFixedSmem + pl->out_stage_bytes + pl->patch_budget;
+    // Shared memory per block: barriers/coefficients/plan records, (8-bit bicubic) the 32 KB weight
+    // table, two output tiles, two patch buffers.  The patch budget follows from how many blocks
+    // should be resident per SM; tiles whose patch is larger take the fallback path.
+    pl->use_table = (pl->pr.in_dt == R360_U8 && pl->pr.interp == R360_CUBIC && dst->channels == 3) ? 1 : 0;
+    {
+        int dev = 0, smem_per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        int want = pl->use_table ? 2 : 4;
+        if (const char* env = std::getenv("R360_TILED_CTAS_PER_SM")) want = std::atoi(env) > 0 ? std::atoi(env) : want;
+        const int fixed = kTiledFixedSmem + (pl->use_table ? kTableBytes : 0) + 2 * pl->out_stage_bytes + 128;
+        for (;; --want) {
+            const int per_block = smem_per_sm / want - 1024;       // 1 KB per block is reserved by the driver
+            pl->patch_budget = ((per_block - fixed) / 2) & ~127;
+            if (pl->patch_budget >= 12 * 1024 || want == 1) break;
+        }
+        if (pl->patch_budget < 4096) pl->patch_budget = 4096;
+        if (pl->patch_budget > 96 * 1024) pl->patch_budget = 96 * 1024;
+        pl->ctas_per_sm = want;
+        pl->smem_bytes = fixed + 2 * pl->patch_budget;
+    }
     // the data pointers are not known yet: assume 16-byte aligned bases (checked at remap time)
     pl->bulk_load_ok = src->pitch_bytes % 16 == 0 && src->image_stride_bytes % 16 == 0 &&
                        ((int64_t)src->width * src->channels * in_es) % 16 == 0;
@@ -424,25 +442,19 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
 
 struct TiledLauncher {
     const r360_plan* pl; const r360_images* src; const r360_images* dst; cudaStream_t s;
-    float* dx32; float* dy32; double* dx64; double* dy64; unsigned char* dvalid;
 
     template <int PROJ, int INTERP, typename TIn, typename TOut> int run() {
-        const bool debug = dx32 != nullptr;
         const LaunchParams& lp = pl->pr.lp;
-        const int n_groups = debug ? 1 : src->count / pl->pr.n_lenses;
+        const int n_groups = src->count / pl->pr.n_lenses;
         TiledParams T;
         std::memset(&T, 0, sizeof(T));
-        if (!debug) {
-            T.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
-            T.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
-        } else {
-            T.src = lp.src; T.dst = lp.dst;
-        }
-        T.channels = lp.channels; T.n_views = pl->pr.n_views; T.view_base = 0; T.n_views_total = pl->pr.n_views;
+        T.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
+        T.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
+        T.channels = lp.channels; T.n_views = pl->pr.n_views; T.n_groups = n_groups;
         T.n_lenses = pl->pr.n_lenses; T.tiles_x = pl->tiles_x; T.tiles_y = pl->tiles_y;
-        T.out_stage_bytes = pl->out_stage_bytes; T.bulk_store_ok = pl->bulk_store_ok; T.border_value = lp.border_value;
+        T.out_stage_bytes = pl->out_stage_bytes; T.patch_budget = pl->patch_budget;
+        T.bulk_store_ok = pl->bulk_store_ok; T.use_table = pl->use_table; T.border_value = lp.border_value;
         T.plans = pl->d_plans;
-        T.dbg_x32 = dx32; T.dbg_y32 = dy32; T.dbg_x64 = dx64; T.dbg_y64 = dy64; T.dbg_valid = dvalid;
 
         auto kernel = remap_tiled_kernel<INTERP, TIn, TOut>;
         static thread_local int configured_smem = -1;     // per instantiation and thread
@@ -450,19 +462,14 @@ struct TiledLauncher {
             R360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
             configured_smem = pl->smem_bytes;
         }
-        const int max_groups = 65535 / pl->pr.n_views > 0 ? 65535 / pl->pr.n_views : 1;
-        for (int g0 = 0; g0 < n_groups; g0 += max_groups) {
-            TiledParams Q = T;
-            const int ng = n_groups - g0 < max_groups ? n_groups - g0 : max_groups;
-            if (!debug) {
-                Q.src.data += (long long)g0 * pl->pr.n_lenses * Q.src.image_stride;
-                Q.dst.data += (long long)g0 * pl->pr.n_views * Q.dst.image_stride;
-            }
-            kernel<<<dim3(pl->n_tiles, ng * pl->pr.n_views), 256, pl->smem_bytes, s>>>(Q);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            R360_CUDA(cudaGetLastError());
-        }
-        if (pl->n_fallback > 0 && !debug) {
+        const long long total = (long long)n_groups * pl->pr.n_views * pl->n_tiles;
+        long long grid = (long long)pl->sm_count * pl->ctas_per_sm;
+        if (grid > total) grid = total;
+        kernel<<<dim3((unsigned)grid), kTiledThreads, pl->smem_bytes, s>>>(T);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        R360_CUDA(cudaGetLastError());
+
+        if (pl->n_fallback > 0) {
             FallbackParams F;
             std::memset(&F, 0, sizeof(F));
             F.lp = lp;
@@ -617,7 +624,7 @@ int r360_remap_planned(const r360_plan* plan, const r360_images* src, const r360
         return R360_E_INVALID_ARG;
     if (plan->bulk_store_ok && !aligned16(dst->data, dst->pitch_bytes, dst->count > 1 ? dst->image_stride_bytes : 0))
         return R360_E_INVALID_ARG;
-    TiledLauncher L{plan, src, dst, static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, nullptr, nullptr};
+    TiledLauncher L{plan, src, dst, static_cast<cudaStream_t>(stream)};
     return dispatch(plan->pr.proj, plan->pr.interp, plan->pr.in_dt, plan->pr.out_dt, L);
 }
 
@@ -643,11 +650,15 @@ int r360_plan_coords(const r360_plan* plan, float* map_x32, float* map_y32, doub
         g_launches.fetch_add(1, std::memory_order_relaxed);
         R360_CUDA(cudaGetLastError());
     }
-    r360_plan dbg = *plan;      // shallow copy: give the launcher a destination size to index with
-    dbg.pr.lp.dst.width = p.out_w; dbg.pr.lp.dst.height = p.out_h;
-    dbg.pr.lp.src.width = plan->src_layout.width; dbg.pr.lp.src.height = plan->src_layout.height;
-    TiledLauncher L{&dbg, nullptr, nullptr, s, map_x32, map_y32, map_x64, map_y64, valid};
-    return dispatch(plan->pr.proj, plan->pr.interp, plan->pr.in_dt, plan->pr.out_dt, L);
+    TiledCoordParams T;
+    std::memset(&T, 0, sizeof(T));
+    T.out_w = p.out_w; T.out_h = p.out_h; T.tiles_x = plan->tiles_x; T.tiles_y = plan->tiles_y;
+    T.plans = plan->d_plans;
+    T.x32 = map_x32; T.y32 = map_y32; T.x64 = map_x64; T.y64 = map_y64; T.valid = valid;
+    coords_tiled_kernel<<<dim3(plan->n_tiles, n_views), 256, 0, s>>>(T);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    R360_CUDA(cudaGetLastError());
+    return R360_OK;
 }
 
 void r360_plan_destroy(r360_plan* plan) { delete plan; }
