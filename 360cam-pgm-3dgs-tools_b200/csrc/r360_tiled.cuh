@@ -247,7 +247,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0xF4240;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return done != 0;
@@ -256,7 +256,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     // try_wait suspends for a hardware time slice per call; a copy that never completes is a
     // bug, so trap instead of hanging the device
     for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 24)) __trap();
+        if (spins > 20000u) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -272,10 +272,16 @@ __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy
 
 // ---- the remap kernel -------------------------------------------------------------------------------
 //
-// Persistent, warp-specialised: each block loops over (frame, view, tile) work items with a
-// producer warp that stages the NEXT item (plan record + source patch, bulk-async copies
-// completing on an mbarrier) while eight consumer warps sample the CURRENT one; the output tile
-// is double-buffered in shared memory and leaves as bulk-async row stores.
+// Persistent and warp-specialised.  Each block walks (frame, view, tile) work items:
+//   * one producer warp runs ahead: it reads the next item's patch geometry from the plan, carves
+//     space out of a shared-memory ring (variable-size patches, up to 8 items in flight), arms the
+//     item's mbarrier with the byte count and issues the bulk-async copies (plan record + one copy
+//     per patch row);
+//   * eight consumer warps each own 4 rows of every tile and never synchronise with one another:
+//     wait for the item's mbarrier, derive the 4 rows' polynomial coefficients, sample 4 pixels
+//     per lane, write their rows of the output tile to a per-warp double-buffered stage and send
+//     them off as bulk-async row stores; the last reader of a patch releases it to the producer
+//     through a second mbarrier (8 arrivals).
 
 struct TiledParams {
     ImageSetDev src, dst;
@@ -285,19 +291,21 @@ struct TiledParams {
     int n_lenses;
     int tiles_x, tiles_y;
     int out_stage_bytes;    // kTile * kTile * channels * sizeof(TOut), rounded up to 128
-    int patch_budget;       // bytes per patch buffer (multiple of 128)
+    int ring_bytes;         // shared-memory ring for patches (multiple of 128)
     int bulk_store_ok;      // destination layout allows 16-byte aligned row stores
     int use_table;          // copy the fixed-point cubic table into shared memory
     float border_value;
     const TilePlan* plans;  // whole plan (all views)
 };
 
-constexpr int kConsumerThreads = 256;
+constexpr int kSlots = 8;                               // work items in flight per block
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kTiledThreads = kConsumerThreads + 32;
-constexpr int kTiledFixedSmem = 128 + 1536 + 2 * 320 + 128;     // barriers, row coefficients, 2 plan records, pad = 2432
+// barriers (128) + ring bookkeeping (128) + row coefficients (1536) + plan records (8 x 320)
+constexpr int kTiledFixedSmem = 128 + 128 + 1536 + kSlots * 320;      // 4352
 constexpr int kTableBytes = 32 * 32 * 16 * 2;
 
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -306,21 +314,22 @@ __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk
 template <int INTERP, typename TIn, typename TOut>
 __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid_constant__ TiledParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [2]
-    uint64_t* empty = full + 2;                                    // [2]
-    float* rowc = reinterpret_cast<float*>(smem + 128);
-    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 128 + 1536);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [kSlots]
+    uint64_t* empty = full + kSlots;                               // [kSlots]
+    int* slot_off = reinterpret_cast<int*>(smem + 128);            // [kSlots] ring offset of the item's patch
+    int* slot_size = slot_off + kSlots;                            // [kSlots] bytes to give back on release
+    float* rowc = reinterpret_cast<float*>(smem + 256);            // [32 rows][12]
+    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 256 + 1536);
     unsigned char* table = smem + kTiledFixedSmem;
     unsigned char* stage0 = table + (P.use_table ? kTableBytes : 0);
-    unsigned char* patch0 = stage0 + 2 * P.out_stage_bytes;
+    unsigned char* ring = stage0 + 2 * P.out_stage_bytes;
 
     const int tid = threadIdx.x;
     const int n_tiles = P.tiles_x * P.tiles_y;
-    const long long total = (long long)P.n_groups * P.n_views * n_tiles;
+    const int total = P.n_groups * P.n_views * n_tiles;             // the host keeps this below 2^31
 
     if (tid == 0) {
-        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-        mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+        for (int q = 0; q < kSlots; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], kConsumerWarps); }
         fence_mbar_init();
     }
     if (P.use_table) {
@@ -332,144 +341,170 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
     if (tid >= kConsumerThreads) {
         // ================= producer warp ==========================================================
         const int lane = tid - kConsumerThreads;
+        int head = 0, used = 0, oldest = 0;       // ring state, identical in every lane
         int k = 0;
-        for (long long w = blockIdx.x; w < total; w += gridDim.x, ++k) {
-            const int b = k & 1, use = k >> 1;
-            if (use > 0) mbar_wait(&empty[b], (use - 1) & 1);
-            const int tile = (int)(w % n_tiles);
-            const int unit = (int)(w / n_tiles);
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++k) {
+            const int slot = k & (kSlots - 1);
+            const int tile = item % n_tiles, unit = item / n_tiles;
             const int v = unit % P.n_views, g = unit / P.n_views;
             const TilePlan* gp = P.plans + (long long)v * n_tiles + tile;
             const int4 geo0 = __ldg(reinterpret_cast<const int4*>(gp) + 18);   // x0 y0 py0 rows
             const int4 geo1 = __ldg(reinterpret_cast<const int4*>(gp) + 19);   // xb0 row_bytes pitch mode_slot
-            const int mode = geo1.w & 0xff, slot = geo1.w >> 8;
+            const int mode = geo1.w & 0xff, src_slot = geo1.w >> 8;
             const int py0 = geo0.z, rows = mode == kModeFast ? geo0.w : 0;
             const int xb0 = geo1.x, row_bytes = geo1.y, pitch = geo1.z;
-            if (lane == 0) {
-                mbar_expect_tx(&full[b], (uint32_t)(sizeof(TilePlan) + rows * row_bytes));
-                bulk_g2s(&planbuf[b], gp, (uint32_t)sizeof(TilePlan), &full[b]);
+            const int need = (rows * pitch + 127) & ~127;
+            // ---- find room: FIFO ring, items are released in order ----------------------------
+            int off = 0, charge = 0;
+            for (;;) {
+                bool ok = (k - oldest) < kSlots;
+                if (ok) {
+                    if (used == 0) head = 0;
+                    const int tail = oldest < k ? slot_off[oldest & (kSlots - 1)] : head;
+                    if (need == 0) { off = head; charge = 0; }
+                    else if (used == 0 || head > tail) {
+                        if (head + need <= P.ring_bytes) { off = head; charge = need; }
+                        else if (need <= tail) { off = 0; charge = need + (P.ring_bytes - head); }
+                        else ok = false;
+                    } else if (head < tail) {
+                        if (head + need <= tail) { off = head; charge = need; } else ok = false;
+                    } else ok = false;                                   // head == tail with bytes in use: full
+                }
+                if (ok) break;
+                mbar_wait(&empty[oldest & (kSlots - 1)], (oldest / kSlots) & 1);
+                used -= slot_size[oldest & (kSlots - 1)];
+                ++oldest;
             }
             __syncwarp();
-            const unsigned char* img = P.src.data + ((long long)g * P.n_lenses + slot) * P.src.image_stride;
-            unsigned char* patch = patch0 + b * P.patch_budget;
+            if (lane == 0) {
+                slot_off[slot] = off; slot_size[slot] = charge;
+                mbar_expect_tx(&full[slot], (uint32_t)(sizeof(TilePlan) + rows * row_bytes));
+                bulk_g2s(&planbuf[slot], gp, (uint32_t)sizeof(TilePlan), &full[slot]);
+            }
+            __syncwarp();
+            used += charge;
+            head = off + need;
+            const unsigned char* img = P.src.data + ((long long)g * P.n_lenses + src_slot) * P.src.image_stride;
+            unsigned char* patch = ring + off;
             for (int r = lane; r < rows; r += 32) {
                 const int sy = min(max(py0 + r, 0), P.src.height - 1);            // pole rows replicate
-                bulk_g2s(patch + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[b]);
+                bulk_g2s(patch + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[slot]);
             }
         }
         return;
     }
 
     // ================= consumer warps ================================================================
-    const int jl = tid >> 3;                 // tile row of this thread
+    const int warp = tid >> 5, lane = tid & 31;
+    const int jl = tid >> 3;                 // tile row of this thread (4 rows per warp)
     const int il0 = (tid & 7) * 4;           // first of its 4 pixels
     const int row_out_bytes = kTile * P.channels * (int)sizeof(TOut);
+    float* rc = rowc + jl * 12;
     int k = 0;
-    for (long long w = blockIdx.x; w < total; w += gridDim.x, ++k) {
-        const int b = k & 1, use = k >> 1;
-        const int tile = (int)(w % n_tiles);
-        const int unit = (int)(w / n_tiles);
-        const int i0 = (tile % P.tiles_x) * kTile, j0 = (tile / P.tiles_x) * kTile;
-        mbar_wait(&full[b], use & 1);
-        const TilePlan* plan = &planbuf[b];
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++k) {
+        const int slot = k & (kSlots - 1);
+        mbar_wait(&full[slot], (k / kSlots) & 1);
+        const TilePlan* plan = &planbuf[slot];
         const int mode = plan->mode_slot & 0xff;
-        unsigned char* stage = stage0 + b * P.out_stage_bytes;
-        const unsigned char* patch = patch0 + b * P.patch_budget;
-
+        if (mode == kModeFallback) {                       // remap_fallback_kernel owns this tile
+            if (lane < 4) bulk_commit();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+            continue;
+        }
+        const int tile = item % n_tiles, unit = item / n_tiles;
+        const int i0 = (tile % P.tiles_x) * kTile, j0 = (tile / P.tiles_x) * kTile;
+        unsigned char* stage = stage0 + (k & 1) * P.out_stage_bytes;
+        TOut* stage_row = reinterpret_cast<TOut*>(stage) + (jl * kTile + il0) * P.channels;
+        if (lane < 4) bulk_wait_read_1();      // this warp's stores from two items ago have left the stage
         if (mode == kModeFast) {
-            for (int task = tid; task < kTile * 12; task += kConsumerThreads) {
-                const int row = task / 12, c = task % 12;
-                const float* K = c < 6 ? plan->kx : plan->ky;
-                const int kk = c % 6;
-                const float t = (float)(2 * row - (kTile - 1)) * (1.0f / (kTile - 1));
-                float a = K[5 * 6 + kk];
+            // the 12 coefficients of this lane's row, spread over the 8 lanes that share the row
+            const float t = (float)(2 * jl - (kTile - 1)) * (1.0f / (kTile - 1));
+            for (int c = lane & 7; c < 12; c += 8) {
+                const float* K = (c < 6 ? plan->kx : plan->ky) + (c < 6 ? c : c - 6);
+                float a = K[30];
 #pragma unroll
-                for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6 + kk]);
-                rowc[row * 12 + c] = a;
+                for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6]);
+                rc[c] = a;
             }
         }
-        if (tid < kTile) bulk_wait_read_1();       // the stores that last read this stage buffer are done
-        consumer_barrier();
-
-        if (mode != kModeFallback) {
-            TOut* stage_row = reinterpret_cast<TOut*>(stage) + (jl * kTile + il0) * P.channels;
-            if (mode == kModeFill) {
-                for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
-            } else {
-                const float X0 = (float)(plan->x0 * 32), Y0 = (float)(plan->y0 * 32);
-                const float* rc = rowc + jl * 12;
-                float sxf[4], syf[4];
+        __syncwarp();
+        if (mode == kModeFill) {
+            for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
+        } else {
+            const unsigned char* patch = ring + slot_off[slot];
+            const float X0 = (float)(plan->x0 * 32), Y0 = (float)(plan->y0 * 32);
+            float sxf[4], syf[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float s = (float)(2 * (il0 + q) - (kTile - 1)) * (1.0f / (kTile - 1));
-                    float dx = rc[5], dy = rc[11];
+            for (int q = 0; q < 4; ++q) {
+                const float s = (float)(2 * (il0 + q) - (kTile - 1)) * (1.0f / (kTile - 1));
+                float dx = rc[5], dy = rc[11];
 #pragma unroll
-                    for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
-                    // 32 * float32(x): the rounding of this add is the float32 cast cv2.remap's map would see
-                    sxf[q] = __fadd_rn(dx, X0); syf[q] = __fadd_rn(dy, Y0);
-                }
-                bool done = false;
-                if constexpr (std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
-                              INTERP != kNearest) {
-                    if (P.channels == 3) {
-                        uint32_t bias = patch_bias_u8c3(smem_u32(patch), plan->pitch, plan->xb0, plan->py0);
-                        uint32_t px[4];
-                        if constexpr (INTERP == kLinear) {
+                for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
+                // 32 * float32(x): the rounding of this add is the float32 cast cv2.remap's map would see
+                sxf[q] = __fadd_rn(dx, X0); syf[q] = __fadd_rn(dy, Y0);
+            }
+            bool done = false;
+            if constexpr (std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
+                          INTERP != kNearest) {
+                if (P.channels == 3) {
+                    uint32_t bias = patch_bias_u8c3(smem_u32(patch), plan->pitch, plan->xb0, plan->py0);
+                    uint32_t px[4];
+                    if constexpr (INTERP == kLinear) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                px[q] = bilinear_u8c3(bias, (uint32_t)plan->pitch, round_bits(sxf[q]), round_bits(syf[q]));
-                        } else {
-                            bias -= 3u + (uint32_t)plan->pitch;
-                            const uint32_t tab = smem_u32(table);
+                        for (int q = 0; q < 4; ++q)
+                            px[q] = bilinear_u8c3(bias, (uint32_t)plan->pitch, round_bits(sxf[q]), round_bits(syf[q]));
+                    } else {
+                        bias -= 3u + (uint32_t)plan->pitch;
+                        const uint32_t tab = smem_u32(table);
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                px[q] = bicubic_u8c3(bias, (uint32_t)plan->pitch, tab, round_bits(sxf[q]), round_bits(syf[q]));
-                        }
-                        uint32_t w0, w1, w2;
-                        pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
-                        uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
-                        o[0] = w0; o[1] = w1; o[2] = w2;
-                        done = true;
+                        for (int q = 0; q < 4; ++q)
+                            px[q] = bicubic_u8c3(bias, (uint32_t)plan->pitch, tab, round_bits(sxf[q]), round_bits(syf[q]));
                     }
-                }
-                if (!done) {
-                    const PatchTaps<TIn> taps{patch, plan->pitch, plan->xb0, plan->py0, P.channels};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
-                                                        sxf[q] * (1.0f / 32.0f), syf[q] * (1.0f / 32.0f),
-                                                        stage_row + q * P.channels);
+                    uint32_t w0, w1, w2;
+                    pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
+                    uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
+                    o[0] = w0; o[1] = w1; o[2] = w2;
+                    done = true;
                 }
             }
-            const int v = unit % P.n_views, g = unit / P.n_views;
-            unsigned char* dst_base = P.dst.data + ((long long)g * P.n_views + v) * P.dst.image_stride;
-            const bool full_tile = i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height;
-            if (full_tile && P.bulk_store_ok) {
-                fence_async_shared();
-                consumer_barrier();
-                if (tid < kTile) {
-                    bulk_s2g(dst_base + (long long)(j0 + tid) * P.dst.pitch + (long long)i0 * P.channels * sizeof(TOut),
-                             stage + tid * row_out_bytes, (uint32_t)row_out_bytes);
-                }
-            } else {
-                consumer_barrier();
-                const int nelem = kTile * P.channels;
-                for (int e = tid; e < kTile * nelem; e += kConsumerThreads) {
-                    const int r = e / nelem, c = e % nelem;
-                    const int i = i0 + c / P.channels, j = j0 + r;
-                    if (i < P.dst.width && j < P.dst.height)
-                        reinterpret_cast<TOut*>(dst_base + (long long)j * P.dst.pitch)[(long long)i0 * P.channels + c] =
-                            reinterpret_cast<const TOut*>(stage)[r * nelem + c];
-                }
-                consumer_barrier();
+            if (!done) {
+                const PatchTaps<TIn> taps{patch, plan->pitch, plan->xb0, plan->py0, P.channels};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
+                                                    sxf[q] * (1.0f / 32.0f), syf[q] * (1.0f / 32.0f),
+                                                    stage_row + q * P.channels);
+            }
+        }
+        // ---- this warp's 4 rows leave; the patch is released ------------------------------------------
+        const int v = unit % P.n_views, g = unit / P.n_views;
+        unsigned char* dst_base = P.dst.data + ((long long)g * P.n_views + v) * P.dst.image_stride;
+        const bool full_tile = i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height;
+        if (full_tile && P.bulk_store_ok) {
+            fence_async_shared();
+            __syncwarp();
+            if (lane < 4) {
+                const int r = warp * 4 + lane;
+                bulk_s2g(dst_base + (long long)(j0 + r) * P.dst.pitch + (long long)i0 * P.channels * sizeof(TOut),
+                         stage + r * row_out_bytes, (uint32_t)row_out_bytes);
             }
         } else {
-            consumer_barrier();
+            __syncwarp();
+            const int nelem = kTile * P.channels;
+            for (int e = lane; e < 4 * nelem; e += 32) {
+                const int r = warp * 4 + e / nelem, c = e % nelem;
+                const int i = i0 + c / P.channels, j = j0 + r;
+                if (i < P.dst.width && j < P.dst.height)
+                    reinterpret_cast<TOut*>(dst_base + (long long)j * P.dst.pitch)[(long long)i0 * P.channels + c] =
+                        reinterpret_cast<const TOut*>(stage)[r * nelem + c];
+            }
+            __syncwarp();
         }
-        if (tid < kTile) bulk_commit();            // one (possibly empty) group per iteration keeps the count in step
-        if (tid == 0) mbar_arrive(&empty[b]);      // patch / plan buffer b may be refilled
+        if (lane < 4) bulk_commit();               // one (possibly empty) group per item keeps the count in step
+        if (lane == 0) mbar_arrive(&empty[slot]);  // all 8 warps arrived -> the producer may reuse the bytes
     }
-    if (tid < kTile) bulk_wait_read_all();
+    if (lane < 4) bulk_wait_read_all();
 }
 
 // Debug twin: what the tiled kernel samples at, written as maps (r360_plan_coords).  One block per

@@ -3,6 +3,7 @@
 // float64 path) and r360_tiled.cuh (tile-staged fast path).
 #include "../../include/remap360.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -342,7 +343,7 @@ struct r360_plan {
     r360_images src_layout, dst_layout;
     std::vector<ViewDev> views;
     int tiles_x, tiles_y, n_tiles, n_fallback;
-    int out_stage_bytes, patch_budget, smem_bytes, ctas_per_sm, use_table, sm_count;
+    int out_stage_bytes, patch_budget, ring_bytes, smem_bytes, ctas_per_sm, use_table, sm_count;
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
     PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback;
@@ -390,13 +391,14 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         const int fixed = kTiledFixedSmem + (pl->use_table ? kTableBytes : 0) + 2 * pl->out_stage_bytes + 128;
         for (;; --want) {
             const int per_block = smem_per_sm / want - 1024;       // 1 KB per block is reserved by the driver
-            pl->patch_budget = ((per_block - fixed) / 2) & ~127;
-            if (pl->patch_budget >= 12 * 1024 || want == 1) break;
+            pl->ring_bytes = (per_block - fixed) & ~127;
+            if (pl->ring_bytes >= 24 * 1024 || want == 1) break;
         }
-        if (pl->patch_budget < 4096) pl->patch_budget = 4096;
-        if (pl->patch_budget > 96 * 1024) pl->patch_budget = 96 * 1024;
+        if (pl->ring_bytes < 8192) pl->ring_bytes = 8192;
+        if (pl->ring_bytes > 160 * 1024) pl->ring_bytes = 160 * 1024;
+        pl->patch_budget = pl->ring_bytes;                          // a patch may use the whole ring
         pl->ctas_per_sm = want;
-        pl->smem_bytes = fixed + 2 * pl->patch_budget;
+        pl->smem_bytes = fixed + pl->ring_bytes;
     }
     // the data pointers are not known yet: assume 16-byte aligned bases (checked at remap time)
     pl->bulk_load_ok = src->pitch_bytes % 16 == 0 && src->image_stride_bytes % 16 == 0 &&
@@ -452,7 +454,7 @@ struct TiledLauncher {
         T.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
         T.channels = lp.channels; T.n_views = pl->pr.n_views; T.n_groups = n_groups;
         T.n_lenses = pl->pr.n_lenses; T.tiles_x = pl->tiles_x; T.tiles_y = pl->tiles_y;
-        T.out_stage_bytes = pl->out_stage_bytes; T.patch_budget = pl->patch_budget;
+        T.out_stage_bytes = pl->out_stage_bytes; T.ring_bytes = pl->ring_bytes;
         T.bulk_store_ok = pl->bulk_store_ok; T.use_table = pl->use_table; T.border_value = lp.border_value;
         T.plans = pl->d_plans;
 
@@ -462,12 +464,21 @@ struct TiledLauncher {
             R360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
             configured_smem = pl->smem_bytes;
         }
-        const long long total = (long long)n_groups * pl->pr.n_views * pl->n_tiles;
-        long long grid = (long long)pl->sm_count * pl->ctas_per_sm;
-        if (grid > total) grid = total;
-        kernel<<<dim3((unsigned)grid), kTiledThreads, pl->smem_bytes, s>>>(T);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        R360_CUDA(cudaGetLastError());
+        // work items are indexed with 32-bit ints inside the kernel: chunk the groups if needed
+        const long long per_group = (long long)pl->pr.n_views * pl->n_tiles;
+        const int max_groups = (int)std::max<long long>(1, (1LL << 30) / per_group);
+        for (int g0 = 0; g0 < n_groups; g0 += max_groups) {
+            TiledParams Q = T;
+            Q.n_groups = n_groups - g0 < max_groups ? n_groups - g0 : max_groups;
+            Q.src.data += (long long)g0 * pl->pr.n_lenses * Q.src.image_stride;
+            Q.dst.data += (long long)g0 * pl->pr.n_views * Q.dst.image_stride;
+            const long long total = Q.n_groups * per_group;
+            long long grid = (long long)pl->sm_count * pl->ctas_per_sm;
+            if (grid > total) grid = total;
+            kernel<<<dim3((unsigned)grid), kTiledThreads, pl->smem_bytes, s>>>(Q);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            R360_CUDA(cudaGetLastError());
+        }
 
         if (pl->n_fallback > 0) {
             FallbackParams F;
