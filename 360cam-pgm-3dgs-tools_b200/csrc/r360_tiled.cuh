@@ -5,7 +5,7 @@
 //   float64 at 6x6 Chebyshev nodes (ray -> R.d -> atan2/asin, or equisolid + Brown: exactly the
 //   direct path's math), converts them into two bivariate degree-5 polynomials in tile-local
 //   units of 1/32 px, bounds the fit error with 13 extra check points and the top-degree
-//   coefficients, and derives the bounding source patch.  320 bytes per tile (0.31 B per output
+//   coefficients, and derives the bounding source patch.  368 bytes per tile (0.36 B per output
 //   pixel, against 8 B for a float map) -- the analogue of the reference building its maps once
 //   (DF:1857-1907) and applying them to every frame (DF:1996-2014).
 //   Tiles the polynomial cannot describe to a few 1e-6 px (around a pole), whose patch does not
@@ -23,6 +23,8 @@
 
 #include <climits>
 
+#include <cuda.h>
+
 #include "r360_common.cuh"
 #include "r360_direct.cuh"
 #include "r360_sample.cuh"
@@ -35,18 +37,39 @@ constexpr int kFitN = 6;                 // nodes per axis (degree 5)
 constexpr int kFitChecks = 13;
 constexpr int kTapLo = 2, kTapHi = 3;    // patch margin around floor(coord): cubic taps -1..+2, +1 safety
 
-enum TileMode : int { kModeFallback = 0, kModeFast = 1, kModeFill = 2 };
+// kModeFast: patch staged with 2-D tensor TMA boxes; kModeFastRows: staged row by row with 1-D bulk
+// copies (rows clamped at the poles, or wider than the largest box).
+enum TileMode : int { kModeFallback = 0, kModeFast = 1, kModeFill = 2, kModeFastRows = 3 };
+
+// Box shapes of the tensor-TMA descriptors: widths in bytes (odd multiples of 32 keep consecutive
+// rows on different banks; 1024 = 256 uint32 elements is the hardware limit) x heights {32, 8}.
+constexpr int kNumBoxWidths = 11;
+constexpr int kNumBoxHeights = 2;
+__host__ __device__ constexpr int box_width_bytes(int k) {
+    return k == 0 ? 96 : k == 1 ? 160 : k == 2 ? 224 : k == 3 ? 288 : k == 4 ? 352 : k == 5 ? 416
+         : k == 6 ? 544 : k == 7 ? 672 : k == 8 ? 800 : k == 9 ? 928 : 1024;
+}
+__host__ __device__ constexpr int box_height_rows(int k) { return k == 0 ? 32 : 8; }
+// rows actually staged for `rows` needed rows: as many 32-row boxes as fit, the rest in 8-row boxes
+__host__ __device__ constexpr int staged_rows(int rows) { return (rows / 32) * 32 + (((rows % 32) + 7) / 8) * 8; }
 
 struct TilePlan {
-    float kx[36];        // 32 * (x - x0) = sum kx[l*6+k] t^l s^k   (s, t in [-1, 1] across the tile)
-    float ky[36];
-    int x0, y0;          // integer origins (source pixels)
+    // source coordinate in units of 1/32 px, absolute:
+    //   32 x = ax[0] + ax[1] * il + ax[2] * jl  +  sum rx[l*6+k] t^l s^k
+    // (il, jl) = pixel index inside the tile, s = (2 il - 31) / 31, t = (2 jl - 31) / 31.  The affine
+    // part carries the large magnitudes and is evaluated in float64; the residual polynomial (its
+    // constant and pure-linear terms are zero) is small and is evaluated in float32.
+    float rx[36];
+    float ry[36];
+    double ax[3];
+    double ay[3];
     int py0, rows;       // first source row of the patch (may be < 0: clamped while staging), row count
-    int xb0, row_bytes;  // source byte column of patch byte 0 (multiple of 16), bytes per row (multiple of 16)
+    int xb0, row_bytes;  // source byte column of patch byte 0 (multiple of 16), bytes needed per row
     int pitch;           // patch row pitch in shared memory
-    int mode_slot;       // TileMode | (source slot << 8)
+    int mode_slot;       // TileMode | (source slot << 8) | (box width index << 16)
+    int pad[2];
 };
-static_assert(sizeof(TilePlan) == 320, "TilePlan layout");
+static_assert(sizeof(TilePlan) == 368, "TilePlan layout");
 
 struct PlanHeader {      // first 256 bytes of the plan workspace
     int n_fallback;
@@ -66,6 +89,7 @@ struct PlanParams {
     int src_w, src_h, px_bytes;      // px_bytes = channels * sizeof(source element)
     int patch_budget;                // bytes of shared memory the remap kernel can give to a patch
     int bulk_load_ok;                // source layout allows 16-byte aligned row copies
+    int tensor_ok;                   // tensor-TMA descriptors can be built for the source layout
     int fill_invalid;
     ErpDev erp;
     LensDev lens[kMaxLenses];
@@ -177,12 +201,17 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
     __syncthreads();
     // -- origin, float32 coefficients, verdict ------------------------------------------------------
     TilePlan* out = P.plans + (long long)v * (P.tiles_x * P.tiles_y) + tile;
-    const int x0 = (int)(((long long)bmin_x + bmax_x) >> 1), y0 = (int)(((long long)bmin_y + bmax_y) >> 1);
     if (tid < 36) {
-        double cx = kx[tid], cy = ky[tid];
-        if (tid == 0) { cx -= x0; cy -= y0; }
-        out->kx[tid] = (float)(cx * 32.0);
-        out->ky[tid] = (float)(cy * 32.0);
+        // residual = everything but the constant and the two pure-linear terms
+        const bool affine_term = tid == 0 || tid == 1 || tid == 6;
+        out->rx[tid] = affine_term ? 0.0f : (float)(kx[tid] * 32.0);
+        out->ry[tid] = affine_term ? 0.0f : (float)(ky[tid] * 32.0);
+    }
+    if (tid == 36) {
+        // K00 + K01 s + K10 t with s = (2 il - 31) / 31, t likewise, in units of 1/32 px
+        const double g = 2.0 / (kTile - 1);
+        out->ax[0] = (kx[0] - kx[1] - kx[6]) * 32.0; out->ax[1] = kx[1] * g * 32.0; out->ax[2] = kx[6] * g * 32.0;
+        out->ay[0] = (ky[0] - ky[1] - ky[6]) * 32.0; out->ay[1] = ky[1] * g * 32.0; out->ay[2] = ky[6] * g * 32.0;
     }
     if (tid == 0) {
         double top_x = 0.0, top_y = 0.0;
@@ -201,24 +230,34 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
         // patch geometry
         const int xs0 = bmin_x - kTapLo, xs1 = bmax_x + kTapHi;
         const int ys0 = bmin_y - kTapLo, ys1 = bmax_y + kTapHi;
-        int mode = kModeFallback;
+        int mode = kModeFallback, wbox = 0;
         int xb0 = 0, row_bytes = 0, pitch = 0, rows = 0;
         if (fit_ok) {
             xb0 = (xs0 * P.px_bytes) & ~15;
             const int xb1 = ((xs1 + 1) * P.px_bytes + 15) & ~15;
             row_bytes = xb1 - xb0;
-            pitch = row_bytes + ((row_bytes & 127) == 0 ? 16 : 0);      // keep rows off the same banks
             rows = ys1 - ys0 + 1;
-            bool fast = P.bulk_load_ok && rows * pitch <= P.patch_budget;
             // columns must lie inside one period of the panorama / inside the sensor
-            fast = fast && xs0 >= 0 && xb1 <= P.src_w * P.px_bytes;
+            bool fast = P.bulk_load_ok && xs0 >= 0 && xb1 <= P.src_w * P.px_bytes;
             if (PROJ == kProjFisheye) fast = fast && ys0 >= 0 && ys1 < P.src_h && invalid_count == 0;
-            if (fast) mode = kModeFast;
+            if (fast) {
+                while (wbox < kNumBoxWidths && box_width_bytes(wbox) < row_bytes) ++wbox;
+                const bool rows_inside = ys0 >= 0 && ys1 < P.src_h;
+                if (P.tensor_ok && wbox < kNumBoxWidths && rows_inside &&
+                    staged_rows(rows) * box_width_bytes(wbox) <= P.patch_budget) {
+                    mode = kModeFast;                                    // tensor boxes: pitch = box width
+                    pitch = box_width_bytes(wbox);
+                } else {
+                    wbox = 0;
+                    pitch = row_bytes + ((row_bytes & 127) == 0 ? 16 : 0);   // keep rows off the same banks
+                    if (rows * pitch <= P.patch_budget) mode = kModeFastRows;
+                }
+            }
         }
         if (PROJ == kProjFisheye && P.fill_invalid && valid_count == 0) mode = kModeFill;
-        out->x0 = x0; out->y0 = y0;
         out->py0 = ys0; out->rows = rows; out->xb0 = xb0; out->row_bytes = row_bytes; out->pitch = pitch;
-        out->mode_slot = mode | (view.slot << 8);
+        out->mode_slot = mode | (view.slot << 8) | (wbox << 16);
+        out->pad[0] = 0; out->pad[1] = 0;
         if (mode == kModeFallback) {
             const int idx = atomicAdd(&P.header->n_fallback, 1);
             P.fallback[idx] = make_int2(v, tile);
@@ -255,12 +294,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     // try_wait suspends for a hardware time slice per call; a copy that never completes is a
     // bug, so trap instead of hanging the device
-    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > 20000u) __trap();
+    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        __nanosleep(spins < 64 ? 100 : 2000);
+        if (spins > 4000000u) __trap();
+    }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tensor_g2s_3d(void* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -283,6 +328,36 @@ __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy
 //     them off as bulk-async row stores; the last reader of a patch releases it to the producer
 //     through a second mbarrier (8 arrivals).
 
+// FIFO allocator for variable-size patches in the shared-memory ring.  The bytes in flight form
+// one circular interval [tail, head) of length `used`; allocations are contiguous (an allocation
+// that does not fit before the end of the ring skips the end and is charged for the skipped
+// bytes) and are released in allocation order.
+struct PatchRing {
+    int head = 0, tail = 0, used = 0;
+    // On success returns true with the byte offset and the bytes to give back on release.
+    __host__ __device__ bool try_alloc(int need, int capacity, int& off, int& charge) {
+        if (used == 0) { head = 0; tail = 0; }
+        if (need == 0) { off = head; charge = 0; return true; }
+        if (used == 0 || head > tail) {
+            if (head + need <= capacity) { off = head; charge = need; }
+            else if (need <= tail) { off = 0; charge = need + (capacity - head); }
+            else return false;
+        } else if (head < tail) {
+            if (head + need <= tail) { off = head; charge = need; } else return false;
+        } else {
+            return false;                       // head == tail with bytes in use: full
+        }
+        used += charge;
+        head = off + need;
+        return true;
+    }
+    __host__ __device__ void release(int charge, int capacity) {
+        used -= charge;
+        tail += charge;
+        if (tail >= capacity) tail -= capacity;
+    }
+};
+
 struct TiledParams {
     ImageSetDev src, dst;
     int channels;
@@ -302,8 +377,16 @@ constexpr int kSlots = 8;                               // work items in flight 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kTiledThreads = kConsumerThreads + 32;
-// barriers (128) + ring bookkeeping (128) + row coefficients (1536) + plan records (8 x 320)
-constexpr int kTiledFixedSmem = 128 + 128 + 1536 + kSlots * 320;      // 4352
+struct SlotInfo {            // written by the producer, read by the consumers of the item
+    int off;                 // ring offset of the patch
+    int size;                // ring bytes to give back on release
+    int i0, j0;              // tile origin in the output image
+    long long dst_off;       // byte offset of the destination image (frame, view) in the batch
+    long long pad;
+};
+static_assert(sizeof(SlotInfo) == 32, "SlotInfo layout");
+// barriers (128) + slot info (8 x 32) + row coefficients (1536) + plan records (8 x 368)
+constexpr int kTiledFixedSmem = 128 + kSlots * 32 + 1536 + kSlots * 368;      // 4864
 constexpr int kTableBytes = 32 * 32 * 16 * 2;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -311,15 +394,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
+// One descriptor per box shape, all over the same 3-D view of the source batch:
+// (row bytes / 4 as uint32, rows, images) with strides (pitch, image stride).
+struct TensorMaps {
+    CUtensorMap m[kNumBoxWidths * kNumBoxHeights];     // [width index][height index]
+};
+
 template <int INTERP, typename TIn, typename TOut>
-__global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid_constant__ TiledParams P) {
+__global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid_constant__ TiledParams P,
+                                                                    const __grid_constant__ TensorMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [kSlots]
     uint64_t* empty = full + kSlots;                               // [kSlots]
-    int* slot_off = reinterpret_cast<int*>(smem + 128);            // [kSlots] ring offset of the item's patch
-    int* slot_size = slot_off + kSlots;                            // [kSlots] bytes to give back on release
-    float* rowc = reinterpret_cast<float*>(smem + 256);            // [32 rows][12]
-    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 256 + 1536);
+    SlotInfo* slots = reinterpret_cast<SlotInfo*>(smem + 128);     // [kSlots]
+    float* rowc = reinterpret_cast<float*>(smem + 128 + kSlots * 32);            // [32 rows][12]
+    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 128 + kSlots * 32 + 1536);
     unsigned char* table = smem + kTiledFixedSmem;
     unsigned char* stage0 = table + (P.use_table ? kTableBytes : 0);
     unsigned char* ring = stage0 + 2 * P.out_stage_bytes;
@@ -341,54 +430,55 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
     if (tid >= kConsumerThreads) {
         // ================= producer warp ==========================================================
         const int lane = tid - kConsumerThreads;
-        int head = 0, used = 0, oldest = 0;       // ring state, identical in every lane
+        PatchRing ringst;                // identical in every lane
+        int oldest = 0;
         int k = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++k) {
             const int slot = k & (kSlots - 1);
             const int tile = item % n_tiles, unit = item / n_tiles;
             const int v = unit % P.n_views, g = unit / P.n_views;
             const TilePlan* gp = P.plans + (long long)v * n_tiles + tile;
-            const int4 geo0 = __ldg(reinterpret_cast<const int4*>(gp) + 18);   // x0 y0 py0 rows
-            const int4 geo1 = __ldg(reinterpret_cast<const int4*>(gp) + 19);   // xb0 row_bytes pitch mode_slot
-            const int mode = geo1.w & 0xff, src_slot = geo1.w >> 8;
-            const int py0 = geo0.z, rows = mode == kModeFast ? geo0.w : 0;
-            const int xb0 = geo1.x, row_bytes = geo1.y, pitch = geo1.z;
-            const int need = (rows * pitch + 127) & ~127;
-            // ---- find room: FIFO ring, items are released in order ----------------------------
+            const int4 geo0 = __ldg(reinterpret_cast<const int4*>(gp) + 21);   // py0 rows xb0 row_bytes
+            const int4 geo1 = __ldg(reinterpret_cast<const int4*>(gp) + 22);   // pitch mode_slot - -
+            const int mode = geo1.y & 0xff, src_slot = (geo1.y >> 8) & 0xff, wbox = geo1.y >> 16;
+            const bool staged = mode == kModeFast || mode == kModeFastRows;
+            const int py0 = geo0.x, rows = staged ? geo0.y : 0;
+            const int xb0 = geo0.z, row_bytes = geo0.w, pitch = geo1.x;
+            const int srows = mode == kModeFast ? staged_rows(rows) : rows;      // rows written to the ring
+            const int need = (srows * pitch + 127) & ~127;
+            // ---- find room: wait for the oldest items to be released until the patch fits ---------
             int off = 0, charge = 0;
-            for (;;) {
-                bool ok = (k - oldest) < kSlots;
-                if (ok) {
-                    if (used == 0) head = 0;
-                    const int tail = oldest < k ? slot_off[oldest & (kSlots - 1)] : head;
-                    if (need == 0) { off = head; charge = 0; }
-                    else if (used == 0 || head > tail) {
-                        if (head + need <= P.ring_bytes) { off = head; charge = need; }
-                        else if (need <= tail) { off = 0; charge = need + (P.ring_bytes - head); }
-                        else ok = false;
-                    } else if (head < tail) {
-                        if (head + need <= tail) { off = head; charge = need; } else ok = false;
-                    } else ok = false;                                   // head == tail with bytes in use: full
-                }
-                if (ok) break;
+            while ((k - oldest) >= kSlots || !ringst.try_alloc(need, P.ring_bytes, off, charge)) {
                 mbar_wait(&empty[oldest & (kSlots - 1)], (oldest / kSlots) & 1);
-                used -= slot_size[oldest & (kSlots - 1)];
+                ringst.release(slots[oldest & (kSlots - 1)].size, P.ring_bytes);
                 ++oldest;
             }
             __syncwarp();
             if (lane == 0) {
-                slot_off[slot] = off; slot_size[slot] = charge;
-                mbar_expect_tx(&full[slot], (uint32_t)(sizeof(TilePlan) + rows * row_bytes));
+                SlotInfo si;
+                si.off = off; si.size = charge;
+                si.i0 = (tile % P.tiles_x) * kTile; si.j0 = (tile / P.tiles_x) * kTile;
+                si.dst_off = ((long long)g * P.n_views + v) * P.dst.image_stride; si.pad = 0;
+                slots[slot] = si;
+                mbar_expect_tx(&full[slot], (uint32_t)(sizeof(TilePlan) + (mode == kModeFast ? srows * pitch : rows * row_bytes)));
                 bulk_g2s(&planbuf[slot], gp, (uint32_t)sizeof(TilePlan), &full[slot]);
             }
             __syncwarp();
-            used += charge;
-            head = off + need;
-            const unsigned char* img = P.src.data + ((long long)g * P.n_lenses + src_slot) * P.src.image_stride;
             unsigned char* patch = ring + off;
-            for (int r = lane; r < rows; r += 32) {
-                const int sy = min(max(py0 + r, 0), P.src.height - 1);            // pole rows replicate
-                bulk_g2s(patch + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[slot]);
+            if (mode == kModeFast) {
+                // a few tensor boxes: 32-row boxes first, then 8-row boxes
+                const int n32 = rows / 32, n8 = ((rows % 32) + 7) / 8;
+                if (lane < n32 + n8) {
+                    const int r0 = lane < n32 ? lane * 32 : n32 * 32 + (lane - n32) * 8;
+                    const CUtensorMap* tm = &maps.m[wbox * kNumBoxHeights + (lane < n32 ? 0 : 1)];
+                    tensor_g2s_3d(patch + r0 * pitch, tm, xb0 >> 2, py0 + r0, g * P.n_lenses + src_slot, &full[slot]);
+                }
+            } else {
+                const unsigned char* img = P.src.data + ((long long)g * P.n_lenses + src_slot) * P.src.image_stride;
+                for (int r = lane; r < rows; r += 32) {
+                    const int sy = min(max(py0 + r, 0), P.src.height - 1);            // pole rows replicate
+                    bulk_g2s(patch + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[slot]);
+                }
             }
         }
         return;
@@ -412,16 +502,16 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             if (lane == 0) mbar_arrive(&empty[slot]);
             continue;
         }
-        const int tile = item % n_tiles, unit = item / n_tiles;
-        const int i0 = (tile % P.tiles_x) * kTile, j0 = (tile / P.tiles_x) * kTile;
+        const SlotInfo si = slots[slot];
+        const int i0 = si.i0, j0 = si.j0;
         unsigned char* stage = stage0 + (k & 1) * P.out_stage_bytes;
         TOut* stage_row = reinterpret_cast<TOut*>(stage) + (jl * kTile + il0) * P.channels;
         if (lane < 4) bulk_wait_read_1();      // this warp's stores from two items ago have left the stage
-        if (mode == kModeFast) {
+        if (mode != kModeFill) {
             // the 12 coefficients of this lane's row, spread over the 8 lanes that share the row
             const float t = (float)(2 * jl - (kTile - 1)) * (1.0f / (kTile - 1));
             for (int c = lane & 7; c < 12; c += 8) {
-                const float* K = (c < 6 ? plan->kx : plan->ky) + (c < 6 ? c : c - 6);
+                const float* K = (c < 6 ? plan->rx : plan->ry) + (c < 6 ? c : c - 6);
                 float a = K[30];
 #pragma unroll
                 for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6]);
@@ -432,8 +522,11 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
         if (mode == kModeFill) {
             for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
         } else {
-            const unsigned char* patch = ring + slot_off[slot];
-            const float X0 = (float)(plan->x0 * 32), Y0 = (float)(plan->y0 * 32);
+            const unsigned char* patch = ring + si.off;
+            // affine part in float64 (absolute, exact to ~1e-10 px), residual in float32; the final
+            // double -> float conversion IS the float32 cast of the map cv2.remap would be given
+            const double bx = fma(plan->ax[2], (double)jl, plan->ax[0]), by = fma(plan->ay[2], (double)jl, plan->ay[0]);
+            const double axi = plan->ax[1], ayi = plan->ay[1];
             float sxf[4], syf[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -441,8 +534,8 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                 float dx = rc[5], dy = rc[11];
 #pragma unroll
                 for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
-                // 32 * float32(x): the rounding of this add is the float32 cast cv2.remap's map would see
-                sxf[q] = __fadd_rn(dx, X0); syf[q] = __fadd_rn(dy, Y0);
+                sxf[q] = __double2float_rn(fma(axi, (double)(il0 + q), bx) + (double)dx);
+                syf[q] = __double2float_rn(fma(ayi, (double)(il0 + q), by) + (double)dy);
             }
             bool done = false;
             if constexpr (std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
@@ -478,8 +571,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             }
         }
         // ---- this warp's 4 rows leave; the patch is released ------------------------------------------
-        const int v = unit % P.n_views, g = unit / P.n_views;
-        unsigned char* dst_base = P.dst.data + ((long long)g * P.n_views + v) * P.dst.image_stride;
+        unsigned char* dst_base = P.dst.data + si.dst_off;
         const bool full_tile = i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height;
         if (full_tile && P.bulk_store_ok) {
             fence_async_shared();
@@ -521,23 +613,23 @@ __global__ void __launch_bounds__(256) coords_tiled_kernel(const __grid_constant
     const int tid = threadIdx.x, tile = blockIdx.x, v = blockIdx.y;
     const int i0 = (tile % P.tiles_x) * kTile, j0 = (tile / P.tiles_x) * kTile;
     const int4* gp = reinterpret_cast<const int4*>(P.plans + (long long)v * (P.tiles_x * P.tiles_y) + tile);
-    if (tid < 20) reinterpret_cast<int4*>(&plan)[tid] = __ldg(gp + tid);
+    if (tid < (int)(sizeof(TilePlan) / 16)) reinterpret_cast<int4*>(&plan)[tid] = __ldg(gp + tid);
     __syncthreads();
-    if ((plan.mode_slot & 0xff) != kModeFast) return;
+    const int mode = plan.mode_slot & 0xff;
+    if (mode != kModeFast && mode != kModeFastRows) return;
     for (int task = tid; task < kTile * 12; task += 256) {
         const int row = task / 12, c = task % 12;
-        const float* K = c < 6 ? plan.kx : plan.ky;
-        const int kk = c % 6;
+        const float* K = (c < 6 ? plan.rx : plan.ry) + (c < 6 ? c : c - 6);
         const float t = (float)(2 * row - (kTile - 1)) * (1.0f / (kTile - 1));
-        float a = K[5 * 6 + kk];
+        float a = K[30];
 #pragma unroll
-        for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6 + kk]);
+        for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6]);
         rowc[row * 12 + c] = a;
     }
     __syncthreads();
     const int jl = tid >> 3, il0 = (tid & 7) * 4;
-    const float X0 = (float)(plan.x0 * 32), Y0 = (float)(plan.y0 * 32);
     const float* rc = rowc + jl * 12;
+    const double bx = fma(plan.ax[2], (double)jl, plan.ax[0]), by = fma(plan.ay[2], (double)jl, plan.ay[0]);
     for (int q = 0; q < 4; ++q) {
         const int i = i0 + il0 + q, j = j0 + jl;
         if (i >= P.out_w || j >= P.out_h) continue;
@@ -545,11 +637,12 @@ __global__ void __launch_bounds__(256) coords_tiled_kernel(const __grid_constant
         float dx = rc[5], dy = rc[11];
 #pragma unroll
         for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
-        const float sxf = __fadd_rn(dx, X0), syf = __fadd_rn(dy, Y0);
+        const double sx = fma(plan.ax[1], (double)(il0 + q), bx) + (double)dx;
+        const double sy = fma(plan.ay[1], (double)(il0 + q), by) + (double)dy;
         const long long o = ((long long)v * P.out_h + j) * P.out_w + i;
-        P.x32[o] = sxf * (1.0f / 32.0f); P.y32[o] = syf * (1.0f / 32.0f);
-        P.x64[o] = (double)plan.x0 + (double)dx * (1.0 / 32.0);
-        P.y64[o] = (double)plan.y0 + (double)dy * (1.0 / 32.0);
+        P.x32[o] = __double2float_rn(sx) * (1.0f / 32.0f); P.y32[o] = __double2float_rn(sy) * (1.0f / 32.0f);
+        P.x64[o] = sx * (1.0 / 32.0);
+        P.y64[o] = sy * (1.0 / 32.0);
         if (P.valid) P.valid[o] = 1;
     }
 }

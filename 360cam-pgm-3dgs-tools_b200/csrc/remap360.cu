@@ -347,9 +347,55 @@ struct r360_plan {
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
     PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback;
+    // tensor-TMA descriptors depend on the source base pointer and batch size: small cache
+    bool tensor_ok;
+    mutable std::mutex tm_mutex;
+    struct TmEntry { const void* data; int count; int64_t stride; TensorMaps maps; };
+    mutable std::vector<TmEntry> tm_cache;
 };
 
 namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// Descriptors for every box shape over (row bytes / 4 as uint32, rows, images).
+int encode_tensor_maps(const r360_images& src, TensorMaps* out) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return R360_E_CUDA;
+    const int es = elem_size(src.dtype);
+    const cuuint64_t dims[3] = {(cuuint64_t)src.width * src.channels * es / 4, (cuuint64_t)src.height,
+                                (cuuint64_t)src.count};
+    const cuuint64_t strides[2] = {(cuuint64_t)src.pitch_bytes,
+                                   (cuuint64_t)(src.count > 1 ? src.image_stride_bytes : src.pitch_bytes * src.height)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int wk = 0; wk < kNumBoxWidths; ++wk)
+        for (int hk = 0; hk < kNumBoxHeights; ++hk) {
+            const cuuint32_t box[3] = {(cuuint32_t)box_width_bytes(wk) / 4, (cuuint32_t)box_height_rows(hk), 1};
+            const CUresult r = enc(&out->m[wk * kNumBoxHeights + hk], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.data, dims,
+                                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                std::snprintf(tl_cuda_error, sizeof(tl_cuda_error), "cuTensorMapEncodeTiled failed (%d) for box %dx%d",
+                              (int)r, box_width_bytes(wk), box_height_rows(hk));
+                return R360_E_CUDA;
+            }
+        }
+    return R360_OK;
+}
 
 bool aligned16(const void* p, int64_t pitch, int64_t stride) {
     return reinterpret_cast<uintptr_t>(p) % 16 == 0 && pitch % 16 == 0 && stride % 16 == 0;
@@ -404,6 +450,7 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     pl->bulk_load_ok = src->pitch_bytes % 16 == 0 && src->image_stride_bytes % 16 == 0 &&
                        ((int64_t)src->width * src->channels * in_es) % 16 == 0;
     pl->bulk_store_ok = dst->pitch_bytes % 16 == 0 && dst->image_stride_bytes % 16 == 0;
+    pl->tensor_ok = pl->bulk_load_ok && encode_tiled_fn() != nullptr && std::getenv("R360_NO_TENSOR_TMA") == nullptr;
     pl->ws = static_cast<unsigned char*>(workspace);
     pl->d_header = reinterpret_cast<PlanHeader*>(pl->ws + wl.header);
     pl->d_views = reinterpret_cast<ViewDev*>(pl->ws + wl.views);
@@ -420,7 +467,8 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     std::memset(&P, 0, sizeof(P));
     P.proj = proj; P.out_w = dst->width; P.out_h = dst->height; P.tiles_x = pl->tiles_x; P.tiles_y = pl->tiles_y;
     P.n_views = n_views; P.src_w = src->width; P.src_h = src->height; P.px_bytes = src->channels * in_es;
-    P.patch_budget = pl->patch_budget; P.bulk_load_ok = pl->bulk_load_ok; P.fill_invalid = pl->pr.lp.fill_invalid;
+    P.patch_budget = pl->patch_budget; P.bulk_load_ok = pl->bulk_load_ok; P.tensor_ok = pl->tensor_ok;
+    P.fill_invalid = pl->pr.lp.fill_invalid;
     P.erp = pl->pr.lp.erp;
     std::memcpy(P.lens, pl->pr.lp.lens, sizeof(P.lens));
     P.views = pl->d_views; P.plans = pl->d_plans; P.header = pl->d_header; P.fallback = pl->d_fallback;
@@ -475,7 +523,28 @@ struct TiledLauncher {
             const long long total = Q.n_groups * per_group;
             long long grid = (long long)pl->sm_count * pl->ctas_per_sm;
             if (grid > total) grid = total;
-            kernel<<<dim3((unsigned)grid), kTiledThreads, pl->smem_bytes, s>>>(Q);
+            TensorMaps maps;
+            std::memset(&maps, 0, sizeof(maps));
+            if (pl->tensor_ok) {
+                r360_images chunk = *src;
+                chunk.data = Q.src.data;
+                chunk.count = Q.n_groups * pl->pr.n_lenses;
+                std::lock_guard<std::mutex> lock(pl->tm_mutex);
+                const r360_plan::TmEntry* hit = nullptr;
+                for (const auto& e : pl->tm_cache)
+                    if (e.data == chunk.data && e.count == chunk.count && e.stride == chunk.image_stride_bytes) hit = &e;
+                if (!hit) {
+                    r360_plan::TmEntry e;
+                    e.data = chunk.data; e.count = chunk.count; e.stride = chunk.image_stride_bytes;
+                    const int erc = encode_tensor_maps(chunk, &e.maps);
+                    if (erc != R360_OK) return erc;
+                    if (pl->tm_cache.size() >= 8) pl->tm_cache.erase(pl->tm_cache.begin());
+                    pl->tm_cache.push_back(e);
+                    hit = &pl->tm_cache.back();
+                }
+                maps = hit->maps;
+            }
+            kernel<<<dim3((unsigned)grid), kTiledThreads, pl->smem_bytes, s>>>(Q, maps);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             R360_CUDA(cudaGetLastError());
         }
@@ -684,6 +753,27 @@ int r360_debug_weight_tables(int16_t* cubic_fixed_16384, float* cubic_1d_128) {
     if (cubic_fixed_16384) std::memcpy(cubic_fixed_16384, t.cubic_fixed, sizeof(t.cubic_fixed));
     if (cubic_1d_128) std::memcpy(cubic_1d_128, t.cubic_1d, sizeof(t.cubic_1d));
     return R360_OK;
+}
+
+// Test hook: drives the shared-memory ring allocator (PatchRing, r360_tiled.cuh) on the host with a
+// sequence of patch sizes and at most `slots` allocations in flight; returns -1 if no two live
+// allocations ever overlap and none leaves the ring, else the index of the offending request.
+int r360_debug_ring_check(const int32_t* sizes, int32_t n, int32_t capacity, int32_t slots) {
+    PatchRing ring;
+    std::vector<int> off(n), charge(n);
+    int oldest = 0;
+    for (int k = 0; k < n; ++k) {
+        if (sizes[k] > capacity) return k;
+        while ((k - oldest) >= slots || !ring.try_alloc(sizes[k], capacity, off[k], charge[k])) {
+            if (oldest >= k) return k;                 // nothing left to release and still no room
+            ring.release(charge[oldest], capacity);
+            ++oldest;
+        }
+        if (off[k] < 0 || off[k] + sizes[k] > capacity) return k;
+        for (int j = oldest; j < k; ++j)
+            if (sizes[j] && sizes[k] && !(off[k] + sizes[k] <= off[j] || off[j] + sizes[j] <= off[k])) return k;
+    }
+    return -1;
 }
 
 }  // extern "C"

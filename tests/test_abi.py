@@ -99,3 +99,30 @@ def test_python_api_refuses_cpu_tensors():
     with pytest.raises(ValueError, match="no CPU path"):
         remap360.remap_erp(torch.zeros((1, 8, 16, 3), dtype=torch.uint8),
                            [remap360.PerspectiveView(0, 0, 90, 90)], (4, 4))
+
+
+def test_shared_memory_ring_allocator_never_overlaps(lib):
+    """The producer warp's patch allocator (PatchRing in csrc/r360_tiled.cuh), driven on the host:
+    random patch sizes including empty requests (fallback tiles) and patches close to the ring
+    capacity -- the mix that occurs around the poles."""
+    import ctypes
+    import random
+    lib.r360_debug_ring_check.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]
+    cap = 100 * 1024
+    for seed in range(300):
+        rnd = random.Random(seed)
+        sizes = []
+        for _ in range(400):
+            r = rnd.random()
+            if r < 0.15:
+                sizes.append(0)
+            elif r < 0.5:
+                sizes.append(rnd.randrange(8, 16) * 1024)
+            elif r < 0.8:
+                sizes.append(rnd.randrange(30, 80) * 1024 // 128 * 128)
+            else:
+                sizes.append(rnd.randrange(80, 101) * 1024 // 128 * 128)
+        arr = np.asarray(sizes, dtype=np.int32)
+        assert lib.r360_debug_ring_check(arr.ctypes.data, len(sizes), cap, 8) == -1, seed
+    one = np.asarray([cap + 128], dtype=np.int32)
+    assert lib.r360_debug_ring_check(one.ctypes.data, 1, cap, 8) == 0
