@@ -35,7 +35,11 @@ namespace r360 {
 constexpr int kTile = 32;
 constexpr int kFitN = 6;                 // nodes per axis (degree 5)
 constexpr int kFitChecks = 13;
-constexpr int kTapLo = 2, kTapHi = 3;    // patch margin around floor(coord): cubic taps -1..+2, +1 safety
+// Patch margins around the range of floor(coord).  The quantised coordinate rint(32 x) / 32 can round
+// up to the next integer, so bilinear taps reach floor(x) + 2 and bicubic taps floor(x) - 1 .. + 3;
+// one more column / row is kept on the low side.
+__host__ __device__ constexpr int tap_margin_lo(int interp) { return interp == kCubic ? 2 : 1; }
+__host__ __device__ constexpr int tap_margin_hi(int interp) { return interp == kCubic ? 3 : 2; }
 
 // kModeFast: patch staged with 2-D tensor TMA boxes; kModeFastRows: staged row by row with 1-D bulk
 // copies (rows clamped at the poles, or wider than the largest box).
@@ -91,6 +95,7 @@ struct PlanParams {
     int bulk_load_ok;                // source layout allows 16-byte aligned row copies
     int tensor_ok;                   // tensor-TMA descriptors can be built for the source layout
     int fill_invalid;
+    int interp;                      // decides the tap margins of the patch
     ErpDev erp;
     LensDev lens[kMaxLenses];
     const ViewDev* views;            // n_views, device
@@ -228,8 +233,9 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
         fit_ok = fit_ok && (long long)bmax_x - bmin_x < 2048 && (long long)bmax_y - bmin_y < 2048;
 
         // patch geometry
-        const int xs0 = bmin_x - kTapLo, xs1 = bmax_x + kTapHi;
-        const int ys0 = bmin_y - kTapLo, ys1 = bmax_y + kTapHi;
+        const int lo = tap_margin_lo(P.interp), hi = tap_margin_hi(P.interp);
+        const int xs0 = bmin_x - lo, xs1 = bmax_x + hi;
+        const int ys0 = bmin_y - lo, ys1 = bmax_y + hi;
         int mode = kModeFallback, wbox = 0;
         int xb0 = 0, row_bytes = 0, pitch = 0, rows = 0;
         if (fit_ok) {
@@ -281,22 +287,35 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar_saddr, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0xF4240;\n"
         "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
     return done != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_s(smem_u32(bar), parity); }
+// Wait on a barrier given by its shared-memory address (cheaper in the per-tile loop).
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
+    if (mbar_try_wait_s(bar_saddr, parity)) return;
+    for (unsigned spins = 0; !mbar_try_wait_s(bar_saddr, parity); ++spins) {
+        __nanosleep(256);
+        if (spins > 8000000u) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     // try_wait suspends for a hardware time slice per call; a copy that never completes is a
     // bug, so trap instead of hanging the device
+    if (mbar_try_wait(bar, parity)) return;
     for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        __nanosleep(spins < 64 ? 100 : 2000);
-        if (spins > 4000000u) __trap();
+        __nanosleep(256);
+        if (spins > 8000000u) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -318,15 +337,16 @@ __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy
 // ---- the remap kernel -------------------------------------------------------------------------------
 //
 // Persistent and warp-specialised.  Each block walks (frame, view, tile) work items:
-//   * one producer warp runs ahead: it reads the next item's patch geometry from the plan, carves
-//     space out of a shared-memory ring (variable-size patches, up to 8 items in flight), arms the
-//     item's mbarrier with the byte count and issues the bulk-async copies (plan record + one copy
-//     per patch row);
+//   * one producer warp runs ahead.  Per item it reads the tile's plan record, carves space for the
+//     patch out of a shared-memory ring (variable-size patches, FIFO), issues the tensor-TMA boxes
+//     (or per-row bulk copies) that complete on the item's mbarrier, and meanwhile prepares
+//     everything that is uniform per tile or per row -- the 12 residual-polynomial coefficients,
+//     the float64 affine base and the destination address of each of the 32 rows -- so that the
+//     consumers spend their issue slots on pixels only;
 //   * eight consumer warps each own 4 rows of every tile and never synchronise with one another:
-//     wait for the item's mbarrier, derive the 4 rows' polynomial coefficients, sample 4 pixels
-//     per lane, write their rows of the output tile to a per-warp double-buffered stage and send
-//     them off as bulk-async row stores; the last reader of a patch releases it to the producer
-//     through a second mbarrier (8 arrivals).
+//     wait for the item's mbarrier, sample 4 pixels per lane, write their rows of the output tile
+//     to a per-warp double-buffered stage and send them off as bulk-async row stores; the last
+//     reader of a patch releases it to the producer through a second mbarrier (8 arrivals).
 
 // FIFO allocator for variable-size patches in the shared-memory ring.  The bytes in flight form
 // one circular interval [tail, head) of length `used`; allocations are contiguous (an allocation
@@ -373,21 +393,29 @@ struct TiledParams {
     const TilePlan* plans;  // whole plan (all views)
 };
 
-constexpr int kSlots = 8;                               // work items in flight per block
+constexpr int kSlots = 4;                               // work items in flight per block
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kTiledThreads = kConsumerThreads + 32;
-struct SlotInfo {            // written by the producer, read by the consumers of the item
-    int off;                 // ring offset of the patch
+
+struct SlotInfo {            // per item, written by the producer
+    uint32_t patch_saddr;    // shared-memory address of the patch
+    uint32_t bias;           // 8-bit RGB fast path: tap address bias (r360_fast_u8.cuh)
     int size;                // ring bytes to give back on release
-    int i0, j0;              // tile origin in the output image
-    long long dst_off;       // byte offset of the destination image (frame, view) in the batch
+    int mode;                // TileMode
+    int pitch, xb0, py0;     // patch geometry
+    int full_tile;           // the tile lies completely inside the destination image
+    int i0, j0;
+    long long dst_tile;      // byte offset of the tile's first output pixel inside the destination batch
+    long long dst_off;       // byte offset of the destination image (frame, view)
     long long pad;
 };
-static_assert(sizeof(SlotInfo) == 32, "SlotInfo layout");
-// barriers (128) + slot info (8 x 32) + row coefficients (1536) + plan records (8 x 368)
-constexpr int kTiledFixedSmem = 128 + kSlots * 32 + 1536 + kSlots * 368;      // 4864
+static_assert(sizeof(SlotInfo) == 64, "SlotInfo layout");
+
 constexpr int kTableBytes = 32 * 32 * 16 * 2;
+// barriers (64) + slot info + per-warp row coefficients (32 rows x 12 floats) + plan records
+constexpr int kTiledFixedSmem = (64 + kSlots * 64 + 1536 + kSlots * 368 + 127) / 128 * 128;      // 3456
+static_assert(kTiledFixedSmem % 128 == 0 && kTableBytes % 128 == 0, "ring alignment");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -406,13 +434,15 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [kSlots]
     uint64_t* empty = full + kSlots;                               // [kSlots]
-    SlotInfo* slots = reinterpret_cast<SlotInfo*>(smem + 128);     // [kSlots]
-    float* rowc = reinterpret_cast<float*>(smem + 128 + kSlots * 32);            // [32 rows][12]
-    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 128 + kSlots * 32 + 1536);
+    SlotInfo* slots = reinterpret_cast<SlotInfo*>(smem + 64);      // [kSlots]
+    float* rowc = reinterpret_cast<float*>(smem + 64 + kSlots * 64);             // [32 rows][12], per-warp regions
+    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 64 + kSlots * 64 + 1536);   // [kSlots]
     unsigned char* table = smem + kTiledFixedSmem;
     unsigned char* stage0 = table + (P.use_table ? kTableBytes : 0);
-    unsigned char* ring = stage0 + 2 * P.out_stage_bytes;
+    unsigned char* ring = stage0 + P.out_stage_bytes;
 
+    constexpr bool kFastU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
+                             INTERP != kNearest;
     const int tid = threadIdx.x;
     const int n_tiles = P.tiles_x * P.tiles_y;
     const int total = P.n_groups * P.n_views * n_tiles;             // the host keeps this below 2^31
@@ -428,22 +458,45 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
     __syncthreads();
 
     if (tid >= kConsumerThreads) {
-        // ================= producer warp ==========================================================
+        // ================= producer warp: keep it short, it is the serial part of the pipeline ======
         const int lane = tid - kConsumerThreads;
         PatchRing ringst;                // identical in every lane
-        int oldest = 0;
-        int k = 0;
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++k) {
+        int oldest = 0, k = 0;
+        // (tile, view, group) of the current item, advanced incrementally (no divisions in the loop)
+        int item = blockIdx.x;
+        int tile = item % n_tiles, unit = item / n_tiles;
+        int v = unit % P.n_views, g = unit / P.n_views;
+        int ti = tile % P.tiles_x, tj = tile / P.tiles_x;
+        const int step_tile = gridDim.x % n_tiles, step_unit = gridDim.x / n_tiles;
+        const int step_ti = step_tile % P.tiles_x, step_tj = step_tile / P.tiles_x;
+        // geometry of the item about to be processed: lanes 0 and 1 hold the record's last two
+        // 16-byte pieces (py0 rows xb0 row_bytes | pitch mode_slot - -), prefetched one item ahead
+        int4 geo = make_int4(0, 0, 0, 0);
+        const TilePlan* gp = P.plans + (long long)v * n_tiles + tile;
+        if (item < total && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
+        for (; item < total; item += gridDim.x, ++k) {
             const int slot = k & (kSlots - 1);
-            const int tile = item % n_tiles, unit = item / n_tiles;
-            const int v = unit % P.n_views, g = unit / P.n_views;
-            const TilePlan* gp = P.plans + (long long)v * n_tiles + tile;
-            const int4 geo0 = __ldg(reinterpret_cast<const int4*>(gp) + 21);   // py0 rows xb0 row_bytes
-            const int4 geo1 = __ldg(reinterpret_cast<const int4*>(gp) + 22);   // pitch mode_slot - -
-            const int mode = geo1.y & 0xff, src_slot = (geo1.y >> 8) & 0xff, wbox = geo1.y >> 16;
+            const int py0 = __shfl_sync(0xffffffffu, geo.x, 0), rows_needed = __shfl_sync(0xffffffffu, geo.y, 0);
+            const int xb0 = __shfl_sync(0xffffffffu, geo.z, 0), row_bytes = __shfl_sync(0xffffffffu, geo.w, 0);
+            const int pitch = __shfl_sync(0xffffffffu, geo.x, 1), mode_slot = __shfl_sync(0xffffffffu, geo.y, 1);
+            const TilePlan* gp_cur = gp;
+            const int cur_g = g, cur_v = v, cur_ti = ti, cur_tj = tj;
+            // advance to the next item and start fetching its geometry
+            {
+                int du = step_unit;
+                ti += step_ti; tj += step_tj;
+                if (ti >= P.tiles_x) { ti -= P.tiles_x; ++tj; }
+                tile += step_tile;
+                if (tile >= n_tiles) { tile -= n_tiles; tj -= P.tiles_y; ++du; }
+                v += du;
+                while (v >= P.n_views) { v -= P.n_views; ++g; }
+            }
+            gp = P.plans + (long long)v * n_tiles + tile;
+            if (item + (int)gridDim.x < total && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
+
+            const int mode = mode_slot & 0xff, src_slot = (mode_slot >> 8) & 0xff, wbox = mode_slot >> 16;
             const bool staged = mode == kModeFast || mode == kModeFastRows;
-            const int py0 = geo0.x, rows = staged ? geo0.y : 0;
-            const int xb0 = geo0.z, row_bytes = geo0.w, pitch = geo1.x;
+            const int rows = staged ? rows_needed : 0;
             const int srows = mode == kModeFast ? staged_rows(rows) : rows;      // rows written to the ring
             const int need = (srows * pitch + 127) & ~127;
             // ---- find room: wait for the oldest items to be released until the patch fits ---------
@@ -453,28 +506,39 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                 ringst.release(slots[oldest & (kSlots - 1)].size, P.ring_bytes);
                 ++oldest;
             }
-            __syncwarp();
+            unsigned char* patch = ring + off;
+            __syncwarp();                                              // slots[] reads above are done
             if (lane == 0) {
+                const int i0 = cur_ti * kTile, j0 = cur_tj * kTile;
                 SlotInfo si;
-                si.off = off; si.size = charge;
-                si.i0 = (tile % P.tiles_x) * kTile; si.j0 = (tile / P.tiles_x) * kTile;
-                si.dst_off = ((long long)g * P.n_views + v) * P.dst.image_stride; si.pad = 0;
+                si.patch_saddr = smem_u32(patch);
+                si.bias = 0;
+                if (kFastU8) {
+                    si.bias = patch_bias_u8c3(si.patch_saddr, pitch, xb0, py0);
+                    if (INTERP == kCubic) si.bias -= 3u + (uint32_t)pitch;
+                }
+                si.size = charge; si.mode = mode; si.pitch = pitch; si.xb0 = xb0; si.py0 = py0;
+                si.full_tile = (i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height) ? 1 : 0;
+                si.i0 = i0; si.j0 = j0;
+                si.dst_off = ((long long)cur_g * P.n_views + cur_v) * P.dst.image_stride;
+                si.dst_tile = si.dst_off + (long long)j0 * P.dst.pitch + (long long)i0 * P.channels * (int)sizeof(TOut);
+                si.pad = 0;
                 slots[slot] = si;
-                mbar_expect_tx(&full[slot], (uint32_t)(sizeof(TilePlan) + (mode == kModeFast ? srows * pitch : rows * row_bytes)));
-                bulk_g2s(&planbuf[slot], gp, (uint32_t)sizeof(TilePlan), &full[slot]);
+                const uint32_t patch_bytes = !staged ? 0u : (uint32_t)(mode == kModeFast ? srows * pitch : rows * row_bytes);
+                mbar_expect_tx(&full[slot], (uint32_t)sizeof(TilePlan) + patch_bytes);     // arrive + expect
+                bulk_g2s(&planbuf[slot], gp_cur, (uint32_t)sizeof(TilePlan), &full[slot]);
             }
             __syncwarp();
-            unsigned char* patch = ring + off;
             if (mode == kModeFast) {
                 // a few tensor boxes: 32-row boxes first, then 8-row boxes
                 const int n32 = rows / 32, n8 = ((rows % 32) + 7) / 8;
                 if (lane < n32 + n8) {
                     const int r0 = lane < n32 ? lane * 32 : n32 * 32 + (lane - n32) * 8;
                     const CUtensorMap* tm = &maps.m[wbox * kNumBoxHeights + (lane < n32 ? 0 : 1)];
-                    tensor_g2s_3d(patch + r0 * pitch, tm, xb0 >> 2, py0 + r0, g * P.n_lenses + src_slot, &full[slot]);
+                    tensor_g2s_3d(patch + r0 * pitch, tm, xb0 >> 2, py0 + r0, cur_g * P.n_lenses + src_slot, &full[slot]);
                 }
-            } else {
-                const unsigned char* img = P.src.data + ((long long)g * P.n_lenses + src_slot) * P.src.image_stride;
+            } else if (mode == kModeFastRows) {
+                const unsigned char* img = P.src.data + ((long long)cur_g * P.n_lenses + src_slot) * P.src.image_stride;
                 for (int r = lane; r < rows; r += 32) {
                     const int sy = min(max(py0 + r, 0), P.src.height - 1);            // pole rows replicate
                     bulk_g2s(patch + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[slot]);
@@ -489,70 +553,83 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
     const int jl = tid >> 3;                 // tile row of this thread (4 rows per warp)
     const int il0 = (tid & 7) * 4;           // first of its 4 pixels
     const int row_out_bytes = kTile * P.channels * (int)sizeof(TOut);
+    const float s0 = (float)(2 * il0 - (kTile - 1)) * (1.0f / (kTile - 1));
+    const float ds = 2.0f / (kTile - 1);
+    const float trow = (float)(2 * jl - (kTile - 1)) * (1.0f / (kTile - 1));
+    const double dil0 = (double)il0, djl = (double)jl;
     float* rc = rowc + jl * 12;
+    // residual-coefficient tasks of this lane: coefficient c0 = lane & 7 always, c1 = c0 + 8 for c0 < 4
+    const int ctask0 = lane & 7, ctask1 = ctask0 + 8;
+    const int koff0 = ctask0 < 6 ? ctask0 : 36 + ctask0 - 6;             // float offset into rx[36] ry[36]
+    const int koff1 = 36 + ctask1 - 6;
+    // this lane's share of the warp's 4 output rows when they leave as 16-byte chunks
+    const int chunks_per_row = row_out_bytes >> 4;                        // 6 for 8-bit RGB
+    const int st_r = lane / chunks_per_row, st_c = lane - st_r * chunks_per_row;
+    const int st_dr = 32 / chunks_per_row, st_dc = 32 - st_dr * chunks_per_row;
+    const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty);
+    unsigned char* stage = stage0;          // each warp only ever touches its own 4 rows of it
+    TOut* stage_row = reinterpret_cast<TOut*>(stage) + (jl * kTile + il0) * P.channels;
     int k = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++k) {
         const int slot = k & (kSlots - 1);
-        mbar_wait(&full[slot], (k / kSlots) & 1);
-        const TilePlan* plan = &planbuf[slot];
-        const int mode = plan->mode_slot & 0xff;
+        mbar_wait_s(full_s + slot * 8, (k / kSlots) & 1);
+        const SlotInfo* si = &slots[slot];
+        const int mode = si->mode;
         if (mode == kModeFallback) {                       // remap_fallback_kernel owns this tile
-            if (lane < 4) bulk_commit();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
+            if (lane == 0) mbar_arrive_s(empty_s + slot * 8);
             continue;
         }
-        const SlotInfo si = slots[slot];
-        const int i0 = si.i0, j0 = si.j0;
-        unsigned char* stage = stage0 + (k & 1) * P.out_stage_bytes;
-        TOut* stage_row = reinterpret_cast<TOut*>(stage) + (jl * kTile + il0) * P.channels;
-        if (lane < 4) bulk_wait_read_1();      // this warp's stores from two items ago have left the stage
+        const TilePlan* plan = &planbuf[slot];
         if (mode != kModeFill) {
-            // the 12 coefficients of this lane's row, spread over the 8 lanes that share the row
-            const float t = (float)(2 * jl - (kTile - 1)) * (1.0f / (kTile - 1));
-            for (int c = lane & 7; c < 12; c += 8) {
-                const float* K = (c < 6 ? plan->rx : plan->ry) + (c < 6 ? c : c - 6);
-                float a = K[30];
+            // the 12 residual coefficients of this lane's row, spread over the 8 lanes that share the row
+            const float* K = plan->rx + koff0;
+            float a = K[30];
 #pragma unroll
-                for (int l = 4; l >= 0; --l) a = fmaf(a, t, K[l * 6]);
-                rc[c] = a;
+            for (int l = 4; l >= 0; --l) a = fmaf(a, trow, K[l * 6]);
+            rc[ctask0] = a;
+            if (ctask0 < 4) {
+                const float* K1 = plan->rx + koff1;
+                float b = K1[30];
+#pragma unroll
+                for (int l = 4; l >= 0; --l) b = fmaf(b, trow, K1[l * 6]);
+                rc[ctask1] = b;
             }
         }
         __syncwarp();
         if (mode == kModeFill) {
             for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
         } else {
-            const unsigned char* patch = ring + si.off;
-            // affine part in float64 (absolute, exact to ~1e-10 px), residual in float32; the final
-            // double -> float conversion IS the float32 cast of the map cv2.remap would be given
-            const double bx = fma(plan->ax[2], (double)jl, plan->ax[0]), by = fma(plan->ay[2], (double)jl, plan->ay[0]);
+            // residual polynomial in float32, affine part in float64 (absolute, exact to ~1e-10 px);
+            // the final double -> float conversion IS the float32 cast of the map cv2.remap would get
+            const float4 c0 = *reinterpret_cast<const float4*>(rc), c1 = *reinterpret_cast<const float4*>(rc + 4),
+                         c2 = *reinterpret_cast<const float4*>(rc + 8);
             const double axi = plan->ax[1], ayi = plan->ay[1];
+            double ax_q = fma(axi, dil0, fma(plan->ax[2], djl, plan->ax[0]));
+            double ay_q = fma(ayi, dil0, fma(plan->ay[2], djl, plan->ay[0]));
             float sxf[4], syf[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float s = (float)(2 * (il0 + q) - (kTile - 1)) * (1.0f / (kTile - 1));
-                float dx = rc[5], dy = rc[11];
-#pragma unroll
-                for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
-                sxf[q] = __double2float_rn(fma(axi, (double)(il0 + q), bx) + (double)dx);
-                syf[q] = __double2float_rn(fma(ayi, (double)(il0 + q), by) + (double)dy);
+                const float s = fmaf((float)q, ds, s0);
+                float dx = c1.y, dy = c2.w;
+                dx = fmaf(dx, s, c1.x); dx = fmaf(dx, s, c0.w); dx = fmaf(dx, s, c0.z); dx = fmaf(dx, s, c0.y); dx = fmaf(dx, s, c0.x);
+                dy = fmaf(dy, s, c2.z); dy = fmaf(dy, s, c2.y); dy = fmaf(dy, s, c2.x); dy = fmaf(dy, s, c1.w); dy = fmaf(dy, s, c1.z);
+                sxf[q] = __double2float_rn(ax_q + (double)dx);
+                syf[q] = __double2float_rn(ay_q + (double)dy);
+                ax_q += axi; ay_q += ayi;
             }
             bool done = false;
-            if constexpr (std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
-                          INTERP != kNearest) {
+            if constexpr (kFastU8) {
                 if (P.channels == 3) {
-                    uint32_t bias = patch_bias_u8c3(smem_u32(patch), plan->pitch, plan->xb0, plan->py0);
+                    const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch;
                     uint32_t px[4];
                     if constexpr (INTERP == kLinear) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            px[q] = bilinear_u8c3(bias, (uint32_t)plan->pitch, round_bits(sxf[q]), round_bits(syf[q]));
+                        for (int q = 0; q < 4; ++q) px[q] = bilinear_u8c3(bias, pitch, round_bits(sxf[q]), round_bits(syf[q]));
                     } else {
-                        bias -= 3u + (uint32_t)plan->pitch;
                         const uint32_t tab = smem_u32(table);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            px[q] = bicubic_u8c3(bias, (uint32_t)plan->pitch, tab, round_bits(sxf[q]), round_bits(syf[q]));
+                        for (int q = 0; q < 4; ++q) px[q] = bicubic_u8c3(bias, pitch, tab, round_bits(sxf[q]), round_bits(syf[q]));
                     }
                     uint32_t w0, w1, w2;
                     pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
@@ -562,7 +639,8 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                 }
             }
             if (!done) {
-                const PatchTaps<TIn> taps{patch, plan->pitch, plan->xb0, plan->py0, P.channels};
+                unsigned char* patch = smem + (si->patch_saddr - smem_u32(smem));
+                const PatchTaps<TIn> taps{patch, si->pitch, si->xb0, si->py0, P.channels};
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
@@ -570,19 +648,24 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                                                     stage_row + q * P.channels);
             }
         }
-        // ---- this warp's 4 rows leave; the patch is released ------------------------------------------
-        unsigned char* dst_base = P.dst.data + si.dst_off;
-        const bool full_tile = i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height;
-        if (full_tile && P.bulk_store_ok) {
-            fence_async_shared();
-            __syncwarp();
-            if (lane < 4) {
-                const int r = warp * 4 + lane;
-                bulk_s2g(dst_base + (long long)(j0 + r) * P.dst.pitch + (long long)i0 * P.channels * sizeof(TOut),
-                         stage + r * row_out_bytes, (uint32_t)row_out_bytes);
+        // ---- this warp's 4 rows leave as 16-byte vector stores; the patch is released ----------------
+        const bool vec_store = si->full_tile && P.bulk_store_ok;
+        const long long dst_tile = si->dst_tile;
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(empty_s + slot * 8);  // all 8 warps arrived -> the producer may reuse the bytes
+        if (vec_store) {
+            unsigned char* dst_rows = P.dst.data + dst_tile + (long long)(warp * 4) * P.dst.pitch;
+            const unsigned char* src_rows = stage + warp * 4 * row_out_bytes;
+            // chunk e = lane, lane + 32, ... of the 4 * chunks_per_row chunks; (r, c) advanced without dividing
+            for (int r = st_r, c = st_c; r < 4;) {
+                *reinterpret_cast<int4*>(dst_rows + (long long)r * P.dst.pitch + c * 16) =
+                    *reinterpret_cast<const int4*>(src_rows + r * row_out_bytes + c * 16);
+                r += st_dr; c += st_dc;
+                if (c >= chunks_per_row) { c -= chunks_per_row; ++r; }
             }
         } else {
-            __syncwarp();
+            const int i0 = si->i0, j0 = si->j0;
+            unsigned char* dst_base = P.dst.data + si->dst_off;
             const int nelem = kTile * P.channels;
             for (int e = lane; e < 4 * nelem; e += 32) {
                 const int r = warp * 4 + e / nelem, c = e % nelem;
@@ -591,12 +674,9 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                     reinterpret_cast<TOut*>(dst_base + (long long)j * P.dst.pitch)[(long long)i0 * P.channels + c] =
                         reinterpret_cast<const TOut*>(stage)[r * nelem + c];
             }
-            __syncwarp();
         }
-        if (lane < 4) bulk_commit();               // one (possibly empty) group per item keeps the count in step
-        if (lane == 0) mbar_arrive(&empty[slot]);  // all 8 warps arrived -> the producer may reuse the bytes
+        __syncwarp();                              // the stage rows are free again
     }
-    if (lane < 4) bulk_wait_read_all();
 }
 
 // Debug twin: what the tiled kernel samples at, written as maps (r360_plan_coords).  One block per

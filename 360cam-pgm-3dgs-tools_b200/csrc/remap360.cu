@@ -434,7 +434,7 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
         int want = pl->use_table ? 2 : 4;
         if (const char* env = std::getenv("R360_TILED_CTAS_PER_SM")) want = std::atoi(env) > 0 ? std::atoi(env) : want;
-        const int fixed = kTiledFixedSmem + (pl->use_table ? kTableBytes : 0) + 2 * pl->out_stage_bytes + 128;
+        const int fixed = kTiledFixedSmem + (pl->use_table ? kTableBytes : 0) + pl->out_stage_bytes + 128;
         for (;; --want) {
             const int per_block = smem_per_sm / want - 1024;       // 1 KB per block is reserved by the driver
             pl->ring_bytes = (per_block - fixed) & ~127;
@@ -469,6 +469,7 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     P.n_views = n_views; P.src_w = src->width; P.src_h = src->height; P.px_bytes = src->channels * in_es;
     P.patch_budget = pl->patch_budget; P.bulk_load_ok = pl->bulk_load_ok; P.tensor_ok = pl->tensor_ok;
     P.fill_invalid = pl->pr.lp.fill_invalid;
+    P.interp = pl->pr.interp;
     P.erp = pl->pr.lp.erp;
     std::memcpy(P.lens, pl->pr.lp.lens, sizeof(P.lens));
     P.views = pl->d_views; P.plans = pl->d_plans; P.header = pl->d_header; P.fallback = pl->d_fallback;
