@@ -322,9 +322,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tensor_g2s_3d(void* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+// L2 policies: the source frame is re-read by every view of the frame -> keep it (evict_last);
+// output tiles are written once and never read -> stream them (st.global.cs below).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tensor_g2s_3d(void* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar,
+                                              uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+                 "[%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_global_streaming(void* gptr, const int4& v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -462,6 +474,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
         const int lane = tid - kConsumerThreads;
         PatchRing ringst;                // identical in every lane
         int oldest = 0, k = 0;
+        const uint64_t keep = l2_policy_evict_last();
         // (tile, view, group) of the current item, advanced incrementally (no divisions in the loop)
         int item = blockIdx.x;
         int tile = item % n_tiles, unit = item / n_tiles;
@@ -535,7 +548,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                 if (lane < n32 + n8) {
                     const int r0 = lane < n32 ? lane * 32 : n32 * 32 + (lane - n32) * 8;
                     const CUtensorMap* tm = &maps.m[wbox * kNumBoxHeights + (lane < n32 ? 0 : 1)];
-                    tensor_g2s_3d(patch + r0 * pitch, tm, xb0 >> 2, py0 + r0, cur_g * P.n_lenses + src_slot, &full[slot]);
+                    tensor_g2s_3d(patch + r0 * pitch, tm, xb0 >> 2, py0 + r0, cur_g * P.n_lenses + src_slot, &full[slot], keep);
                 }
             } else if (mode == kModeFastRows) {
                 const unsigned char* img = P.src.data + ((long long)cur_g * P.n_lenses + src_slot) * P.src.image_stride;
@@ -597,6 +610,43 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             }
         }
         __syncwarp();
+        if constexpr (kFastU8 && INTERP == kCubic) {
+            // ---- bicubic 8-bit RGB: lane = pixel column, 4 rows per lane -------------------------------
+            // Sixteen taps per pixel make this path shared-memory bound; with adjacent lanes on adjacent
+            // pixels the tap loads of a warp fall into neighbouring words (few bank conflicts), and the
+            // finished row leaves straight from registers: three lanes out of four hold one 32-bit
+            // word of the 96-byte row after a shuffle, so the store is contiguous.
+            if (mode != kModeFill && P.channels == 3 && si->full_tile && P.bulk_store_ok) {
+                const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch, tab = smem_u32(table);
+                const float s = (float)(2 * lane - (kTile - 1)) * (1.0f / (kTile - 1));
+                const double axi = plan->ax[1], ayi = plan->ay[1], axj = plan->ax[2], ayj = plan->ay[2];
+                double ax_r = fma(axi, (double)lane, fma(axj, (double)(warp * 4), plan->ax[0]));
+                double ay_r = fma(ayi, (double)lane, fma(ayj, (double)(warp * 4), plan->ay[0]));
+                const int m = lane & 3;
+                unsigned char* out_word = P.dst.data + si->dst_tile + (long long)(warp * 4) * P.dst.pitch +
+                                          ((lane >> 2) * 3 + m) * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float* rq = rowc + (warp * 4 + q) * 12;
+                    const float4 c0 = *reinterpret_cast<const float4*>(rq), c1 = *reinterpret_cast<const float4*>(rq + 4),
+                                 c2 = *reinterpret_cast<const float4*>(rq + 8);
+                    float dx = c1.y, dy = c2.w;
+                    dx = fmaf(dx, s, c1.x); dx = fmaf(dx, s, c0.w); dx = fmaf(dx, s, c0.z); dx = fmaf(dx, s, c0.y); dx = fmaf(dx, s, c0.x);
+                    dy = fmaf(dy, s, c2.z); dy = fmaf(dy, s, c2.y); dy = fmaf(dy, s, c2.x); dy = fmaf(dy, s, c1.w); dy = fmaf(dy, s, c1.z);
+                    const float sx = __double2float_rn(ax_r + (double)dx), sy = __double2float_rn(ay_r + (double)dy);
+                    ax_r += axj; ay_r += ayj;
+                    const uint32_t own = bicubic_u8c3(bias, pitch, tab, round_bits(sx), round_bits(sy));
+                    const uint32_t nxt = __shfl_down_sync(0xffffffffu, own, 1);
+                    const uint32_t word = (own >> (8 * m)) | (nxt << (24 - 8 * m));
+                    if (m < 3) {
+                        asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(out_word + (long long)q * P.dst.pitch), "r"(word) : "memory");
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(empty_s + slot * 8);
+                continue;
+            }
+        }
         if (mode == kModeFill) {
             for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
         } else {
@@ -658,8 +708,8 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             const unsigned char* src_rows = stage + warp * 4 * row_out_bytes;
             // chunk e = lane, lane + 32, ... of the 4 * chunks_per_row chunks; (r, c) advanced without dividing
             for (int r = st_r, c = st_c; r < 4;) {
-                *reinterpret_cast<int4*>(dst_rows + (long long)r * P.dst.pitch + c * 16) =
-                    *reinterpret_cast<const int4*>(src_rows + r * row_out_bytes + c * 16);
+                st_global_streaming(dst_rows + (long long)r * P.dst.pitch + c * 16,
+                                    *reinterpret_cast<const int4*>(src_rows + r * row_out_bytes + c * 16));
                 r += st_dr; c += st_dc;
                 if (c >= chunks_per_row) { c -= chunks_per_row; ++r; }
             }

@@ -49,6 +49,15 @@ FOOTPRINT_PX = {
 }
 
 
+# DRAM traffic of ONE launch of the tiled kernel at the bench configuration (16 frames x 12 views),
+# dram__bytes_read.sum + dram__bytes_write.sum from the `ncu --set full` captures summarised in
+# profiles/ (r01_tiled_*_b16.json).  Only valid for the default workload.
+NCU_TRAFFIC_BYTES = {
+    ("full360coverage", "cubic", 16): None,
+    ("full360coverage", "linear", 16): None,
+}
+
+
 def preset_views(preset, size):
     """(views, hfov) of a gs360_360PerspCut preset through the drop-in planner."""
     from remap360 import perspcut
@@ -74,7 +83,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -166,7 +175,7 @@ def cpu_reference_arm(views, size, interp, seconds_budget, steps=None, warmup=1)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--interp", choices=["cubic", "linear"], default="cubic",
@@ -178,6 +187,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip timing the other interpolation")
     ns = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -235,8 +245,8 @@ def main():
         frames[f] = torch.randint(0, 256, (ERP_H, ERP_W, CHANNELS), dtype=torch.uint8, device=dev, generator=g)
     out = torch.empty((ns.frames, n_views, ns.size, ns.size, CHANNELS), dtype=torch.uint8, device=dev)
 
-    def step():
-        remap360.remap_erp(frames, pviews, (ns.size, ns.size), interp=ns.interp, out=out, path=ns.path)
+    def step(interp=ns.interp):
+        remap360.remap_erp(frames, pviews, (ns.size, ns.size), interp=interp, out=out, path=ns.path)
 
     def barrier():
         torch.cuda.synchronize()
@@ -244,45 +254,64 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(ns.warmup):
-        step()
-    barrier()
-    launches0 = remap360.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(ns.steps + 1)]
-    with ClockSampler(local_rank) as clocks:
+    def timed(interp, steps, warmup, sample_clocks):
+        """K steps bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks."""
+        for _ in range(warmup):
+            step(interp)
+        barrier()
+        l0 = remap360.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
         ev[0].record()
-        for k in range(ns.steps):
-            step()
+        for k in range(steps):
+            step(interp)
             ev[k + 1].record()
         barrier()
-    launches = remap360.launch_count() - launches0
-    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(ns.steps)]
-    total_ms = ev[0].elapsed_time(ev[ns.steps])
-    if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / ns.steps
+        if sampler:
+            sampler.__exit__(None, None, None)
+        per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+        total = ev[0].elapsed_time(ev[steps])
+        if dist is not None:
+            t = torch.tensor([total], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total / steps, per_step, remap360.launch_count() - l0, sampler
+
+    ms_per_step, step_ms, launches, clocks = timed(ns.interp, ns.steps, ns.warmup, True)
     out_pix_step = ns.frames * n_views * ns.size * ns.size
     value = out_pix_step * world / (ms_per_step * 1e-3) / 1e6          # Mpix/s, whole job
 
-    # roofline of the dominant kernel: one launch per step (<=16 views) -> launch time = step time
+    # roofline of the dominant kernel (remap_tiled_kernel: one launch per step covers the whole batch;
+    # the small fallback-tile launch that follows it is part of the step time used here)
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    u_px = FOOTPRINT_PX.get((ns.preset, ns.interp))
-    launches_per_step = max(1, launches // ns.steps)
-    roofline = None
-    if u_px is not None and ns.size == 1600:
-        bytes_per_frame = (u_px + n_views * ns.size * ns.size) * CHANNELS
-        bytes_per_launch = bytes_per_frame * ns.frames / launches_per_step
-        kernel_ms = statistics.median(step_ms) / launches_per_step
+
+    def roofline_for(interp, per_step_ms):
+        u_px = FOOTPRINT_PX.get((ns.preset, interp))
+        if u_px is None or ns.size != 1600:
+            return None
+        bytes_per_launch = (u_px + n_views * ns.size * ns.size) * CHANNELS * ns.frames
+        kernel_ms = statistics.median(per_step_ms)
         achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "kernel_ms": kernel_ms, "launches_per_step": launches_per_step}
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_TRAFFIC_BYTES.get((ns.preset, interp, ns.frames)), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": kernel_ms,
+                "kernel": "remap_tiled_kernel<%s, u8, u8> (+ remap_fallback_kernel for %s)" % (
+                    interp, "tiles the plan routes to the direct path")}
+
+    roofline = roofline_for(ns.interp, step_ms)
+    # the other interpolation on the same workload (kernel-only), for context
+    variants = {}
+    if not ns.no_variants:
+        other = "linear" if ns.interp == "cubic" else "cubic"
+        o_ms, o_steps, _, _ = timed(other, max(3, ns.steps // 2), 3, False)
+        variants[other] = {"value": out_pix_step * world / (o_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": o_ms,
+                           "roofline": roofline_for(other, o_steps)}
 
     # ------------------------------------------------------------------ end to end (host buffers)
     e2e = None
@@ -330,7 +359,7 @@ def main():
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "views_per_s": value * 1e6 / (ns.size * ns.size), "frames_per_s": value * 1e6 / (n_views * ns.size * ns.size),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "variants": variants}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
