@@ -43,7 +43,9 @@ __host__ __device__ constexpr int tap_margin_hi(int interp) { return interp == k
 
 // kModeFast: patch staged with 2-D tensor TMA boxes; kModeFastRows: staged row by row with 1-D bulk
 // copies (rows clamped at the poles, or wider than the largest box).
-enum TileMode : int { kModeFallback = 0, kModeFast = 1, kModeFill = 2, kModeFastRows = 3 };
+// kModeFastSeam: a panorama tile that straddles the +-180 degree seam: rows are staged in two pieces
+// (unwrapped in shared memory) and every pixel wraps its coordinate before the float32 cast.
+enum TileMode : int { kModeFallback = 0, kModeFast = 1, kModeFill = 2, kModeFastRows = 3, kModeFastSeam = 4 };
 
 // Box shapes of the tensor-TMA descriptors: widths in bytes (odd multiples of 32 keep consecutive
 // rows on different banks; 1024 = 256 uint32 elements is the hardware limit) x heights {32, 8}.
@@ -244,8 +246,12 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
             row_bytes = xb1 - xb0;
             rows = ys1 - ys0 + 1;
             // columns must lie inside one period of the panorama / inside the sensor
-            bool fast = P.bulk_load_ok && xs0 >= 0 && xb1 <= P.src_w * P.px_bytes;
+            const int row_total = P.src_w * P.px_bytes;
+            bool fast = P.bulk_load_ok && xs0 >= 0 && xb1 <= row_total;
             if (PROJ == kProjFisheye) fast = fast && ys0 >= 0 && ys1 < P.src_h && invalid_count == 0;
+            // seam: only when the coordinate period equals the image width (halfpixel convention)
+            const bool seam = PROJ == kProjErp && P.bulk_load_ok && !fast && P.erp.su == (double)P.src_w &&
+                              row_bytes <= row_total && xb0 > -row_total && xb1 < 2 * row_total;
             if (fast) {
                 while (wbox < kNumBoxWidths && box_width_bytes(wbox) < row_bytes) ++wbox;
                 const bool rows_inside = ys0 >= 0 && ys1 < P.src_h;
@@ -258,6 +264,9 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
                     pitch = row_bytes + ((row_bytes & 127) == 0 ? 16 : 0);   // keep rows off the same banks
                     if (rows * pitch <= P.patch_budget) mode = kModeFastRows;
                 }
+            } else if (seam) {
+                pitch = row_bytes + ((row_bytes & 127) == 0 ? 16 : 0);
+                if (rows * pitch <= P.patch_budget) mode = kModeFastSeam;
             }
         }
         if (PROJ == kProjFisheye && P.fill_invalid && valid_count == 0) mode = kModeFill;
@@ -508,7 +517,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             if (item + (int)gridDim.x < total && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
 
             const int mode = mode_slot & 0xff, src_slot = (mode_slot >> 8) & 0xff, wbox = mode_slot >> 16;
-            const bool staged = mode == kModeFast || mode == kModeFastRows;
+            const bool staged = mode == kModeFast || mode == kModeFastRows || mode == kModeFastSeam;
             const int rows = staged ? rows_needed : 0;
             const int srows = mode == kModeFast ? staged_rows(rows) : rows;      // rows written to the ring
             const int need = (srows * pitch + 127) & ~127;
@@ -555,6 +564,20 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                 for (int r = lane; r < rows; r += 32) {
                     const int sy = min(max(py0 + r, 0), P.src.height - 1);            // pole rows replicate
                     bulk_g2s(patch + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[slot]);
+                }
+            } else if (mode == kModeFastSeam) {
+                // the patch spans the seam: its first bytes come from the end of the image row, the rest
+                // from its beginning (both pieces are multiples of 16 bytes)
+                const unsigned char* img = P.src.data + ((long long)cur_g * P.n_lenses + src_slot) * P.src.image_stride;
+                const int row_total = P.src.width * P.channels * (int)sizeof(TIn);
+                const int start = xb0 < 0 ? xb0 + row_total : xb0;                   // wrapped first byte
+                const int len1 = min(row_bytes, row_total - start);
+                for (int r = lane; r < rows; r += 32) {
+                    const int sy = min(max(py0 + r, 0), P.src.height - 1);
+                    const unsigned char* row = img + (long long)sy * P.src.pitch;
+                    bulk_g2s(patch + r * pitch, row + start, (uint32_t)len1, &full[slot]);
+                    if (len1 < row_bytes)
+                        bulk_g2s(patch + r * pitch + len1, row, (uint32_t)(row_bytes - len1), &full[slot]);
                 }
             }
         }
@@ -616,7 +639,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             // pixels the tap loads of a warp fall into neighbouring words (few bank conflicts), and the
             // finished row leaves straight from registers: three lanes out of four hold one 32-bit
             // word of the 96-byte row after a shuffle, so the store is contiguous.
-            if (mode != kModeFill && P.channels == 3 && si->full_tile && P.bulk_store_ok) {
+            if (mode != kModeFill && mode != kModeFastSeam && P.channels == 3 && si->full_tile && P.bulk_store_ok) {
                 const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch, tab = smem_u32(table);
                 const float s = (float)(2 * lane - (kTile - 1)) * (1.0f / (kTile - 1));
                 const double axi = plan->ax[1], ayi = plan->ay[1], axj = plan->ax[2], ayj = plan->ay[2];
@@ -649,6 +672,31 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
         }
         if (mode == kModeFill) {
             for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
+        } else if (mode == kModeFastSeam) {
+            // ---- a tile on the +-180 degree seam: same arithmetic, one pixel at a time, the coordinate
+            //      wrapped into (-0.5, W - 0.5] before the float32 cast; the taps of a wrapped pixel sit one
+            //      image width further along the (unwrapped) patch -------------------------------------
+            unsigned char* patch = smem + (si->patch_saddr - smem_u32(smem));
+            const int row_total = P.src.width * P.channels * (int)sizeof(TIn);
+            const double period32 = 32.0 * P.src.width;
+            const double axi = plan->ax[1], ayi = plan->ay[1];
+            const double ax_b = fma(plan->ax[2], djl, plan->ax[0]), ay_b = fma(plan->ay[2], djl, plan->ay[0]);
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const float s = fmaf((float)q, ds, s0);
+                float dx = rc[5], dy = rc[11];
+#pragma unroll
+                for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
+                double sx = fma(axi, (double)(il0 + q), ax_b) + (double)dx;
+                const double sy = fma(ayi, (double)(il0 + q), ay_b) + (double)dy;
+                int wrapk = 0;
+                if (sx > period32 - 16.0) { sx -= period32; wrapk = 1; }
+                else if (sx <= -16.0) { sx += period32; wrapk = -1; }
+                const PatchTaps<TIn> taps{patch, si->pitch, si->xb0 - wrapk * row_total, si->py0, P.channels};
+                sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
+                                                __double2float_rn(sx) * (1.0f / 32.0f), __double2float_rn(sy) * (1.0f / 32.0f),
+                                                stage_row + q * P.channels);
+            }
         } else {
             // residual polynomial in float32, affine part in float64 (absolute, exact to ~1e-10 px);
             // the final double -> float conversion IS the float32 cast of the map cv2.remap would get
@@ -733,6 +781,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
 // (tile, view); only fast tiles write (the caller pre-fills everything from the direct path).
 struct TiledCoordParams {
     int out_w, out_h, tiles_x, tiles_y;
+    double period32;        // 32 * source width (seam tiles wrap their x coordinate)
     const TilePlan* plans;
     float* x32; float* y32; double* x64; double* y64; unsigned char* valid;
 };
@@ -746,7 +795,7 @@ __global__ void __launch_bounds__(256) coords_tiled_kernel(const __grid_constant
     if (tid < (int)(sizeof(TilePlan) / 16)) reinterpret_cast<int4*>(&plan)[tid] = __ldg(gp + tid);
     __syncthreads();
     const int mode = plan.mode_slot & 0xff;
-    if (mode != kModeFast && mode != kModeFastRows) return;
+    if (mode != kModeFast && mode != kModeFastRows && mode != kModeFastSeam) return;
     for (int task = tid; task < kTile * 12; task += 256) {
         const int row = task / 12, c = task % 12;
         const float* K = (c < 6 ? plan.rx : plan.ry) + (c < 6 ? c : c - 6);
@@ -767,8 +816,12 @@ __global__ void __launch_bounds__(256) coords_tiled_kernel(const __grid_constant
         float dx = rc[5], dy = rc[11];
 #pragma unroll
         for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
-        const double sx = fma(plan.ax[1], (double)(il0 + q), bx) + (double)dx;
+        double sx = fma(plan.ax[1], (double)(il0 + q), bx) + (double)dx;
         const double sy = fma(plan.ay[1], (double)(il0 + q), by) + (double)dy;
+        if (mode == kModeFastSeam) {
+            if (sx > P.period32 - 16.0) sx -= P.period32;
+            else if (sx <= -16.0) sx += P.period32;
+        }
         const long long o = ((long long)v * P.out_h + j) * P.out_w + i;
         P.x32[o] = __double2float_rn(sx) * (1.0f / 32.0f); P.y32[o] = __double2float_rn(sy) * (1.0f / 32.0f);
         P.x64[o] = sx * (1.0 / 32.0);

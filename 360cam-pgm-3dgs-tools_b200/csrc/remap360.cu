@@ -734,6 +734,7 @@ int r360_plan_coords(const r360_plan* plan, float* map_x32, float* map_y32, doub
     TiledCoordParams T;
     std::memset(&T, 0, sizeof(T));
     T.out_w = p.out_w; T.out_h = p.out_h; T.tiles_x = plan->tiles_x; T.tiles_y = plan->tiles_y;
+    T.period32 = 32.0 * plan->src_layout.width;
     T.plans = plan->d_plans;
     T.x32 = map_x32; T.y32 = map_y32; T.x64 = map_x64; T.y64 = map_y64; T.valid = valid;
     coords_tiled_kernel<<<dim3(plan->n_tiles, n_views), 256, 0, s>>>(T);
