@@ -3,7 +3,7 @@
 Host layer (Python + PyTorch for device memory and streams) over the hand-written sm_100a
 kernels in ../csrc, reached through the C ABI declared in include/remap360.h."""
 
-from .api import (FisheyeCalibration, PerspectiveView, remap_erp, remap_fisheye,  # noqa: F401
+from .api import (FisheyeCalibration, PerspectiveView, alloc_views, remap_erp, remap_fisheye,  # noqa: F401
                   sample_coordinates)
 from ._lib import Remap360Error, launch_count  # noqa: F401
 

@@ -119,6 +119,30 @@ def _stream_handle(stream: Optional[torch.cuda.Stream], device) -> int:
     return (stream or torch.cuda.current_stream(device)).cuda_stream
 
 
+def alloc_views(n_groups: int, n_views: int, h: int, w: int, c: int, dtype, device) -> torch.Tensor:
+    """Output tensor [G, V, h, w, C] whose rows start on 16-byte boundaries: when ``w * C * itemsize`` is
+    not a multiple of 16 (e.g. the dual-fisheye default 1750 px x 3 bytes) the rows are padded and a
+    strided view is returned, so that the kernels can use 16-byte vector stores.  ``.contiguous()``
+    gives the packed image."""
+    es = torch.empty((), dtype=dtype).element_size()
+    row_bytes = w * c * es
+    if row_bytes % 16 == 0:
+        return torch.empty((n_groups, n_views, h, w, c), dtype=dtype, device=device)
+    pitch = (row_bytes + 15) // 16 * 16 // es            # elements per padded row
+    flat = torch.empty((n_groups, n_views, h, pitch), dtype=dtype, device=device)
+    return flat.as_strided((n_groups, n_views, h, w, c), (n_views * h * pitch, h * pitch, pitch, c, 1))
+
+
+def _as_image_batch(t: torch.Tensor) -> torch.Tensor:
+    """[G, V, h, w, C] -> [G * V, h, w, C] without copying, also for row-padded tensors."""
+    g, v, h, w, c = t.shape
+    if t.is_contiguous():
+        return t.view(g * v, h, w, c)
+    if t.stride(0) != v * t.stride(1):
+        raise ValueError("out: views of a group must be equally spaced and groups back to back")
+    return t.as_strided((g * v, h, w, c), (t.stride(1), t.stride(2), t.stride(3), t.stride(4)))
+
+
 # ---- plans --------------------------------------------------------------------------------------
 
 class Plan:
@@ -226,11 +250,13 @@ def remap_erp(frames: torch.Tensor, views: Sequence[PerspectiveView], size: Tupl
     w, h = int(size[0]), int(size[1])
     dt = out_dtype or frames.dtype
     if out is None:
-        out = torch.empty((b, len(views), h, w, c), dtype=dt, device=frames.device)
+        out = alloc_views(b, len(views), h, w, c, dt, frames.device)
     elif tuple(out.shape) != (b, len(views), h, w, c) or out.dtype != dt:
         raise ValueError("out must be %s %s" % ((b, len(views), h, w, c), dt))
+    if len(views) == 0:
+        raise _lib.Remap360Error(-1, "invalid argument (no views)")
     src = _describe(frames, "frames")
-    dst = _describe(out.view(b * max(len(views), 1), h, w, c) if len(views) else out.view(0, h, w, c), "out")
+    dst = _describe(_as_image_batch(out), "out")
     opt = _options(interp, convention, path, out_dtype=None if dt == frames.dtype else dt)
     _run(src, dst, views, opt, path, frames.device, stream)
     return out
@@ -251,13 +277,15 @@ def remap_fisheye(images: torch.Tensor, calibs: Sequence[FisheyeCalibration],
     w, h = int(size[0]), int(size[1])
     dt = out_dtype or images.dtype
     if out is None:
-        out = torch.empty((g, len(views), h, w, c), dtype=dt, device=images.device)
+        out = alloc_views(g, len(views), h, w, c, dt, images.device)
     elif tuple(out.shape) != (g, len(views), h, w, c) or out.dtype != dt:
         raise ValueError("out must be %s %s" % ((g, len(views), h, w, c), dt))
     if not images.is_contiguous():
         raise ValueError("images must be contiguous")
+    if len(views) == 0:
+        raise _lib.Remap360Error(-1, "invalid argument (no views)")
     src = _describe(images.view(g * nl, hh, ww, c), "images")
-    dst = _describe(out.view(g * len(views), h, w, c), "out")
+    dst = _describe(_as_image_batch(out), "out")
     opt = _options(interp, "halfpixel", path, fill_invalid, border_value, None if dt == images.dtype else dt)
     _run(src, dst, views, opt, path, images.device, stream, calibs)
     return out

@@ -13,7 +13,7 @@ from typing import Deque, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import torch
 
-from .api import PerspectiveView, remap_erp
+from .api import PerspectiveView, alloc_views, remap_erp
 
 
 class _Slot:
@@ -21,7 +21,7 @@ class _Slot:
         h, w, c = frame_shape
         self.host_in = torch.empty((h, w, c), dtype=dtype).pin_memory()
         self.dev_in = torch.empty((1, h, w, c), dtype=dtype, device=device)
-        self.dev_out = torch.empty((1, n_views, size[1], size[0], c), dtype=out_dtype, device=device)
+        self.dev_out = alloc_views(1, n_views, size[1], size[0], c, out_dtype, device)
         self.host_out = torch.empty((n_views, size[1], size[0], c), dtype=out_dtype).pin_memory()
         self.ev_h2d = torch.cuda.Event()
         self.ev_kernel = torch.cuda.Event()

@@ -70,10 +70,13 @@ def main():
         yaw_rel = ((s["yaw_deg"] - (0.0, 180.0)[slot] + 180.0) % 360.0) - 180.0
         views.append(remap360.PerspectiveView(yaw_rel, s["pitch_deg"], s["hfov_deg"], s["vfov_deg"], src_slot=slot))
     pairs = torch.randint(0, 256, (8, 2, 3840, 3840, 3), dtype=torch.uint8, device=dev)
-    out = torch.empty((8, 10, 1750, 1750, 3), dtype=torch.uint8, device=dev)
+    out = remap360.alloc_views(8, 10, 1750, 1750, 3, torch.uint8, dev)       # rows padded to 16 bytes
     for interp in ("cubic", "linear"):
         ms = timeit(lambda: remap360.remap_fisheye(pairs, [calib, calib], views, (1750, 1750), interp=interp, out=out))
+        from remap360 import api
+        plan = list(api._PLAN_CACHE.values())[-1]
         rows.append({"case": "cfg5 dual fisheye u8 %s, 8 pairs x 10 views 1750^2" % interp, "ms": ms,
+                     "fallback_tiles": plan.n_fallback, "tiles": plan.tiles_per_view * plan.n_views,
                      "Mpix_per_s": 8 * 10 * 1750 * 1750 / ms / 1e3, "pairs_per_s": 8 / ms * 1e3, "interp": interp})
     for r in rows:
         print(json.dumps(r))
