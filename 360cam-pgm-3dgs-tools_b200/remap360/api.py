@@ -234,6 +234,8 @@ def _run(src: Images, dst: Images, views, opt: Options, path: str, device, strea
     if len(views) == 0:
         raise _lib.Remap360Error(-1, "invalid argument (no views)")
     plan = get_plan(src, dst, views, opt, device, calibs, stream)
+    if stream is not None:
+        plan.workspace.record_stream(stream)       # the plan may be evicted from the cache while in use
     with torch.cuda.device(device):
         _lib.check(lib.r360_remap_planned(plan.handle, ctypes.byref(src), ctypes.byref(dst),
                                           _stream_handle(stream, device)))
