@@ -12,11 +12,20 @@
 
 #include "r360_common.cuh"
 
+#ifndef R360_CUBIC_LDS64
+#define R360_CUBIC_LDS64 0   // measured on B200: 103 vs 105 Gpix/s -- fewer wavefronts, but the selects cost more
+#endif
+
 namespace r360 {
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
     return v;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
@@ -70,8 +79,8 @@ __device__ __forceinline__ uint32_t bilinear_u8c3(uint32_t bias, uint32_t pitch,
     return r | (g << 8) | (b << 16);
 }
 
-// One bicubic sample; `table_saddr` is the shared-memory copy of cv2's fixed-point table
-// ([fy][fx][ky][kx] int16).  `bias` must address tap (ix - 1, iy - 1): pass the bilinear bias
+// One bicubic sample; `table_saddr` is the shared-memory copy of cv2's fixed-point table, split
+// into two planes [ky/2][fy][fx][ky%2][kx] int16 (16-byte entries, 16 KB apart).  `bias` must address tap (ix - 1, iy - 1): pass the bilinear bias
 // minus (3 + pitch).  Returns R | G << 8 | B << 16.
 __device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, uint32_t table_saddr,
                                                  uint32_t ux, uint32_t uy) {
@@ -79,14 +88,27 @@ __device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, 
     const uint32_t addr = (ux >> 5) * 3u + (uy >> 5) * pitch + bias;
     uint32_t a4 = addr & ~3u;
     const uint32_t sh = (addr & 3u) << 3;
-    const uint32_t wt = table_saddr + ((fy << 5) + fx) * 32u;
-    const uint4 wa = lds128(wt), wb = lds128(wt + 16);          // rows 0,1 | rows 2,3: (w0|w1<<16, w2|w3<<16) each
+#if R360_CUBIC_LDS64
+    uint32_t a8 = addr & ~7u;
+    const bool odd = (addr & 4u) != 0;
+#endif
+    const uint32_t wt = table_saddr + ((fy << 5) + fx) * 16u;
+    const uint4 wa = lds128(wt), wb = lds128(wt + 16384u);      // plane of rows 0,1 | plane of rows 2,3: (w0|w1<<16, w2|w3<<16) each
     const uint32_t wrow[4][2] = {{wa.x, wa.y}, {wa.z, wa.w}, {wb.x, wb.y}, {wb.z, wb.w}};
     int r = 16384, g = 16384, b = 16384;
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
+#if R360_CUBIC_LDS64
+        // two aligned 64-bit loads + one 32-bit load cover the 20 bytes from the 8-byte boundary below
+        // the row's first tap; a 64-bit load of neighbouring lanes costs the same wavefronts as a 32-bit one
+        const uint2 lo = lds64(a8), hi = lds64(a8 + 8);
+        const uint32_t w4 = lds32(a8 + 16);
+        const uint32_t q0 = odd ? lo.y : lo.x, q1 = odd ? hi.x : lo.y, q2 = odd ? hi.y : hi.x, q3 = odd ? w4 : hi.y;
+        a8 += pitch;
+#else
         const uint32_t q0 = lds32(a4), q1 = lds32(a4 + 4), q2 = lds32(a4 + 8), q3 = lds32(a4 + 12);
         a4 += pitch;
+#endif
         const uint32_t p0 = __funnelshift_r(q0, q1, sh);       // R0 G0 B0 R1
         const uint32_t p1 = __funnelshift_r(q1, q2, sh);       // G1 B1 R2 G2
         const uint32_t p2 = __funnelshift_r(q2, q3, sh);       // B2 R3 G3 B3

@@ -474,7 +474,10 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
     }
     if (P.use_table) {
         const int4* src = reinterpret_cast<const int4*>(g_tables.cubic_fixed);
-        for (int q = tid; q < kTableBytes / 16; q += kTiledThreads) reinterpret_cast<int4*>(table)[q] = __ldg(src + q);
+        // Two planes (tap rows 0,1 | rows 2,3) with a 16-byte entry stride: a warp's 32 random entries
+        // then spread over all 8 bank groups instead of the 4 a 32-byte stride would reach.
+        for (int q = tid; q < kTableBytes / 16; q += kTiledThreads)
+            reinterpret_cast<int4*>(table)[(q >> 1) + (q & 1) * (kTableBytes / 32)] = __ldg(src + q);
     }
     __syncthreads();
 

@@ -6,6 +6,7 @@ anything that needs it raises."""
 from __future__ import annotations
 
 import ctypes
+import os
 import pathlib
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 
@@ -59,11 +60,12 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    lib_path = pathlib.Path(os.environ.get("R360_LIBRARY") or LIB_PATH)      # override: kernel experiments only
+    if not lib_path.exists():
         raise ImportError(
             "%s is missing: build it with `python 360cam-pgm-3dgs-tools_b200/build.py` "
-            "(there is no CPU fallback for the remap kernels)" % LIB_PATH)
-    lib = ctypes.CDLL(str(LIB_PATH))
+            "(there is no CPU fallback for the remap kernels)" % lib_path)
+    lib = ctypes.CDLL(str(lib_path))
     lib.r360_abi_version.restype = c_int
     lib.r360_error_string.restype = c_char_p
     lib.r360_error_string.argtypes = [c_int]
