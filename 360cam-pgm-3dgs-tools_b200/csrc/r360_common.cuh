@@ -16,7 +16,9 @@ namespace r360 {
 constexpr int kMaxViewsPerLaunch = 16;
 constexpr int kMaxLenses = 4;
 
-enum Proj : int { kProjErp = 0, kProjFisheye = 1 };
+// kProjUndistort: fisheye image -> "undistorted" fisheye image (DF:1008-1051); its views carry the
+// normalised sensor-plane coordinates (x / zoom, y / zoom, 1) instead of a world ray.
+enum Proj : int { kProjErp = 0, kProjFisheye = 1, kProjUndistort = 2 };
 enum Interp : int { kNearest = 0, kLinear = 1, kCubic = 2 };
 
 // A view is a linear map from output pixel indices to an (unnormalised) world ray:
@@ -40,6 +42,7 @@ struct LensDev {         // one fisheye calibration
     double k1, k2, k3, k4, p1, p2;
     double xmax, ymax;   // width - 1, height - 1
     double cos_theta_max;
+    double sin_half_theta_max;   // kProjUndistort: valid <=> min(r / 2, 1) <= sin(theta_max / 2)
 };
 
 struct ImageSetDev {
@@ -97,17 +100,9 @@ __device__ __forceinline__ void erp_xy(const ErpDev& e, double lon, double lat, 
     y = fma(fma(-lat, inv_pi, 0.5), e.sv, e.ov);
 }
 
-// Equisolid fisheye with Brown distortion.  With n = |d|:
-//   2 sin(theta/2) / rho = sqrt(2 / (n (n + dz)))   (theta from +z, rho = hypot(dx, dy) / n)
-// so no trigonometry is needed.  valid = theta <= theta_max and inside the sensor.
-__device__ __forceinline__ bool fisheye_xy(const LensDev& L, double dx, double dy, double dz,
-                                           double& x, double& y) {
-    const double n2 = fma(dx, dx, fma(dy, dy, dz * dz));
-    const double n = sqrt(n2);
-    const double den = n * (n + dz);
-    const double s = den > 1e-24 * n2 ? sqrt(2.0 / den) : 0.0;
-    const double xn = dx * s;
-    const double yn = -dy * s;
+// Brown distortion in normalised image coordinates, then the affine sensor model
+// (DF:975-1005, DF:1812-1817).  Returns r^2.
+__device__ __forceinline__ double brown_to_sensor(const LensDev& L, double xn, double yn, double& x, double& y) {
     const double r2 = fma(xn, xn, yn * yn);
     const double r4 = r2 * r2;
     const double radial = 1.0 + L.k1 * r2 + L.k2 * r4 + L.k3 * (r4 * r2) + L.k4 * (r4 * r4);
@@ -119,7 +114,31 @@ __device__ __forceinline__ bool fisheye_xy(const LensDev& L, double dx, double d
     }
     x = L.cx0 + xd * L.f + xd * L.b1 + yd * L.b2;
     y = L.cy0 + yd * L.f;
+    return r2;
+}
+
+// Equisolid fisheye with Brown distortion.  With n = |d|:
+//   2 sin(theta/2) / rho = sqrt(2 / (n (n + dz)))   (theta from +z, rho = hypot(dx, dy) / n)
+// so no trigonometry is needed.  valid = theta <= theta_max and inside the sensor.
+__device__ __forceinline__ bool fisheye_xy(const LensDev& L, double dx, double dy, double dz,
+                                           double& x, double& y) {
+    const double n2 = fma(dx, dx, fma(dy, dy, dz * dz));
+    const double n = sqrt(n2);
+    const double den = n * (n + dz);
+    const double s = den > 1e-24 * n2 ? sqrt(2.0 / den) : 0.0;
+    const double xn = dx * s;
+    const double yn = -dy * s;
+    brown_to_sensor(L, xn, yn, x, y);
     const bool in_fov = dz >= L.cos_theta_max * n;
+    return in_fov && x >= 0.0 && x <= L.xmax && y >= 0.0 && y <= L.ymax;
+}
+
+// Fisheye -> undistorted fisheye (DF:1008-1051): (xn, yn) are the output pixel's normalised
+// coordinates divided by the zoom; the source pixel is where the Brown model sends them.  The
+// reference's validity test theta = 2 asin(clip(r / 2, 0, 1)) <= theta_max is monotone in r.
+__device__ __forceinline__ bool undistort_xy(const LensDev& L, double xn, double yn, double& x, double& y) {
+    const double r2 = brown_to_sensor(L, xn, yn, x, y);
+    const bool in_fov = fmin(0.5 * sqrt(fmax(r2, 0.0)), 1.0) <= L.sin_half_theta_max;
     return in_fov && x >= 0.0 && x <= L.xmax && y >= 0.0 && y <= L.ymax;
 }
 

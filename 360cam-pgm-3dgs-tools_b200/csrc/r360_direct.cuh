@@ -5,6 +5,7 @@
 // Arithmetic per pixel:
 //   ray (gs360_GUI.py:377-392) -> lon/lat -> ERP pixel (gs360_GUI.py:419-424)            [ERP]
 //   ray -> equisolid + Brown -> sensor pixel, validity (DF:1794-1821)                     [fisheye]
+//   normalised sensor coordinates / zoom -> Brown -> sensor pixel, validity (DF:1008-1051) [undistort]
 //   float32 cast -> 1/32-px quantisation -> cv2.remap weights (DF:2001-2008)              [sampling]
 #pragma once
 
@@ -26,6 +27,7 @@ __device__ __forceinline__ bool project_pixel(const ViewDev& view, const ErpDev&
         erp_xy(erp, lon, lat, x, y);
         return true;
     }
+    if (PROJ == kProjUndistort) return undistort_xy(lens[view.slot], dx, dy, x, y);
     return fisheye_xy(lens[view.slot], dx, dy, dz, x, y);
 }
 
@@ -37,7 +39,7 @@ __device__ __forceinline__ void direct_pixel(const LaunchParams& p, const ViewDe
     const long long dst_img = (long long)g * p.n_views_total + p.view_base + v;
     TOut* dst = reinterpret_cast<TOut*>(p.dst.data + dst_img * p.dst.image_stride + (long long)j * p.dst.pitch)
                 + (long long)i * p.channels;
-    if (PROJ == kProjFisheye && p.fill_invalid && !valid) {
+    if (PROJ != kProjErp && p.fill_invalid && !valid) {
         for (int c = 0; c < p.channels; ++c) dst[c] = Finish<TIn, TOut>::run(p.border_value);
         return;
     }
@@ -70,7 +72,8 @@ __global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ Coo
     double x, y;
     const bool valid = proj == kProjErp
         ? project_pixel<kProjErp>(p.views[v], p.erp, p.lens, (double)i, (double)j, x, y)
-        : project_pixel<kProjFisheye>(p.views[v], p.erp, p.lens, (double)i, (double)j, x, y);
+        : proj == kProjFisheye ? project_pixel<kProjFisheye>(p.views[v], p.erp, p.lens, (double)i, (double)j, x, y)
+                               : project_pixel<kProjUndistort>(p.views[v], p.erp, p.lens, (double)i, (double)j, x, y);
     const long long o = ((p.view_base + v) * p.out_h + j) * (long long)p.out_w + i;
     if (p.x32) p.x32[o] = (float)x;
     if (p.y32) p.y32[o] = (float)y;

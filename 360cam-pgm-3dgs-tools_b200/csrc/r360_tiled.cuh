@@ -198,7 +198,7 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
             const int fyv = (int)floor(fmin(fmax(poly2d(ky, ps, pt), -lim), lim));
             atomicMin(&bmin_x, fxv); atomicMax(&bmax_x, fxv);
             atomicMin(&bmin_y, fyv); atomicMax(&bmax_y, fyv);
-            if (PROJ == kProjFisheye) {
+            if (PROJ != kProjErp) {
                 double ex, ey;
                 const bool vld = project_pixel<PROJ>(view, P.erp, P.lens, (double)(i0 + il), (double)(j0 + jl), ex, ey);
                 atomicAdd(vld ? &valid_count : &invalid_count, 1);
@@ -248,7 +248,7 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
             // columns must lie inside one period of the panorama / inside the sensor
             const int row_total = P.src_w * P.px_bytes;
             bool fast = P.bulk_load_ok && xs0 >= 0 && xb1 <= row_total;
-            if (PROJ == kProjFisheye) fast = fast && ys0 >= 0 && ys1 < P.src_h && invalid_count == 0;
+            if (PROJ != kProjErp) fast = fast && ys0 >= 0 && ys1 < P.src_h && invalid_count == 0;
             // seam: only when the coordinate period equals the image width (halfpixel convention)
             const bool seam = PROJ == kProjErp && P.bulk_load_ok && !fast && P.erp.su == (double)P.src_w &&
                               row_bytes <= row_total && xb0 > -row_total && xb1 < 2 * row_total;
@@ -269,7 +269,7 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
                 if (rows * pitch <= P.patch_budget) mode = kModeFastSeam;
             }
         }
-        if (PROJ == kProjFisheye && P.fill_invalid && valid_count == 0) mode = kModeFill;
+        if (PROJ != kProjErp && P.fill_invalid && valid_count == 0) mode = kModeFill;
         out->py0 = ys0; out->rows = rows; out->xb0 = xb0; out->row_bytes = row_bytes; out->pitch = pitch;
         out->mode_slot = mode | (view.slot << 8) | (wbox << 16);
         out->pad[0] = 0; out->pad[1] = 0;
@@ -282,7 +282,8 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
 
 __global__ void __launch_bounds__(64) plan_kernel(const __grid_constant__ PlanParams P) {
     if (P.proj == kProjErp) plan_tile<kProjErp>(P);
-    else plan_tile<kProjFisheye>(P);
+    else if (P.proj == kProjFisheye) plan_tile<kProjFisheye>(P);
+    else plan_tile<kProjUndistort>(P);
 }
 
 // ---- bulk-async copy / mbarrier wrappers (PTX) ------------------------------------------------

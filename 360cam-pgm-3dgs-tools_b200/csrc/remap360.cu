@@ -156,6 +156,47 @@ void make_lens(const r360_fisheye_calib& c, LensDev* L) {
     L->ymax = c.height - 1.0;
     const double half = std::fmax(1.0, std::fmin(360.0, c.lens_fov_deg)) * 0.5;   // DF:1800
     L->cos_theta_max = std::cos(half * (M_PI / 180.0));
+    L->sin_half_theta_max = std::sin(half * 0.5 * (M_PI / 180.0));
+}
+
+// Fisheye -> undistorted fisheye (DF:1021-1029): the output pixel (i, j) has normalised coordinates
+//   y = (j - cy0) / f / zoom,   x = (i - cx0 - (j - cy0) / f * b2) / (f + b1) / zoom,
+// a linear function of (i, j): it rides in the view's "ray" slots (dz is unused).
+int make_undistort_view(const r360_undistort& u, const r360_fisheye_calib& c, ViewDev* o) {
+    const double cx0 = c.width * 0.5 + c.cx, cy0 = c.height * 0.5 + c.cy;
+    const double den_y = c.f, den_x = c.f + c.b1;
+    if (std::fabs(den_y) < 1e-12 || std::fabs(den_x) < 1e-12) return R360_E_INVALID_ARG;     // DF:1018-1020
+    const double zoom = std::fmax(1e-6, u.zoom);                                             // DF:1145
+    std::memset(o, 0, sizeof(*o));
+    o->ci[0] = 1.0 / (den_x * zoom);
+    o->cj[0] = -c.b2 / (den_y * den_x * zoom);
+    o->c0[0] = (-cx0 + cy0 * c.b2 / den_y) / (den_x * zoom);
+    o->cj[1] = 1.0 / (den_y * zoom);
+    o->c0[1] = -cy0 / (den_y * zoom);
+    o->c0[2] = 1.0;
+    o->slot = u.src_slot;
+    return R360_OK;
+}
+
+int build_persp_views(const r360_view* views, int n_views, int out_w, int out_h, std::vector<ViewDev>* out) {
+    if (!views || n_views <= 0 || out_w <= 0 || out_h <= 0) return R360_E_INVALID_ARG;
+    out->resize(n_views);
+    for (int v = 0; v < n_views; ++v) make_view(views[v], out_w, out_h, &(*out)[v]);
+    return R360_OK;
+}
+
+int build_undistort_views(const r360_undistort* items, int n_items, const r360_fisheye_calib* calib, int n_lenses,
+                          std::vector<ViewDev>* out) {
+    if (!items || n_items <= 0 || !calib) return R360_E_INVALID_ARG;
+    if (n_lenses < 1) return R360_E_INVALID_ARG;
+    if (n_lenses > R360_MAX_LENSES) return R360_E_TOO_MANY;
+    out->resize(n_items);
+    for (int v = 0; v < n_items; ++v) {
+        if (items[v].src_slot < 0 || items[v].src_slot >= n_lenses) return R360_E_INVALID_ARG;
+        const int rc = make_undistort_view(items[v], calib[items[v].src_slot], &(*out)[v]);
+        if (rc != R360_OK) return rc;
+    }
+    return R360_OK;
 }
 
 int elem_size(int dtype) {
@@ -217,10 +258,14 @@ int dispatch(int proj, int interp, int in_dt, int out_dt, F&& f) {
             if (interp == R360_NEAREST) return f.template run<kProjErp, kNearest, TIN, TOUT>();             \
             if (interp == R360_LINEAR) return f.template run<kProjErp, kLinear, TIN, TOUT>();               \
             if (interp == R360_CUBIC) return f.template run<kProjErp, kCubic, TIN, TOUT>();                 \
-        } else {                                                                                            \
+        } else if (proj == kProjFisheye) {                                                                  \
             if (interp == R360_NEAREST) return f.template run<kProjFisheye, kNearest, TIN, TOUT>();         \
             if (interp == R360_LINEAR) return f.template run<kProjFisheye, kLinear, TIN, TOUT>();           \
             if (interp == R360_CUBIC) return f.template run<kProjFisheye, kCubic, TIN, TOUT>();             \
+        } else if (proj == kProjUndistort) {                                                                \
+            if (interp == R360_NEAREST) return f.template run<kProjUndistort, kNearest, TIN, TOUT>();       \
+            if (interp == R360_LINEAR) return f.template run<kProjUndistort, kLinear, TIN, TOUT>();         \
+            if (interp == R360_CUBIC) return f.template run<kProjUndistort, kCubic, TIN, TOUT>();           \
         }                                                                                                   \
         return R360_E_INVALID_ARG;                                                                          \
     } while (0)
@@ -242,7 +287,7 @@ bool supported_types(int in_dt, int out_dt) {
 // Validates the arguments shared by the plan-less and planned entry points and fills `out`.
 // With `layout_only` the data pointers and counts are not looked at.
 int prepare(int proj, const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
-            int n_lenses, const r360_view* views, int n_views, const r360_options* opt_in, bool layout_only,
+            int n_lenses, const ViewDev* views, int n_views, const r360_options* opt_in, bool layout_only,
             Prepared* out) {
     int rc;
     r360_images s_chk, d_chk;
@@ -258,7 +303,7 @@ int prepare(int proj, const r360_images* src, const r360_images* dst, const r360
     if (!views || n_views <= 0) return R360_E_INVALID_ARG;
     if (n_lenses < 1) return R360_E_INVALID_ARG;
     if (n_lenses > R360_MAX_LENSES) return R360_E_TOO_MANY;
-    if (proj == kProjFisheye && !calib) return R360_E_INVALID_ARG;
+    if (proj != kProjErp && !calib) return R360_E_INVALID_ARG;
     r360_options opt;
     if (opt_in) opt = *opt_in; else r360_default_options(&opt);
     if (opt.interp < R360_NEAREST || opt.interp > R360_CUBIC) return R360_E_INVALID_ARG;
@@ -272,7 +317,7 @@ int prepare(int proj, const r360_images* src, const r360_images* dst, const r360
     if (out_dt != dst->dtype) return R360_E_INVALID_ARG;
     if (!supported_types(src->dtype, out_dt)) return R360_E_UNSUPPORTED;
     for (int v = 0; v < n_views; ++v)
-        if (views[v].src_slot < 0 || views[v].src_slot >= n_lenses) return R360_E_INVALID_ARG;
+        if (views[v].slot < 0 || views[v].slot >= n_lenses) return R360_E_INVALID_ARG;
 
     out->proj = proj; out->n_lenses = n_lenses; out->n_views = n_views; out->interp = opt.interp;
     out->in_dt = src->dtype; out->out_dt = out_dt; out->opt = opt;
@@ -284,8 +329,8 @@ int prepare(int proj, const r360_images* src, const r360_images* dst, const r360
     p.n_views_total = n_views;
     p.n_lenses = n_lenses;
     p.n_groups = n_groups;
-    p.fill_invalid = proj == kProjFisheye ? (opt.fill_invalid != 0) : 0;
-    double bv = proj == kProjFisheye ? opt.border_value : 0.0;
+    p.fill_invalid = proj != kProjErp ? (opt.fill_invalid != 0) : 0;
+    double bv = proj != kProjErp ? opt.border_value : 0.0;
     if (src->dtype == R360_U8) bv = std::nearbyint(std::fmin(std::fmax(bv, 0.0), 255.0));          // saturate_cast<uchar>
     else if (src->dtype == R360_U16) bv = std::nearbyint(std::fmin(std::fmax(bv, 0.0), 65535.0));  // saturate_cast<ushort>
     p.border_value = (float)bv;
@@ -300,9 +345,10 @@ struct DirectLauncher {
 };
 
 int remap_direct(int proj, const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
-                 int n_lenses, const r360_view* views, int n_views, const r360_options* opt_in, void* stream) {
+                 int n_lenses, const std::vector<ViewDev>& views, const r360_options* opt_in, void* stream) {
     Prepared pr;
-    int rc = prepare(proj, src, dst, calib, n_lenses, views, n_views, opt_in, false, &pr);
+    const int n_views = (int)views.size();
+    int rc = prepare(proj, src, dst, calib, n_lenses, views.data(), n_views, opt_in, false, &pr);
     if (rc != R360_OK) return rc;
     if (pr.opt.path == R360_PATH_TILED) return R360_E_INVALID_ARG;      // needs a plan
     if ((rc = ensure_device_ready()) != R360_OK) return rc;
@@ -311,7 +357,7 @@ int remap_direct(int proj, const r360_images* src, const r360_images* dst, const
     for (int v0 = 0; v0 < n_views; v0 += kMaxViewsPerLaunch) {
         p.view_base = v0;
         p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
-        for (int v = 0; v < p.n_views; ++v) make_view(views[v0 + v], dst->width, dst->height, &p.views[v]);
+        for (int v = 0; v < p.n_views; ++v) p.views[v] = views[v0 + v];
         rc = dispatch(proj, pr.interp, pr.in_dt, pr.out_dt, DirectLauncher{p, s});
         if (rc != R360_OK) return rc;
     }
@@ -402,14 +448,15 @@ bool aligned16(const void* p, int64_t pitch, int64_t stride) {
 }
 
 int plan_create(int proj, const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
-                int n_lenses, const r360_view* views, int n_views, const r360_options* opt_in,
+                int n_lenses, const std::vector<ViewDev>& views, const r360_options* opt_in,
                 void* workspace, size_t workspace_bytes, void* stream, r360_plan** plan_out) {
     if (!plan_out || !workspace) return R360_E_INVALID_ARG;
     *plan_out = nullptr;
+    const int n_views = (int)views.size();
     if (reinterpret_cast<uintptr_t>(workspace) % 256) return R360_E_INVALID_ARG;
     r360_plan* pl = new (std::nothrow) r360_plan();
     if (!pl) return R360_E_INVALID_ARG;
-    int rc = prepare(proj, src, dst, calib, n_lenses, views, n_views, opt_in, true, &pl->pr);
+    int rc = prepare(proj, src, dst, calib, n_lenses, views.data(), n_views, opt_in, true, &pl->pr);
     if (rc == R360_OK) rc = ensure_device_ready();
     const WorkspaceLayout wl = workspace_layout(n_views > 0 ? n_views : 1, dst ? dst->width : 1, dst ? dst->height : 1);
     if (rc == R360_OK && workspace_bytes < wl.total) rc = R360_E_INVALID_ARG;
@@ -419,8 +466,7 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     pl->tiles_x = (dst->width + kTile - 1) / kTile;
     pl->tiles_y = (dst->height + kTile - 1) / kTile;
     pl->n_tiles = pl->tiles_x * pl->tiles_y;
-    pl->views.resize(n_views);
-    for (int v = 0; v < n_views; ++v) make_view(views[v], dst->width, dst->height, &pl->views[v]);
+    pl->views = views;
     const int out_es = elem_size(pl->pr.out_dt), in_es = elem_size(pl->pr.in_dt);
     pl->out_stage_bytes = (int)align_up((size_t)kTile * kTile * dst->channels * out_es, 128);
     // Shared memory per block: barriers/coefficients/plan records, (8-bit bicubic) the 32 KB weight
@@ -570,6 +616,21 @@ struct TiledLauncher {
     }
 };
 
+// The maps a projection produces, written out for tests (float32 as cv2 would get them + float64).
+int launch_coords(CoordParams& p, int proj, const std::vector<ViewDev>& views, cudaStream_t s) {
+    const int n_views = (int)views.size();
+    for (int v0 = 0; v0 < n_views; v0 += kMaxViewsPerLaunch) {
+        p.view_base = v0;
+        p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
+        for (int v = 0; v < p.n_views; ++v) p.views[v] = views[v0 + v];
+        dim3 grid((p.out_w + 31) / 32, (p.out_h + 7) / 8, p.n_views);
+        coords_kernel<<<grid, 256, 0, s>>>(p, proj);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        R360_CUDA(cudaGetLastError());
+    }
+    return R360_OK;
+}
+
 bool same_layout(const r360_images& a, const r360_images& b, bool check_stride) {
     return a.width == b.width && a.height == b.height && a.channels == b.channels && a.dtype == b.dtype &&
            a.pitch_bytes == b.pitch_bytes && (!check_stride || a.image_stride_bytes == b.image_stride_bytes);
@@ -621,13 +682,27 @@ int r360_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 int r360_remap_erp(const r360_images* src, const r360_images* dst, const r360_view* views, int32_t n_views,
                    const r360_options* opt, void* stream) {
-    return remap_direct(kProjErp, src, dst, nullptr, 1, views, n_views, opt, stream);
+    std::vector<ViewDev> vd;
+    if (!dst) return R360_E_INVALID_ARG;
+    const int rc = build_persp_views(views, n_views, dst->width, dst->height, &vd);
+    return rc != R360_OK ? rc : remap_direct(kProjErp, src, dst, nullptr, 1, vd, opt, stream);
 }
 
 int r360_remap_fisheye(const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
                        int32_t n_lenses, const r360_view* views, int32_t n_views, const r360_options* opt,
                        void* stream) {
-    return remap_direct(kProjFisheye, src, dst, calib, n_lenses, views, n_views, opt, stream);
+    std::vector<ViewDev> vd;
+    if (!dst) return R360_E_INVALID_ARG;
+    const int rc = build_persp_views(views, n_views, dst->width, dst->height, &vd);
+    return rc != R360_OK ? rc : remap_direct(kProjFisheye, src, dst, calib, n_lenses, vd, opt, stream);
+}
+
+int r360_remap_undistort(const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
+                         int32_t n_lenses, const r360_undistort* items, int32_t n_items, const r360_options* opt,
+                         void* stream) {
+    std::vector<ViewDev> vd;
+    const int rc = build_undistort_views(items, n_items, calib, n_lenses, &vd);
+    return rc != R360_OK ? rc : remap_direct(kProjUndistort, src, dst, calib, n_lenses, vd, opt, stream);
 }
 
 int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, int32_t n_lenses,
@@ -651,17 +726,25 @@ int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, i
     else make_erp(src_w, src_h, opt.convention, &p.erp);
     for (int v = 0; v < n_views; ++v)
         if (calib && (views[v].src_slot < 0 || views[v].src_slot >= n_lenses)) return R360_E_INVALID_ARG;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    for (int v0 = 0; v0 < n_views; v0 += kMaxViewsPerLaunch) {
-        p.view_base = v0;
-        p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
-        for (int v = 0; v < p.n_views; ++v) make_view(views[v0 + v], out_w, out_h, &p.views[v]);
-        dim3 grid((out_w + 31) / 32, (out_h + 7) / 8, p.n_views);
-        coords_kernel<<<grid, 256, 0, s>>>(p, proj);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        R360_CUDA(cudaGetLastError());
-    }
-    return R360_OK;
+    std::vector<ViewDev> vd;
+    if ((rc = build_persp_views(views, n_views, out_w, out_h, &vd)) != R360_OK) return rc;
+    return launch_coords(p, proj, vd, static_cast<cudaStream_t>(stream));
+}
+
+int r360_coords_undistort(const r360_fisheye_calib* calib, int32_t n_lenses, const r360_undistort* items,
+                          int32_t n_items, int32_t out_w, int32_t out_h, float* map_x32, float* map_y32,
+                          double* map_x64, double* map_y64, uint8_t* valid, void* stream) {
+    if (out_w <= 0 || out_h <= 0) return R360_E_INVALID_ARG;
+    std::vector<ViewDev> vd;
+    int rc;
+    if ((rc = build_undistort_views(items, n_items, calib, n_lenses, &vd)) != R360_OK) return rc;
+    if ((rc = ensure_device_ready()) != R360_OK) return rc;
+    CoordParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.out_w = out_w; p.out_h = out_h;
+    p.x32 = map_x32; p.y32 = map_y32; p.x64 = map_x64; p.y64 = map_y64; p.valid = valid;
+    for (int l = 0; l < n_lenses; ++l) make_lens(calib[l], &p.lens[l]);
+    return launch_coords(p, kProjUndistort, vd, static_cast<cudaStream_t>(stream));
 }
 
 size_t r360_plan_workspace_bytes(int32_t n_views, int32_t out_w, int32_t out_h) {
@@ -672,7 +755,12 @@ size_t r360_plan_workspace_bytes(int32_t n_views, int32_t out_w, int32_t out_h) 
 int r360_plan_create_erp(const r360_images* src_layout, const r360_images* dst_layout, const r360_view* views,
                          int32_t n_views, const r360_options* opt, void* workspace_device, size_t workspace_bytes,
                          void* stream, r360_plan** plan_out) {
-    return plan_create(kProjErp, src_layout, dst_layout, nullptr, 1, views, n_views, opt, workspace_device,
+    std::vector<ViewDev> vd;
+    if (plan_out) *plan_out = nullptr;
+    if (!dst_layout) return R360_E_INVALID_ARG;
+    const int rc = build_persp_views(views, n_views, dst_layout->width, dst_layout->height, &vd);
+    if (rc != R360_OK) return rc;
+    return plan_create(kProjErp, src_layout, dst_layout, nullptr, 1, vd, opt, workspace_device,
                        workspace_bytes, stream, plan_out);
 }
 
@@ -680,7 +768,24 @@ int r360_plan_create_fisheye(const r360_images* src_layout, const r360_images* d
                              const r360_fisheye_calib* calib, int32_t n_lenses, const r360_view* views,
                              int32_t n_views, const r360_options* opt, void* workspace_device,
                              size_t workspace_bytes, void* stream, r360_plan** plan_out) {
-    return plan_create(kProjFisheye, src_layout, dst_layout, calib, n_lenses, views, n_views, opt,
+    std::vector<ViewDev> vd;
+    if (plan_out) *plan_out = nullptr;
+    if (!dst_layout) return R360_E_INVALID_ARG;
+    const int rc = build_persp_views(views, n_views, dst_layout->width, dst_layout->height, &vd);
+    if (rc != R360_OK) return rc;
+    return plan_create(kProjFisheye, src_layout, dst_layout, calib, n_lenses, vd, opt,
+                       workspace_device, workspace_bytes, stream, plan_out);
+}
+
+int r360_plan_create_undistort(const r360_images* src_layout, const r360_images* dst_layout,
+                               const r360_fisheye_calib* calib, int32_t n_lenses, const r360_undistort* items,
+                               int32_t n_items, const r360_options* opt, void* workspace_device,
+                               size_t workspace_bytes, void* stream, r360_plan** plan_out) {
+    std::vector<ViewDev> vd;
+    if (plan_out) *plan_out = nullptr;
+    const int rc = build_undistort_views(items, n_items, calib, n_lenses, &vd);
+    if (rc != R360_OK) return rc;
+    return plan_create(kProjUndistort, src_layout, dst_layout, calib, n_lenses, vd, opt,
                        workspace_device, workspace_bytes, stream, plan_out);
 }
 
@@ -722,15 +827,8 @@ int r360_plan_coords(const r360_plan* plan, float* map_x32, float* map_y32, doub
     p.erp = plan->pr.lp.erp;
     std::memcpy(p.lens, plan->pr.lp.lens, sizeof(p.lens));
     const int n_views = plan->pr.n_views;
-    for (int v0 = 0; v0 < n_views; v0 += kMaxViewsPerLaunch) {
-        p.view_base = v0;
-        p.n_views = n_views - v0 < kMaxViewsPerLaunch ? n_views - v0 : kMaxViewsPerLaunch;
-        for (int v = 0; v < p.n_views; ++v) p.views[v] = plan->views[v0 + v];
-        dim3 grid((p.out_w + 31) / 32, (p.out_h + 7) / 8, p.n_views);
-        coords_kernel<<<grid, 256, 0, s>>>(p, plan->pr.proj);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        R360_CUDA(cudaGetLastError());
-    }
+    const int crc = launch_coords(p, plan->pr.proj, plan->views, s);
+    if (crc != R360_OK) return crc;
     TiledCoordParams T;
     std::memset(&T, 0, sizeof(T));
     T.out_w = p.out_w; T.out_h = p.out_h; T.tiles_x = plan->tiles_x; T.tiles_y = plan->tiles_y;

@@ -36,6 +36,10 @@ class FisheyeCalib(Structure):
                                         "p1", "p2", "b1", "b2", "lens_fov_deg")]
 
 
+class Undistort(Structure):
+    _fields_ = [("zoom", c_double), ("src_slot", c_int32), ("reserved", c_int32)]
+
+
 class Options(Structure):
     _fields_ = [("interp", c_int32), ("convention", c_int32), ("path", c_int32), ("fill_invalid", c_int32),
                 ("border_value", c_double), ("out_dtype", c_int32), ("reserved", c_int32)]
@@ -53,7 +57,8 @@ _lib = None
 EXPORTS = ("r360_abi_version", "r360_error_string", "r360_last_cuda_error", "r360_default_options",
            "r360_device_info", "r360_remap_erp", "r360_remap_fisheye", "r360_coords", "r360_launch_count",
            "r360_plan_workspace_bytes", "r360_plan_create_erp", "r360_plan_create_fisheye", "r360_plan_info",
-           "r360_remap_planned", "r360_plan_coords", "r360_plan_destroy")
+           "r360_remap_planned", "r360_plan_coords", "r360_plan_destroy",
+           "r360_remap_undistort", "r360_coords_undistort", "r360_plan_create_undistort")
 
 
 def load() -> ctypes.CDLL:
@@ -88,6 +93,13 @@ def load() -> ctypes.CDLL:
     lib.r360_plan_create_fisheye.argtypes = [POINTER(Images), POINTER(Images), POINTER(FisheyeCalib), c_int32,
                                              POINTER(View), c_int32, POINTER(Options), c_void_p, ctypes.c_size_t,
                                              c_void_p, POINTER(c_void_p)]
+    lib.r360_remap_undistort.argtypes = [POINTER(Images), POINTER(Images), POINTER(FisheyeCalib), c_int32,
+                                         POINTER(Undistort), c_int32, POINTER(Options), c_void_p]
+    lib.r360_coords_undistort.argtypes = [POINTER(FisheyeCalib), c_int32, POINTER(Undistort), c_int32, c_int32,
+                                          c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.r360_plan_create_undistort.argtypes = [POINTER(Images), POINTER(Images), POINTER(FisheyeCalib), c_int32,
+                                               POINTER(Undistort), c_int32, POINTER(Options), c_void_p,
+                                               ctypes.c_size_t, c_void_p, POINTER(c_void_p)]
     lib.r360_plan_info.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32)]
     lib.r360_remap_planned.argtypes = [c_void_p, POINTER(Images), POINTER(Images), c_void_p]
     lib.r360_plan_coords.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -23,7 +23,7 @@ from typing import Dict, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import FisheyeCalib, Images, Options, View
+from ._lib import FisheyeCalib, Images, Options, Undistort, View
 
 
 @dataclass(frozen=True)
@@ -36,6 +36,15 @@ class PerspectiveView:
     vfov_deg: float
     roll_deg: float = 0.0
     src_slot: int = 0          # dual fisheye: 0 = X lens image, 1 = Y lens image
+    view_id: str = ""
+
+
+@dataclass(frozen=True)
+class UndistortItem:
+    """One output of the fisheye -> undistorted-fisheye remap: the lens image it reads and the zoom
+    (RemapCache.undistort_zoom, DF:1136-1145)."""
+    zoom: float
+    src_slot: int = 0
     view_id: str = ""
 
 
@@ -91,6 +100,23 @@ def _views_array(views: Sequence[PerspectiveView]):
         arr[k] = View(float(v.yaw_deg), float(v.pitch_deg), float(v.roll_deg), float(v.hfov_deg),
                       float(v.vfov_deg), int(v.src_slot), 0)
     return arr
+
+
+def _is_undistort(views) -> bool:
+    return len(views) > 0 and isinstance(views[0], UndistortItem)
+
+
+def _undistort_array(items: Sequence[UndistortItem]):
+    arr = (Undistort * len(items))()
+    for k, it in enumerate(items):
+        arr[k] = Undistort(float(it.zoom), int(it.src_slot), 0)
+    return arr
+
+
+def _view_key(v):
+    if isinstance(v, UndistortItem):
+        return ("undistort", v.zoom, v.src_slot)
+    return (v.yaw_deg, v.pitch_deg, v.roll_deg, v.hfov_deg, v.vfov_deg, v.src_slot)
 
 
 def _calib_array(calibs: Sequence[FisheyeCalibration]):
@@ -182,7 +208,7 @@ def get_plan(src: Images, dst: Images, views: Sequence[PerspectiveView], opt: Op
     device = torch.device(device)
     key = (device.index, _layout_key(src, src.data % 16 == 0 if src.data else True),
            _layout_key(dst, dst.data % 16 == 0 if dst.data else True),
-           tuple((v.yaw_deg, v.pitch_deg, v.roll_deg, v.hfov_deg, v.vfov_deg, v.src_slot) for v in views),
+           tuple(_view_key(v) for v in views),
            None if calibs is None else tuple(tuple(getattr(c, n) for n, _ in FisheyeCalib._fields_) for c in calibs),
            (opt.interp, opt.convention, opt.fill_invalid, opt.border_value, opt.out_dtype))
     plan = _PLAN_CACHE.get(key)
@@ -199,6 +225,11 @@ def get_plan(src: Images, dst: Images, views: Sequence[PerspectiveView], opt: Op
             rc = lib.r360_plan_create_erp(ctypes.byref(src), ctypes.byref(dst), _views_array(views), len(views),
                                           ctypes.byref(popt), workspace.data_ptr(), nbytes,
                                           _stream_handle(stream, device), ctypes.byref(handle))
+        elif _is_undistort(views):
+            rc = lib.r360_plan_create_undistort(ctypes.byref(src), ctypes.byref(dst), _calib_array(calibs),
+                                                len(calibs), _undistort_array(views), len(views),
+                                                ctypes.byref(popt), workspace.data_ptr(), nbytes,
+                                                _stream_handle(stream, device), ctypes.byref(handle))
         else:
             rc = lib.r360_plan_create_fisheye(ctypes.byref(src), ctypes.byref(dst), _calib_array(calibs), len(calibs),
                                               _views_array(views), len(views), ctypes.byref(popt),
@@ -225,6 +256,10 @@ def _run(src: Images, dst: Images, views, opt: Options, path: str, device, strea
             if calibs is None:
                 rc = lib.r360_remap_erp(ctypes.byref(src), ctypes.byref(dst), _views_array(views), len(views),
                                         ctypes.byref(opt), _stream_handle(stream, device))
+            elif _is_undistort(views):
+                rc = lib.r360_remap_undistort(ctypes.byref(src), ctypes.byref(dst), _calib_array(calibs),
+                                              len(calibs), _undistort_array(views), len(views), ctypes.byref(opt),
+                                              _stream_handle(stream, device))
             else:
                 rc = lib.r360_remap_fisheye(ctypes.byref(src), ctypes.byref(dst), _calib_array(calibs), len(calibs),
                                             _views_array(views), len(views), ctypes.byref(opt),
@@ -293,6 +328,36 @@ def remap_fisheye(images: torch.Tensor, calibs: Sequence[FisheyeCalibration],
     return out
 
 
+def undistort_fisheye(images: torch.Tensor, calibs: Sequence[FisheyeCalibration],
+                      items: Sequence[UndistortItem], size: Optional[Tuple[int, int]] = None, *,
+                      interp: str = "cubic", border_value: float = 0.0, fill_invalid: bool = True,
+                      out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+                      path: str = "auto", stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """Fisheye groups [G, L, H, W, C] -> undistorted fisheye images [G, N, h, w, C], one per item
+    (DF:1120-1217: build_remap_cache + cv2.remap + mask fill).  ``size`` defaults to the source size,
+    which is what the reference writes."""
+    if images.dim() != 5:
+        raise ValueError("images must be [G, L, H, W, C]")
+    g, nl, hh, ww, c = images.shape
+    if nl != len(calibs):
+        raise ValueError("one calibration per lens image is required")
+    if len(items) == 0:
+        raise _lib.Remap360Error(-1, "invalid argument (no items)")
+    w, h = (ww, hh) if size is None else (int(size[0]), int(size[1]))
+    dt = out_dtype or images.dtype
+    if out is None:
+        out = alloc_views(g, len(items), h, w, c, dt, images.device)
+    elif tuple(out.shape) != (g, len(items), h, w, c) or out.dtype != dt:
+        raise ValueError("out must be %s %s" % ((g, len(items), h, w, c), dt))
+    if not images.is_contiguous():
+        raise ValueError("images must be contiguous")
+    src = _describe(images.view(g * nl, hh, ww, c), "images")
+    dst = _describe(_as_image_batch(out), "out")
+    opt = _options(interp, "halfpixel", path, fill_invalid, border_value, None if dt == images.dtype else dt)
+    _run(src, dst, list(items), opt, path, images.device, stream, calibs)
+    return out
+
+
 def sample_coordinates(views: Sequence[PerspectiveView], size: Tuple[int, int], *,
                        erp_size: Optional[Tuple[int, int]] = None,
                        calibs: Optional[Sequence[FisheyeCalibration]] = None,
@@ -321,6 +386,13 @@ def sample_coordinates(views: Sequence[PerspectiveView], size: Tuple[int, int], 
             raise ValueError("erp_size or calibs is required")
         cal, nl, sw, sh = None, 1, int(erp_size[0]), int(erp_size[1])
     opt = _options("cubic", convention, path)
+    if path == "direct" and _is_undistort(views):
+        with torch.cuda.device(device):
+            _lib.check(lib.r360_coords_undistort(cal, nl, _undistort_array(views), n, w, h,
+                                                 res["x32"].data_ptr(), res["y32"].data_ptr(),
+                                                 res["x64"].data_ptr(), res["y64"].data_ptr(), valid_ptr,
+                                                 _stream_handle(stream, device)))
+        return res
     if path == "direct":
         with torch.cuda.device(device):
             _lib.check(lib.r360_coords(sw if calibs is None else 0, sh if calibs is None else 0, cal, nl,

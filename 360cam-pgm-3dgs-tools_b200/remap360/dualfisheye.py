@@ -4,7 +4,8 @@ Mirrors the pieces of cli_tools/gs360_DualFisheyeDistortionCalibration.py that f
 Metashape calibration XML loading (DF:453-492, :754-828), the SFM10 ten-view layout
 (DF:1243-1307), relative yaw and lens choice per view (DF:1342-1345, :1857-1907), and the
 per-pair rendering loop (DF:1996-2055) -- which here is one batched CUDA call instead of ten
-``cv2.remap`` calls on CPU maps.
+``cv2.remap`` calls on CPU maps -- and the zoom selection of the optional fisheye -> undistorted
+fisheye output (DF:1054-1170).
 
 The lens choice needs each candidate's valid ratio; it is obtained from the device projection
 (``sample_coordinates``), i.e. with the same float64 math that the kernels sample with.
@@ -149,6 +150,71 @@ def to_device_calibration(cal: SensorCalibration, lens_fov_deg: float = 190.0):
     return FisheyeCalibration(width=cal.width, height=cal.height, f=cal.f, cx=cal.cx, cy=cal.cy, k1=cal.k1,
                               k2=cal.k2, k3=cal.k3, k4=cal.k4, p1=cal.p1, p2=cal.p2, b1=cal.b1, b2=cal.b2,
                               lens_fov_deg=float(lens_fov_deg))
+
+
+def _undistort_overflow(cal: SensorCalibration, zoom: float, lens_fov_deg: float, steps: int) -> float:
+    """How far (px) the model-valid samples of a steps x steps grid over the output read outside the
+    sensor at this zoom (the ``overflow`` closure of DF:1073-1099).  Host-side planning, float64."""
+    import numpy as np
+    w, h = int(cal.width), int(cal.height)
+    cx0, cy0 = w * 0.5 + cal.cx, h * 0.5 + cal.cy
+    den_y, den_x = cal.f, cal.f + cal.b1
+    if abs(den_y) < 1e-12 or abs(den_x) < 1e-12:
+        raise ValueError("Invalid focal/b1 configuration caused division by zero.")
+    jj, ii = np.meshgrid(np.linspace(0.0, h - 1.0, steps), np.linspace(0.0, w - 1.0, steps), indexing="ij")
+    yn = (jj - cy0) / den_y
+    xn = (ii - cx0 - yn * cal.b2) / den_x
+    xn, yn = xn / zoom, yn / zoom
+    r2 = xn * xn + yn * yn
+    in_model = np.minimum(0.5 * np.sqrt(r2), 1.0) <= math.sin(math.radians(max(1.0, min(360.0, lens_fov_deg)) * 0.25))
+    if not in_model.any():
+        return 0.0
+    radial = 1.0 + r2 * (cal.k1 + r2 * (cal.k2 + r2 * (cal.k3 + r2 * cal.k4)))
+    xd = xn * radial + cal.p1 * (r2 + 2.0 * xn * xn) + 2.0 * cal.p2 * xn * yn
+    yd = yn * radial + cal.p2 * (r2 + 2.0 * yn * yn) + 2.0 * cal.p1 * xn * yn
+    sx = (cx0 + xd * (cal.f + cal.b1) + yd * cal.b2)[in_model]
+    sy = (cy0 + yd * cal.f)[in_model]
+    return float(max(0.0, (-sx).max(), (sx - (w - 1)).max(), (-sy).max(), (sy - (h - 1)).max()))
+
+
+def estimate_auto_undistort_zoom(cal: SensorCalibration, sample_count: int = 192,
+                                 lens_fov_deg: float = 190.0) -> float:
+    """DF:1054-1117: 1.0 if nothing overflows; otherwise grow the zoom by 1.2 (at most 20 times)
+    until nothing does and bisect 20 times between the last two values."""
+    steps = max(32, int(sample_count))
+    if _undistort_overflow(cal, 1.0, lens_fov_deg, steps) <= 0.0:
+        return 1.0
+    lo = hi = 1.0
+    for _ in range(20):
+        hi *= 1.2
+        if _undistort_overflow(cal, hi, lens_fov_deg, steps) <= 0.0:
+            break
+    else:
+        if _undistort_overflow(cal, hi, lens_fov_deg, steps) > 0.0:
+            return hi
+    for _ in range(20):
+        mid = 0.5 * (lo + hi)
+        if _undistort_overflow(cal, mid, lens_fov_deg, steps) <= 0.0:
+            hi = mid
+        else:
+            lo = mid
+    return hi
+
+
+def build_undistort_items(calibs: Sequence[SensorCalibration], undistort_zoom: Optional[float] = None,
+                          lens_fov_deg: float = 190.0):
+    """One UndistortItem per lens image, zoom as ``build_remap_cache`` picks it (DF:1142-1152):
+    the given value, else the auto estimate; never below 1e-6."""
+    from .api import UndistortItem
+    items = []
+    for slot, cal in enumerate(calibs):
+        if cal.model_type not in SUPPORTED_MODELS:
+            raise ValueError("Unsupported sensor model '{}' (supported: {}).".format(
+                cal.model_type, ", ".join(sorted(SUPPORTED_MODELS))))
+        zoom = float(undistort_zoom) if undistort_zoom is not None else estimate_auto_undistort_zoom(
+            cal, lens_fov_deg=float(lens_fov_deg))
+        items.append(UndistortItem(zoom=max(1e-6, zoom), src_slot=slot, view_id=str(cal.sensor_id)))
+    return items
 
 
 def choose_lenses(calib_x: SensorCalibration, calib_y: SensorCalibration, specs: Sequence[Dict[str, object]],

@@ -102,11 +102,20 @@ typedef struct r360_fisheye_calib {
     double lens_fov_deg;     /* usable lens FOV (DF --lens-fov-deg, default 190)            */
 } r360_fisheye_calib;
 
+/* One output of the fisheye -> undistorted-fisheye remap (DF --save-fisheye-output): which lens
+ * image it reads and the output zoom (RemapCache.undistort_zoom, DF:1136-1145; the auto value
+ * is estimate_auto_undistort_zoom, DF:1054-1117 -- computed by the host layer). */
+typedef struct r360_undistort {
+    double  zoom;            /* > 0 (clamped to >= 1e-6 like DF:1145)                       */
+    int32_t src_slot;        /* image of a source group / index into the calibration array  */
+    int32_t reserved;
+} r360_undistort;
+
 typedef struct r360_options {
     int32_t interp;          /* R360_NEAREST / LINEAR / CUBIC                               */
     int32_t convention;      /* ERP only: R360_CONV_*                                       */
     int32_t path;            /* R360_PATH_*                                                 */
-    int32_t fill_invalid;    /* fisheye only: 1 = write border_value where the ray is outside
+    int32_t fill_invalid;    /* fisheye/undistort: 1 = write border_value where the ray is outside
                                 the lens model or the sensor (DF:2009-2014)                 */
     double  border_value;    /* fisheye only: per-tap constant border (cv2 BORDER_CONSTANT) */
     int32_t out_dtype;       /* -1 = same as source; R360_F16 with a U16 source writes
@@ -154,6 +163,26 @@ int r360_remap_fisheye(const r360_images* src, const r360_images* dst,
                        const r360_options* opt, void* stream);
 
 /*
+ * Fisheye -> undistorted fisheye ("remove the Brown terms, keep the equisolid projection").
+ * Replaces build_remap_cache + cv2.remap + mask fill of undistort_prepared_image
+ * (gs360_DualFisheyeDistortionCalibration.py:1008-1051, :1120-1170, :1173-1217).  Output pixel
+ * (i, j) -- integer coordinates, no half-pixel offset, as in the reference -- samples the source at
+ *   y0 = (j - cy0) / f, x0 = (i - cx0 - y0 * b2) / (f + b1), (x, y) = (x0, y0) / zoom,
+ *   Brown(x, y) -> (cx0 + xd * (f + b1) + yd * b2, cy0 + yd * f),
+ * valid where 2 * asin(min(r / 2, 1)) <= lens_fov / 2 and the source lies on the sensor.
+ *
+ *   src      groups of `n_lenses` images, as r360_remap_fisheye;
+ *   items    n_items outputs per group (typically one per lens);
+ *   dst      (src->count / n_lenses) * n_items images, group-major; any size (the reference
+ *            writes sensor-sized images);
+ *   R360_E_INVALID_ARG if |f| or |f + b1| < 1e-12 (the reference raises, DF:1018-1020).
+ */
+int r360_remap_undistort(const r360_images* src, const r360_images* dst,
+                         const r360_fisheye_calib* calib, int32_t n_lenses,
+                         const r360_undistort* items, int32_t n_items,
+                         const r360_options* opt, void* stream);
+
+/*
  * Test/debug: the source coordinates the kernels sample at, without sampling.  Writes, for
  * view v and output pixel (j, i), element [(v * out_h + j) * out_w + i] of each non-null
  * device array:
@@ -169,6 +198,13 @@ int r360_coords(int32_t src_w, int32_t src_h,
                 int32_t out_w, int32_t out_h, const r360_options* opt,
                 float* map_x32, float* map_y32, double* map_x64, double* map_y64,
                 uint8_t* valid, void* stream);
+
+/* r360_coords for the undistort projection (maps of DF:1120-1170 before the float32 cast too). */
+int r360_coords_undistort(const r360_fisheye_calib* calib, int32_t n_lenses,
+                          const r360_undistort* items, int32_t n_items,
+                          int32_t out_w, int32_t out_h,
+                          float* map_x32, float* map_y32, double* map_x64, double* map_y64,
+                          uint8_t* valid, void* stream);
 
 /* ---- planned (tiled) execution -------------------------------------------------------------------
  *
@@ -199,6 +235,12 @@ int r360_plan_create_fisheye(const r360_images* src_layout, const r360_images* d
                              const r360_view* views, int32_t n_views, const r360_options* opt,
                              void* workspace_device, size_t workspace_bytes, void* stream,
                              r360_plan** plan_out);
+
+int r360_plan_create_undistort(const r360_images* src_layout, const r360_images* dst_layout,
+                               const r360_fisheye_calib* calib, int32_t n_lenses,
+                               const r360_undistort* items, int32_t n_items, const r360_options* opt,
+                               void* workspace_device, size_t workspace_bytes, void* stream,
+                               r360_plan** plan_out);
 
 /* Tiles per view and how many (view, tile) pairs take the direct path. */
 int r360_plan_info(const r360_plan* plan, int32_t* tiles_per_view, int32_t* n_fallback_tiles);

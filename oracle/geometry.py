@@ -142,6 +142,68 @@ def fisheye_map64(calib: Mapping[str, float], yaw_rel_deg: float, pitch_deg: flo
     return mx, my, valid
 
 
+def undistort_map64(calib: Mapping[str, float], zoom: float, lens_fov_deg: float,
+                    out_w: int = 0, out_h: int = 0, grid_x=None, grid_y=None):
+    """Fisheye -> undistorted fisheye: (map_x, map_y, valid, valid_model), float64 restatement of
+    ``_remap_for_zoom`` (DF:1008-1051) on the integer pixel grid of ``build_remap_cache``
+    (DF:1136-1140) or on an explicit grid (``estimate_auto_undistort_zoom``, DF:1069-1071)."""
+    w = int(out_w) or int(calib["width"])
+    h = int(out_h) or int(calib["height"])
+    gx = np.arange(w, dtype=np.float64) if grid_x is None else np.asarray(grid_x, dtype=np.float64)
+    gy = np.arange(h, dtype=np.float64) if grid_y is None else np.asarray(grid_y, dtype=np.float64)
+    dst_x, dst_y = np.meshgrid(gx, gy)
+    cx0 = calib["width"] * 0.5 + calib["cx"]
+    cy0 = calib["height"] * 0.5 + calib["cy"]
+    den_y, den_x = calib["f"], calib["f"] + calib["b1"]
+    if abs(den_y) < 1e-12 or abs(den_x) < 1e-12:
+        raise ValueError("Invalid focal/b1 configuration caused division by zero.")
+    y0 = (dst_y - cy0) / den_y
+    x0 = (dst_x - cx0 - y0 * calib["b2"]) / den_x
+    x, y = x0 / zoom, y0 / zoom
+    xd, yd = brown_distort(x, y, calib)
+    mx = cx0 + xd * calib["f"] + xd * calib["b1"] + yd * calib["b2"]
+    my = cy0 + yd * calib["f"]
+    r = np.sqrt(np.maximum(x * x + y * y, 0.0))
+    theta = 2.0 * np.arcsin(np.clip(r * 0.5, 0.0, 1.0))
+    theta_max = math.radians(max(1.0, min(360.0, float(lens_fov_deg))) * 0.5)
+    valid_model = theta <= theta_max
+    valid = valid_model & (mx >= 0.0) & (mx <= calib["width"] - 1) & (my >= 0.0) & (my <= calib["height"] - 1)
+    return mx, my, valid, valid_model
+
+
+def auto_undistort_zoom(calib: Mapping[str, float], lens_fov_deg: float = 190.0, sample_count: int = 192) -> float:
+    """Smallest zoom (to bisection accuracy) at which no model-valid sample of a coarse grid reads
+    outside the sensor: DF:1054-1117 (x1.2 bracketing up to 20 times, then 20 bisections)."""
+    w, h = int(calib["width"]), int(calib["height"])
+    steps = max(32, int(sample_count))
+    gx, gy = np.linspace(0.0, w - 1.0, steps), np.linspace(0.0, h - 1.0, steps)
+
+    def overflow(zoom):
+        mx, my, _, vm = undistort_map64(calib, zoom, lens_fov_deg, grid_x=gx, grid_y=gy)
+        if not vm.any():
+            return 0.0
+        sx, sy = mx[vm], my[vm]
+        return float(max(np.max(np.maximum(0.0, -sx)), np.max(np.maximum(0.0, sx - (w - 1))),
+                         np.max(np.maximum(0.0, -sy)), np.max(np.maximum(0.0, sy - (h - 1)))))
+
+    if overflow(1.0) <= 0.0:
+        return 1.0
+    low = high = 1.0
+    for _ in range(20):
+        high *= 1.2
+        if overflow(high) <= 0.0:
+            break
+    if overflow(high) > 0.0:
+        return high
+    for _ in range(20):
+        mid = (low + high) * 0.5
+        if overflow(mid) <= 0.0:
+            high = mid
+        else:
+            low = mid
+    return high
+
+
 def wrap_angle_deg(a: float) -> float:
     """DF:1342-1345: wrap to [-180, 180)."""
     return ((float(a) + 180.0) % 360.0) - 180.0

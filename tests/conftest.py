@@ -46,5 +46,10 @@ def golden_df_maps():
 
 
 @pytest.fixture(scope="session")
+def golden_undistort():
+    return json.loads((GOLDEN / "undistort.json").read_text()), np.load(GOLDEN / "undistort_maps.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_cv2():
     return np.load(GOLDEN / "cv2_remap.npz")

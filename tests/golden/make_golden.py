@@ -23,6 +23,10 @@ dualfisheye_maps.npz    reference float32 maps: all views x both lenses at 96 px
                         a strided sample (every 25th pixel) of the chosen-lens
                         maps at 1750 px, and 64 px maps for a synthetic
                         calibration with every Brown/affinity term non-zero
+undistort.json          fisheye -> undistorted fisheye (DF:1008-1170): the auto zoom of
+undistort_maps.npz      ``estimate_auto_undistort_zoom`` and strided ``build_remap_cache`` maps
+                        + validity for the template calibration (auto and fixed zoom) and
+                        the synthetic one; a small full-resolution case for cv2 parity
 cv2_remap.npz           ``cv2.remap`` outputs (the routine the reference calls,
                         DF:2001-2008) for small random sources x dtypes x
                         interpolations x borders
@@ -187,6 +191,42 @@ def dump_dualfisheye(df):
     (HERE / "dualfisheye.json").write_text(json.dumps(meta, indent=1, sort_keys=True) + "\n")
 
 
+def dump_undistort(df):
+    sensor_map, _ = df.load_metashape_calibration(df.DEFAULT_CAMERA_XML)
+    tmpl = sensor_map[sorted(sensor_map)[0]]
+    syn = df.SensorCalibration(sensor_id="9", model_type="equisolid_fisheye", width=3000, height=2800,
+                               f=820.5, cx=12.25, cy=-7.5, k1=0.08, k2=-0.011, k3=0.0021, k4=-0.0003,
+                               p1=0.0007, p2=-0.0004, b1=1.75, b2=-0.6)
+    tiny = df.SensorCalibration(sensor_id="7", model_type="equisolid_fisheye", width=320, height=288,
+                                f=88.0, cx=1.5, cy=-2.25, k1=0.05, k2=-0.008, k3=0.001, k4=0.0,
+                                p1=0.0005, p2=-0.0003, b1=0.4, b2=-0.2)
+    wide = df.SensorCalibration(sensor_id="8", model_type="equisolid_fisheye", width=320, height=288,
+                                f=118.0, cx=-3.0, cy=2.0, k1=0.03, k2=0.004, k3=0.0, k4=0.0,
+                                p1=0.0, p2=0.0, b1=0.0, b2=0.0)      # image circle larger than the sensor
+    meta, arrays = {"cases": {}}, {}
+    cases = [("wide_auto", wide, None, 190.0, 2), ("wide_auto_fov120", wide, None, 120.0, 2),("tmpl_auto", tmpl, None, 190.0, 32), ("tmpl_z1", tmpl, 1.0, 190.0, 32),
+             ("tmpl_z125_fov170", tmpl, 1.25, 170.0, 32), ("syn_auto", syn, None, 185.0, 25),
+             ("tiny_auto", tiny, None, 190.0, 1), ("tiny_z09_fov150", tiny, 0.9, 150.0, 1)]
+    for name, cal, zoom, fov, stride in cases:
+        rc = df.build_remap_cache(cal, zoom, fov)
+        meta["cases"][name] = {"calibration": _calib_dict(cal), "zoom_arg": zoom, "lens_fov_deg": fov,
+                               "undistort_zoom": float(rc.undistort_zoom), "stride": stride,
+                               "valid_ratio": float(np.mean(rc.valid_mask))}
+        arrays[name + "_x"] = rc.map_x[::stride, ::stride].copy()
+        arrays[name + "_y"] = rc.map_y[::stride, ::stride].copy()
+        arrays[name + "_v"] = rc.valid_mask[::stride, ::stride].copy()
+    meta["auto_zoom"] = {"tmpl_190": float(df.estimate_auto_undistort_zoom(tmpl, lens_fov_deg=190.0)),
+                         "tmpl_150": float(df.estimate_auto_undistort_zoom(tmpl, lens_fov_deg=150.0)),
+                         "syn_185": float(df.estimate_auto_undistort_zoom(syn, lens_fov_deg=185.0)),
+                         "wide_190": float(df.estimate_auto_undistort_zoom(wide, lens_fov_deg=190.0)),
+                         "wide_120": float(df.estimate_auto_undistort_zoom(wide, lens_fov_deg=120.0)),
+                         "wide_190_n48": float(df.estimate_auto_undistort_zoom(wide, sample_count=48, lens_fov_deg=190.0)),
+                         "tiny_190": float(df.estimate_auto_undistort_zoom(tiny, lens_fov_deg=190.0)),
+                         "tiny_190_n64": float(df.estimate_auto_undistort_zoom(tiny, sample_count=64, lens_fov_deg=190.0))}
+    np.savez_compressed(HERE / "undistort_maps.npz", **arrays)
+    (HERE / "undistort.json").write_text(json.dumps(meta, indent=1, sort_keys=True) + "\n")
+
+
 def dump_cv2():
     import cv2
     rng = np.random.default_rng(20261017)
@@ -228,6 +268,7 @@ def main():
     import gs360_DualFisheyeDistortionCalibration as df
     dump_perspcut(pc)
     dump_dualfisheye(df)
+    dump_undistort(df)
     dump_cv2()
     for p in sorted(HERE.glob("*.json")) + sorted(HERE.glob("*.npz")):
         print("%9d  %s" % (p.stat().st_size, p.name))

@@ -88,6 +88,25 @@ def test_dualfisheye_host_helpers_match_reference(golden_df):
         dfh.compute_view_fov_deg(0.0, "36 36")
 
 
+def test_auto_undistort_zoom_and_items_match_reference(golden_undistort):
+    meta, _ = golden_undistort
+    cals = {"tmpl": "tmpl_auto", "syn": "syn_auto", "tiny": "tiny_auto", "wide": "wide_auto"}
+    for key, want in meta["auto_zoom"].items():
+        parts = key.split("_")
+        cal = dfh.SensorCalibration(**meta["cases"][cals[parts[0]]]["calibration"])
+        n = int(parts[2][1:]) if len(parts) > 2 else 192
+        got = dfh.estimate_auto_undistort_zoom(cal, sample_count=n, lens_fov_deg=float(parts[1]))
+        assert abs(got - want) <= 2e-6 * want, (key, got, want)
+    wide = dfh.SensorCalibration(**meta["cases"]["wide_auto"]["calibration"])
+    items = dfh.build_undistort_items([wide, wide])
+    assert [it.src_slot for it in items] == [0, 1]
+    assert abs(items[0].zoom - meta["cases"]["wide_auto"]["undistort_zoom"]) < 1e-5
+    assert dfh.build_undistort_items([wide], undistort_zoom=0.0)[0].zoom == 1e-6          # DF:1145
+    bad = dfh.SensorCalibration(sensor_id="1", model_type="frame", width=10, height=10, f=5.0)
+    with pytest.raises(ValueError, match="Unsupported sensor model"):
+        dfh.build_undistort_items([bad])
+
+
 def test_calibration_xml_loader(tmp_path, golden_df):
     want = golden_df["sensors"]["0"]
     xml = tmp_path / "cal.xml"

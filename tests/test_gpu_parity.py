@@ -390,3 +390,90 @@ def test_launch_counter_moves(r360):
     before = r360.launch_count()
     r360.remap_erp(src, _views(r360, [(0, 0)]), (32, 32))
     assert r360.launch_count() > before
+
+
+# ------------------------------------------------------------------------------------------
+# fisheye -> undistorted fisheye (DF:1008-1217)
+# ------------------------------------------------------------------------------------------
+
+def _calib_from(r360, cal, fov):
+    return r360.FisheyeCalibration(**{k: cal[k] for k in ("width", "height", "f", "cx", "cy", "k1", "k2", "k3",
+                                                           "k4", "p1", "p2", "b1", "b2")}, lens_fov_deg=fov)
+
+
+@pytest.mark.parametrize("path", ["direct", "tiled"])
+def test_undistort_coordinates_against_oracle_and_reference_maps(r360, path, golden_undistort):
+    meta, maps = golden_undistort
+    for name, case in meta["cases"].items():
+        cal, st = case["calibration"], case["stride"]
+        w, h = int(cal["width"]), int(cal["height"])
+        items = [r360.UndistortItem(case["undistort_zoom"], 0)]
+        got = r360.sample_coordinates(items, (w, h), calibs=[_calib_from(r360, cal, case["lens_fov_deg"])], path=path)
+        mx, my, ok, _ = geo.undistort_map64(cal, case["undistort_zoom"], case["lens_fov_deg"])
+        x64, y64 = got["x64"][0].cpu().numpy(), got["y64"][0].cpu().numpy()
+        assert np.array_equal(got["valid"][0].cpu().numpy().astype(bool), ok), name
+        assert np.abs(x64 - mx)[ok].max() <= 2e-5 and np.abs(y64 - my)[ok].max() <= 2e-5, name
+        # the reference's own float32 maps
+        assert np.abs(x64[::st, ::st] - maps[name + "_x"])[ok[::st, ::st]].max() < 2e-3, name
+        assert np.abs(y64[::st, ::st] - maps[name + "_y"])[ok[::st, ::st]].max() < 2e-3, name
+        assert np.array_equal(ok[::st, ::st], maps[name + "_v"])
+
+
+@pytest.mark.parametrize("path", ["direct", "tiled"])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic"])
+def test_undistort_pixels(r360, path, dtype, interp, golden_undistort):
+    """Two lens images, three outputs (auto zoom, zoom < 1, a narrower lens FOV), mask fill on and off."""
+    meta, _ = golden_undistort
+    rng = np.random.default_rng(5)
+    cases = [("wide_auto", 0), ("tiny_z09_fov150", 1)]
+    for name, slot in cases:
+        case = meta["cases"][name]
+        cal = case["calibration"]
+        w, h = int(cal["width"]), int(cal["height"])
+        pair = _noise(rng, (2, 2, h, w, 3), dtype)
+        calib = _calib_from(r360, cal, case["lens_fov_deg"])
+        items = [r360.UndistortItem(case["undistort_zoom"], slot), r360.UndistortItem(1.31, 1 - slot)]
+        for fill, bv in ((True, 0), (False, 23)):
+            got = _to_numpy(r360.undistort_fisheye(_to_cuda(pair), [calib, calib], items, interp=interp,
+                                                   border_value=bv, fill_invalid=fill, path=path))
+            assert got.shape == (2, 2, h, w, 3)
+            for g in range(2):
+                for k, it in enumerate(items):
+                    mx, my, ok, _ = geo.undistort_map64(cal, it.zoom, case["lens_fov_deg"])
+                    want = sampler.sample(pair[g, it.src_slot], mx, my, interp, "constant", bv)
+                    if fill:
+                        want = sampler.apply_invalid_fill(want, ok, bv)
+                    exact, within1, worst = _lsb_stats(got[g, k], want)
+                    assert within1 >= PIXEL_OK_FRACTION and exact >= 0.999, (name, g, k, fill, exact, within1, worst)
+
+
+def test_undistort_full_size_against_cv2(r360, golden_undistort):
+    """3840^2 template calibration, u8 cubic, tiled path, checked against the real cv2.remap + mask fill
+    (what undistort_prepared_image does, DF:1198-1211) on the float64 oracle map."""
+    cv2 = pytest.importorskip("cv2")
+    meta, _ = golden_undistort
+    case = meta["cases"]["tmpl_auto"]
+    cal = case["calibration"]
+    w, h = int(cal["width"]), int(cal["height"])
+    rng = np.random.default_rng(77)
+    img = _noise(rng, (h, w, 3), np.uint8)
+    got = _to_numpy(r360.undistort_fisheye(_to_cuda(img)[None, None], [_calib_from(r360, cal, 190.0)],
+                                           [r360.UndistortItem(case["undistort_zoom"], 0)], interp="cubic"))[0, 0]
+    mx, my, ok, _ = geo.undistort_map64(cal, case["undistort_zoom"], 190.0)
+    want = cv2.remap(img, mx.astype(np.float32), my.astype(np.float32), cv2.INTER_CUBIC,
+                     borderMode=cv2.BORDER_CONSTANT, borderValue=0.0)
+    want[~ok] = 0
+    exact, within1, worst = _lsb_stats(got, want)
+    assert within1 >= PIXEL_OK_FRACTION and exact >= 0.999, (exact, within1, worst)
+
+
+def test_undistort_argument_errors(r360):
+    dev = torch.zeros((1, 1, 16, 16, 3), dtype=torch.uint8, device="cuda")
+    good = r360.FisheyeCalibration(16, 16, 10.0)
+    with pytest.raises(r360.Remap360Error):
+        r360.undistort_fisheye(dev, [r360.FisheyeCalibration(16, 16, 0.0)], [r360.UndistortItem(1.0, 0)], path="direct")
+    with pytest.raises(r360.Remap360Error):
+        r360.undistort_fisheye(dev, [good], [r360.UndistortItem(1.0, 3)], path="direct")
+    with pytest.raises(r360.Remap360Error):
+        r360.undistort_fisheye(dev, [good], [])

@@ -139,3 +139,36 @@ def test_every_distortion_term(golden_df, golden_df_maps):
 def test_wrap_angle(golden_df):
     for a, want in golden_df["wrap_angle_deg"]:
         assert g.wrap_angle_deg(a) == want
+
+
+# --- fisheye -> undistorted fisheye (DF:1008-1170) -------------------------------------------
+
+def test_undistort_maps_match_reference_float32_maps(golden_undistort):
+    meta, maps = golden_undistort
+    for name, case in meta["cases"].items():
+        st = case["stride"]
+        mx, my, valid, _ = g.undistort_map64(case["calibration"], case["undistort_zoom"], case["lens_fov_deg"])
+        mx, my, valid = mx[::st, ::st], my[::st, ::st], valid[::st, ::st]
+        assert np.array_equal(valid, maps[name + "_v"]), name
+        assert abs(valid.mean() - case["valid_ratio"]) < 0.02
+        # the reference evaluates in float32 on coordinates up to 3840: ~1e-3 px of rounding
+        assert np.abs(mx - maps[name + "_x"]).max() < 2e-3, name
+        assert np.abs(my - maps[name + "_y"]).max() < 2e-3, name
+
+
+def test_auto_undistort_zoom_matches_reference(golden_undistort):
+    meta, _ = golden_undistort
+    cals = {"tmpl": "tmpl_auto", "syn": "syn_auto", "tiny": "tiny_auto", "wide": "wide_auto"}
+    for key, want in meta["auto_zoom"].items():
+        parts = key.split("_")
+        cal = meta["cases"][cals[parts[0]]]["calibration"]
+        n = int(parts[2][1:]) if len(parts) > 2 else 192
+        got = g.auto_undistort_zoom(cal, float(parts[1]), n)
+        assert abs(got - want) <= 2e-6 * want, (key, got, want)
+    assert meta["auto_zoom"]["wide_190"] > 1.05       # the search really ran
+
+
+def test_undistort_rejects_degenerate_focal():
+    with pytest.raises(ValueError):
+        g.undistort_map64(dict(width=8, height=8, f=0.0, cx=0, cy=0, k1=0, k2=0, k3=0, k4=0, p1=0, p2=0, b1=0, b2=0),
+                          1.0, 190.0)
