@@ -19,7 +19,7 @@ constexpr int kMaxLenses = 4;
 // kProjUndistort: fisheye image -> "undistorted" fisheye image (DF:1008-1051); its views carry the
 // normalised sensor-plane coordinates (x / zoom, y / zoom, 1) instead of a world ray.
 enum Proj : int { kProjErp = 0, kProjFisheye = 1, kProjUndistort = 2 };
-enum Interp : int { kNearest = 0, kLinear = 1, kCubic = 2 };
+enum Interp : int { kNearest = 0, kLinear = 1, kCubic = 2, kLanczos4 = 3 };
 
 // A view is a linear map from output pixel indices to an (unnormalised) world ray:
 //   d(i, j) = c0 + i * ci + j * cj

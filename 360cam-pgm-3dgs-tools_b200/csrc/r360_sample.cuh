@@ -113,13 +113,14 @@ __device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int
                 for (int c = 0; c < 4; ++c)
                     if (c < channels) dst[c] = Finish<uint8_t, TOut>::run((float)((acc[c] + 512) >> 10));
             } else {
-                const short* wt = g_tables.cubic_fixed + (fy * 32 + fx) * 16;
+                constexpr int K = INTERP == kCubic ? 4 : 8, OFF = K / 2 - 1;
+                const short* wt = (INTERP == kCubic ? g_tables.cubic_fixed : g_tables.lanczos_fixed) + (fy * 32 + fx) * (K * K);
+#pragma unroll(K == 4 ? 4 : 1)
+                for (int ky = 0; ky < K; ++ky)
 #pragma unroll
-                for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-                    for (int kx = 0; kx < 4; ++kx) {
-                        taps.load(ix - 1 + kx, iy - 1 + ky, t);
-                        const int wgt = wt[ky * 4 + kx];
+                    for (int kx = 0; kx < K; ++kx) {
+                        taps.load(ix - OFF + kx, iy - OFF + ky, t);
+                        const int wgt = wt[ky * K + kx];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) acc[c] += wgt * (int)t[c];
                     }
@@ -145,19 +146,21 @@ __device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int
                         }
                     }
             } else {
-                const float* wx = g_tables.cubic_1d + 4 * fx;
-                const float* wy = g_tables.cubic_1d + 4 * fy;
-                const int x0 = ix - 1, y0 = iy - 1;
+                constexpr int K = INTERP == kCubic ? 4 : 8, OFF = K / 2 - 1;
+                const float* tab = INTERP == kCubic ? g_tables.cubic_1d : g_tables.lanczos_1d;
+                const float* wx = tab + K * fx;
+                const float* wy = tab + K * fy;
+                const int x0 = ix - OFF, y0 = iy - OFF;
                 bool interior = true;
                 if constexpr (Taps::kConstantBorder)
-                    interior = x0 >= 0 && x0 < max(src_w - 3, 0) && y0 >= 0 && y0 < max(src_h - 3, 0);
+                    interior = x0 >= 0 && x0 < max(src_w - (K - 1), 0) && y0 >= 0 && y0 < max(src_h - (K - 1), 0);
                 if (interior) {
                     // each row summed left to right, rows added to a running sum that starts at zero
-#pragma unroll
-                    for (int ky = 0; ky < 4; ++ky) {
+#pragma unroll(K == 4 ? 4 : 1)
+                    for (int ky = 0; ky < K; ++ky) {
                         float row[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int kx = 0; kx < 4; ++kx) {
+                        for (int kx = 0; kx < K; ++kx) {
                             taps.load(x0 + kx, y0 + ky, t);
                             const float wgt = __fmul_rn(wy[ky], wx[kx]);
 #pragma unroll
@@ -174,8 +177,8 @@ __device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int
                     // (tap - border) * w for the taps that exist
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[c] = border;
-                    for (int ky = 0; ky < 4; ++ky)
-                        for (int kx = 0; kx < 4; ++kx) {
+                    for (int ky = 0; ky < K; ++ky)
+                        for (int kx = 0; kx < K; ++kx) {
                             if (!taps.exists(x0 + kx, y0 + ky)) continue;
                             taps.load(x0 + kx, y0 + ky, t);
                             const float wgt = __fmul_rn(wy[ky], wx[kx]);

@@ -38,8 +38,8 @@ constexpr int kFitChecks = 13;
 // Patch margins around the range of floor(coord).  The quantised coordinate rint(32 x) / 32 can round
 // up to the next integer, so bilinear taps reach floor(x) + 2 and bicubic taps floor(x) - 1 .. + 3;
 // one more column / row is kept on the low side.
-__host__ __device__ constexpr int tap_margin_lo(int interp) { return interp == kCubic ? 2 : 1; }
-__host__ __device__ constexpr int tap_margin_hi(int interp) { return interp == kCubic ? 3 : 2; }
+__host__ __device__ constexpr int tap_margin_lo(int interp) { return interp == kLanczos4 ? 4 : interp == kCubic ? 2 : 1; }
+__host__ __device__ constexpr int tap_margin_hi(int interp) { return interp == kLanczos4 ? 5 : interp == kCubic ? 3 : 2; }
 
 // kModeFast: patch staged with 2-D tensor TMA boxes; kModeFastRows: staged row by row with 1-D bulk
 // copies (rows clamped at the poles, or wider than the largest box).
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
     unsigned char* ring = stage0 + P.out_stage_bytes;
 
     constexpr bool kFastU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
-                             INTERP != kNearest;
+                             (INTERP == kLinear || INTERP == kCubic);
     const int tid = threadIdx.x;
     const int n_tiles = P.tiles_x * P.tiles_y;
     const int total = P.n_groups * P.n_views * n_tiles;             // the host keeps this below 2^31

@@ -258,14 +258,17 @@ int dispatch(int proj, int interp, int in_dt, int out_dt, F&& f) {
             if (interp == R360_NEAREST) return f.template run<kProjErp, kNearest, TIN, TOUT>();             \
             if (interp == R360_LINEAR) return f.template run<kProjErp, kLinear, TIN, TOUT>();               \
             if (interp == R360_CUBIC) return f.template run<kProjErp, kCubic, TIN, TOUT>();                 \
+            if (interp == R360_LANCZOS4) return f.template run<kProjErp, kLanczos4, TIN, TOUT>();           \
         } else if (proj == kProjFisheye) {                                                                  \
             if (interp == R360_NEAREST) return f.template run<kProjFisheye, kNearest, TIN, TOUT>();         \
             if (interp == R360_LINEAR) return f.template run<kProjFisheye, kLinear, TIN, TOUT>();           \
             if (interp == R360_CUBIC) return f.template run<kProjFisheye, kCubic, TIN, TOUT>();             \
+            if (interp == R360_LANCZOS4) return f.template run<kProjFisheye, kLanczos4, TIN, TOUT>();       \
         } else if (proj == kProjUndistort) {                                                                \
             if (interp == R360_NEAREST) return f.template run<kProjUndistort, kNearest, TIN, TOUT>();       \
             if (interp == R360_LINEAR) return f.template run<kProjUndistort, kLinear, TIN, TOUT>();         \
             if (interp == R360_CUBIC) return f.template run<kProjUndistort, kCubic, TIN, TOUT>();           \
+            if (interp == R360_LANCZOS4) return f.template run<kProjUndistort, kLanczos4, TIN, TOUT>();     \
         }                                                                                                   \
         return R360_E_INVALID_ARG;                                                                          \
     } while (0)
@@ -306,7 +309,7 @@ int prepare(int proj, const r360_images* src, const r360_images* dst, const r360
     if (proj != kProjErp && !calib) return R360_E_INVALID_ARG;
     r360_options opt;
     if (opt_in) opt = *opt_in; else r360_default_options(&opt);
-    if (opt.interp < R360_NEAREST || opt.interp > R360_CUBIC) return R360_E_INVALID_ARG;
+    if (opt.interp < R360_NEAREST || opt.interp > R360_LANCZOS4) return R360_E_INVALID_ARG;
     if (opt.convention != R360_CONV_HALFPIXEL && opt.convention != R360_CONV_V360) return R360_E_INVALID_ARG;
     if (opt.path < R360_PATH_AUTO || opt.path > R360_PATH_TILED) return R360_E_INVALID_ARG;
     if (s_chk.channels != d_chk.channels) return R360_E_INVALID_ARG;
@@ -852,6 +855,14 @@ int r360_debug_weight_tables(int16_t* cubic_fixed_16384, float* cubic_1d_128) {
     build_weight_tables(&t);
     if (cubic_fixed_16384) std::memcpy(cubic_fixed_16384, t.cubic_fixed, sizeof(t.cubic_fixed));
     if (cubic_1d_128) std::memcpy(cubic_1d_128, t.cubic_1d, sizeof(t.cubic_1d));
+    return R360_OK;
+}
+
+int r360_debug_weight_tables_lanczos4(int16_t* fixed_65536, float* one_d_256) {
+    static WeightTables t;
+    build_weight_tables(&t);
+    if (fixed_65536) std::memcpy(fixed_65536, t.lanczos_fixed, sizeof(t.lanczos_fixed));
+    if (one_d_256) std::memcpy(one_d_256, t.lanczos_1d, sizeof(t.lanczos_1d));
     return R360_OK;
 }
 

@@ -14,7 +14,7 @@ LIB_PATH = pathlib.Path(__file__).resolve().parent / "libremap360.so"
 
 R360_OK = 0
 DTYPE_U8, DTYPE_U16, DTYPE_F16, DTYPE_F32 = 0, 1, 2, 3
-INTERP = {"nearest": 0, "linear": 1, "bilinear": 1, "cubic": 2, "bicubic": 2}
+INTERP = {"nearest": 0, "linear": 1, "bilinear": 1, "cubic": 2, "bicubic": 2, "lanczos4": 3}
 CONVENTION = {"halfpixel": 0, "v360": 1}
 PATH = {"auto": 0, "direct": 1, "tiled": 2}
 MAX_LENSES = 4
@@ -106,6 +106,7 @@ def load() -> ctypes.CDLL:
     lib.r360_plan_destroy.argtypes = [c_void_p]
     lib.r360_plan_destroy.restype = None
     lib.r360_debug_weight_tables.argtypes = [c_void_p, c_void_p]
+    lib.r360_debug_weight_tables_lanczos4.argtypes = [c_void_p, c_void_p]
     if lib.r360_abi_version() != 1:
         raise ImportError("libremap360.so has ABI version %d, expected 1" % lib.r360_abi_version())
     _lib = lib

@@ -73,7 +73,8 @@ def parse_job_argv(argv: Sequence[str]) -> ParsedJob:
                      jpeg_quality=95 if q == "2" else 100, pix_fmt=opt("-pix_fmt"))
 
 
-_INTERP = {"cubic": "cubic", "linear": "linear", "nearest": "nearest", "near": "nearest"}
+_INTERP = {"cubic": "cubic", "linear": "linear", "nearest": "nearest", "near": "nearest",
+           "lanczos": "lanczos4"}          # v360 `lanczos` -> the cv2-compatible 8x8 Lanczos kernel
 _gpu_lock = threading.Lock()
 
 

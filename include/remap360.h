@@ -45,7 +45,7 @@ enum { R360_U8 = 0, R360_U16 = 1, R360_F16 = 2, R360_F32 = 3 };
 
 /* cv2 names at gs360_DualFisheyeDistortionCalibration.py:59-64; ffmpeg `interp=` at
  * gs360_360PerspCut.py:107-109.  Arithmetic is cv2.remap's (1/32-px fractions, A = -0.75). */
-enum { R360_NEAREST = 0, R360_LINEAR = 1, R360_CUBIC = 2 };
+enum { R360_NEAREST = 0, R360_LINEAR = 1, R360_CUBIC = 2, R360_LANCZOS4 = 3 };
 
 /* ERP pixel convention: HALFPIXEL x = (lon/2pi+.5)*W - .5 (in-repo
  * geometry, gs360_GUI.py:419-424 with pixel centres); V360 x = (lon/2pi+.5)*(W-1) (the
@@ -112,7 +112,7 @@ typedef struct r360_undistort {
 } r360_undistort;
 
 typedef struct r360_options {
-    int32_t interp;          /* R360_NEAREST / LINEAR / CUBIC                               */
+    int32_t interp;          /* R360_NEAREST / LINEAR / CUBIC / LANCZOS4                    */
     int32_t convention;      /* ERP only: R360_CONV_*                                       */
     int32_t path;            /* R360_PATH_*                                                 */
     int32_t fill_invalid;    /* fisheye/undistort: 1 = write border_value where the ray is outside

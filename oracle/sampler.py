@@ -12,7 +12,8 @@ initInterTab2D, remapNearest/remapBilinear/remapBicubic) is restated here:
   (round-half-even), integer part ``s >> 5`` saturated to int16, fraction
   ``s & 31``;
 * 1-D weights for the 32 fractions: linear ``(1-t, t)``; cubic with A = -0.75,
-  evaluated in float32 exactly as ``interpolateCubic``;
+  evaluated in float32 exactly as ``interpolateCubic``; lanczos4 (8 taps) as
+  ``interpolateLanczos4`` (double sin/cos, float32 coefficients and normalisation);
 * 2-D weight = float32 product ``wy * wx``.  uint8 uses 15-bit fixed-point
   weights ``saturate_cast<short>(w * 32768)``; when a table entry does not sum
   to 32768 the difference is folded into the largest (sum too small) or
@@ -30,6 +31,7 @@ real ``cv2.remap`` by padding the source, which is how the model is pinned.
 from __future__ import annotations
 
 import functools
+import math
 from typing import Tuple
 
 import numpy as np
@@ -40,7 +42,7 @@ INTER_TAB = 1 << INTER_BITS          # 32
 COEF_BITS = 15
 COEF_ONE = 1 << COEF_BITS            # 32768
 
-INTERPS = ("nearest", "linear", "cubic")
+INTERPS = ("nearest", "linear", "cubic", "lanczos4")
 
 
 def _cubic_coeffs(t: np.float32) -> np.ndarray:
@@ -55,6 +57,30 @@ def _cubic_coeffs(t: np.float32) -> np.ndarray:
     return np.array([c0, c1, c2, c3], dtype=F32)
 
 
+def _lanczos4_coeffs(t: np.float32) -> np.ndarray:
+    """interpolateLanczos4: a = 4 windowed sinc over 8 taps written with the angle-addition table
+    cs[] (sin/cos in double, each coefficient rounded to float32, float32 normalisation);
+    a zero fraction is the exact unit impulse."""
+    x = F32(t)
+    if x < np.finfo(F32).eps:
+        return np.array([0, 0, 0, 1, 0, 0, 0, 0], dtype=F32)
+    s45 = 0.70710678118654752440084436210485
+    cs = ((1, 0), (-s45, -s45), (0, 1), (s45, -s45), (-1, 0), (s45, s45), (0, -1), (-s45, s45))
+    y0 = -(float(x) + 3.0) * math.pi * 0.25
+    s0, c0 = math.sin(y0), math.cos(y0)
+    co = np.empty(8, dtype=F32)
+    total = F32(0)
+    for i in range(8):
+        d = F32(x + F32(3) - F32(i))
+        if abs(d) >= F32(1e-6):
+            y = -float(d) * math.pi * 0.25
+            co[i] = F32((cs[i][0] * s0 + cs[i][1] * c0) / (y * y))
+        else:
+            co[i] = F32(1e30)
+        total = F32(total + co[i])
+    return (co * F32(F32(1) / total)).astype(F32)
+
+
 @functools.lru_cache(maxsize=None)
 def tables(interp: str) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """(tab1d[32,k] f32, tab2d[32,32,k,k] f32, itab2d[32,32,k,k] int32)."""
@@ -64,6 +90,8 @@ def tables(interp: str) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
                 for i in range(INTER_TAB)]
     elif interp == "cubic":
         rows = [_cubic_coeffs(F32(i) * scale) for i in range(INTER_TAB)]
+    elif interp == "lanczos4":
+        rows = [_lanczos4_coeffs(F32(i) * scale) for i in range(INTER_TAB)]
     else:
         raise ValueError(interp)
     t1 = np.stack(rows).astype(F32)
@@ -157,7 +185,7 @@ def _sample_block(s3, mx, my, interp, border, border_value, out_dtype):
     iy, fy = quantise(my)
     t1, tab, itab = tables(interp)
     k = t1.shape[1]
-    off = k // 2 - 1            # linear: 0, cubic: 1
+    off = k // 2 - 1            # linear: 0, cubic: 1, lanczos4: 3
     if in_dtype == np.uint8:
         acc = np.zeros(mx.shape + (s3.shape[2],), dtype=np.int64)
         fill = np.int64(np.clip(np.rint(border_value), 0, 255))
@@ -179,8 +207,8 @@ def _sample_block(s3, mx, my, interp, border, border_value, out_dtype):
                 term = (p * tab[fy, fx, k1, k2][..., None]).astype(F32)
                 acc = term if acc is None else (acc + term).astype(F32)
         return _finish_float(acc, in_dtype, out_dtype)
-    # remapBicubic, all 16 taps inside: each row summed left to right, rows
-    # added to a running sum that starts at zero
+    # remapBicubic / remapLanczos4, all taps inside: each row summed left to right,
+    # rows added to a running sum that starts at zero
     acc = np.zeros(mx.shape + (s3.shape[2],), dtype=F32)
     for k1 in range(k):
         row = None
@@ -193,7 +221,8 @@ def _sample_block(s3, mx, my, interp, border, border_value, out_dtype):
         # remapBicubic near the border: sum = cval; sum += (tap - cval) * w for
         # the taps that exist, in tap order
         h, w = s3.shape[:2]
-        edge = ~((ix - 1 >= 0) & (ix - 1 < max(w - 3, 0)) & (iy - 1 >= 0) & (iy - 1 < max(h - 3, 0)))
+        edge = ~((ix - off >= 0) & (ix - off < max(w - (k - 1), 0)) &
+                 (iy - off >= 0) & (iy - off < max(h - (k - 1), 0)))
         if edge.any():
             ey, ex = np.nonzero(edge)
             e_acc = np.full((ey.size, s3.shape[2]), fill, dtype=F32)
@@ -237,7 +266,7 @@ def sample_cv2(src: np.ndarray, map_x: np.ndarray, map_y: np.ndarray, interp: st
                border: str = "constant", border_value: float = 0.0) -> np.ndarray:
     import cv2
     flag = {"nearest": cv2.INTER_NEAREST, "linear": cv2.INTER_LINEAR,
-            "cubic": cv2.INTER_CUBIC}[interp]
+            "cubic": cv2.INTER_CUBIC, "lanczos4": cv2.INTER_LANCZOS4}[interp]
     mx = np.ascontiguousarray(map_x, dtype=F32)
     my = np.ascontiguousarray(map_y, dtype=F32)
     nch = 1 if src.ndim == 2 else src.shape[2]
@@ -245,7 +274,7 @@ def sample_cv2(src: np.ndarray, map_x: np.ndarray, map_y: np.ndarray, interp: st
     if border == "constant":
         return cv2.remap(src, mx, my, flag, borderMode=cv2.BORDER_CONSTANT, borderValue=bv)
     # panorama border: wrap columns, replicate rows, then no tap can leave the image
-    pad = 4
+    pad = 8
     h, w = src.shape[:2]
     padded = np.concatenate([src[:, w - pad:], src, src[:, :pad]], axis=1)
     padded = np.concatenate([padded[:1].repeat(pad, 0), padded, padded[-1:].repeat(pad, 0)], axis=0)

@@ -232,7 +232,8 @@ def dump_cv2():
     rng = np.random.default_rng(20261017)
     arrays = {}
     h, w, n = 40, 56, 48
-    flags = {"nearest": cv2.INTER_NEAREST, "linear": cv2.INTER_LINEAR, "cubic": cv2.INTER_CUBIC}
+    flags = {"nearest": cv2.INTER_NEAREST, "linear": cv2.INTER_LINEAR, "cubic": cv2.INTER_CUBIC,
+             "lanczos4": cv2.INTER_LANCZOS4}
     mx = (rng.random((n, n)) * (w + 8) - 4).astype(np.float32)
     my = (rng.random((n, n)) * (h + 8) - 4).astype(np.float32)
     # exact bin centres / boundaries and integer positions too

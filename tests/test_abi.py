@@ -93,6 +93,17 @@ def test_host_built_weight_tables_equal_the_oracles(lib):
     assert np.array_equal(fixed.reshape(32, 32, 4, 4), itab)
 
 
+def test_host_built_lanczos4_tables_equal_the_oracles(lib):
+    from oracle import sampler
+    fixed = np.zeros(32 * 32 * 64, np.int16)
+    one_d = np.zeros(32 * 8, np.float32)
+    assert lib.r360_debug_weight_tables_lanczos4(fixed.ctypes.data, one_d.ctypes.data) == 0
+    t1, _, itab = sampler.tables("lanczos4")
+    assert np.array_equal(one_d.reshape(32, 8), t1)
+    assert np.array_equal(fixed.reshape(32, 32, 8, 8), itab)
+    assert (fixed.reshape(1024, 64).astype(np.int64).sum(axis=1) == 32768).all()
+
+
 def test_python_api_refuses_cpu_tensors():
     torch = pytest.importorskip("torch")
     import remap360

@@ -162,7 +162,7 @@ def _lsb_stats(got, want):
 
 @pytest.mark.parametrize("path", ["direct", "tiled"])
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float16, np.float32])
-@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic"])
+@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic", "lanczos4"])
 @pytest.mark.parametrize("channels", [1, 3, 4])
 def test_erp_pixels_small_noise_all_types(r360, path, dtype, interp, channels):
     rng = np.random.default_rng(1234)
@@ -289,7 +289,7 @@ def _template_calib(r360, golden_df, fov=190.0):
 
 @pytest.mark.parametrize("path", ["direct", "tiled"])
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
-@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic"])
+@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic", "lanczos4"])
 def test_fisheye_pixels_with_invalid_fill(r360, path, dtype, interp, golden_df):
     """Scaled-down sensor so that sensor edges, the lens-FOV circle and fully invalid views all occur."""
     rng = np.random.default_rng(21)
@@ -421,7 +421,7 @@ def test_undistort_coordinates_against_oracle_and_reference_maps(r360, path, gol
 
 @pytest.mark.parametrize("path", ["direct", "tiled"])
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
-@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic"])
+@pytest.mark.parametrize("interp", ["nearest", "linear", "cubic", "lanczos4"])
 def test_undistort_pixels(r360, path, dtype, interp, golden_undistort):
     """Two lens images, three outputs (auto zoom, zoom < 1, a narrower lens FOV), mask fill on and off."""
     meta, _ = golden_undistort
