@@ -24,12 +24,20 @@ enum Interp : int { kNearest = 0, kLinear = 1, kCubic = 2, kLanczos4 = 3 };
 // A view is a linear map from output pixel indices to an (unnormalised) world ray:
 //   d(i, j) = c0 + i * ci + j * cj
 // with d = R * (tan(hfov/2) * ((2i+1)/w - 1), -tan(vfov/2) * ((2j+1)/h - 1), 1).
+//
+// kind == kRayFisheye (v360 `output=fisheye`, equidistant): the pixel's flat coordinates
+//   (u, v) = (f[0] * i + f[1], f[2] * j + f[3])      [= h_fov/180 * ((2i+1)/w - 1), v likewise]
+// give the angle from the view axis alpha = pi/2 * hypot(u, v) and the azimuth atan2(v, u); the
+// camera ray (sin(alpha) cos(phi), -sin(alpha) sin(phi), cos(alpha)) is rotated by the matrix
+// whose COLUMNS are c0, ci, cj.
+enum RayKind : int { kRayLinear = 0, kRayFisheye = 1 };
 struct ViewDev {
     double c0[3];
     double ci[3];
     double cj[3];
+    double f[4];
     int32_t slot;
-    int32_t pad;
+    int32_t kind;
 };
 
 struct ErpDev {          // x = (lon/2pi + 0.5) * su + ou ;  y = (0.5 - lat/pi) * sv + ov
@@ -81,6 +89,18 @@ struct CoordParams {
 
 // (fi, fj) may be fractional: the tile fitter samples between pixel centres.
 __device__ __forceinline__ void ray_at(const ViewDev& v, double fi, double fj, double& dx, double& dy, double& dz) {
+    if (v.kind == kRayFisheye) {
+        const double u = fma(fi, v.f[0], v.f[1]), w = fma(fj, v.f[2], v.f[3]);
+        const double r = sqrt(fma(u, u, w * w));
+        double sa, ca;
+        sincos(1.5707963267948966 * r, &sa, &ca);
+        const double k = r > 1e-12 ? sa / r : 1.5707963267948966;
+        const double cx = u * k, cy = -w * k;
+        dx = fma(cx, v.c0[0], fma(cy, v.ci[0], ca * v.cj[0]));
+        dy = fma(cx, v.c0[1], fma(cy, v.ci[1], ca * v.cj[1]));
+        dz = fma(cx, v.c0[2], fma(cy, v.ci[2], ca * v.cj[2]));
+        return;
+    }
     dx = fma(fi, v.ci[0], fma(fj, v.cj[0], v.c0[0]));
     dy = fma(fi, v.ci[1], fma(fj, v.cj[1], v.c0[1]));
     dz = fma(fi, v.ci[2], fma(fj, v.cj[2], v.c0[2]));

@@ -125,6 +125,18 @@ void make_view(const r360_view& v, int out_w, int out_h, ViewDev* o) {
             R[a][b] = 0;
             for (int k = 0; k < 3; ++k) R[a][b] += ry[a][k] * t[k][b];
         }
+    std::memset(o, 0, sizeof(*o));
+    o->slot = v.src_slot;
+    if (v.projection == R360_OUT_FISHEYE) {
+        // v360 output=fisheye: flat coordinates scaled by fov / 180 (prepare_fisheye_out), R's columns in c0/ci/cj
+        o->kind = kRayFisheye;
+        for (int a = 0; a < 3; ++a) { o->c0[a] = R[a][0]; o->ci[a] = R[a][1]; o->cj[a] = R[a][2]; }
+        const double su = std::fmin(std::fmax(v.hfov_deg, 1e-3), 360.0) / 180.0;
+        const double sv = std::fmin(std::fmax(v.vfov_deg, 1e-3), 360.0) / 180.0;
+        o->f[0] = su * 2.0 / out_w; o->f[1] = su * (1.0 / out_w - 1.0);
+        o->f[2] = sv * 2.0 / out_h; o->f[3] = sv * (1.0 / out_h - 1.0);
+        return;
+    }
     const double tx = std::tan(clamp_fov_rad(v.hfov_deg) * 0.5);
     const double ty = std::tan(clamp_fov_rad(v.vfov_deg) * 0.5);
     // camera ray (tx*u, -ty*vv, 1), u = (2i+1)/w - 1, vv = (2j+1)/h - 1
@@ -135,8 +147,6 @@ void make_view(const r360_view& v, int out_w, int out_h, ViewDev* o) {
         o->ci[a] = R[a][0] * (tx * du);
         o->cj[a] = -R[a][1] * (ty * dv);
     }
-    o->slot = v.src_slot;
-    o->pad = 0;
 }
 
 void make_erp(int W, int H, int convention, ErpDev* e) {
@@ -181,7 +191,11 @@ int make_undistort_view(const r360_undistort& u, const r360_fisheye_calib& c, Vi
 int build_persp_views(const r360_view* views, int n_views, int out_w, int out_h, std::vector<ViewDev>* out) {
     if (!views || n_views <= 0 || out_w <= 0 || out_h <= 0) return R360_E_INVALID_ARG;
     out->resize(n_views);
-    for (int v = 0; v < n_views; ++v) make_view(views[v], out_w, out_h, &(*out)[v]);
+    for (int v = 0; v < n_views; ++v) {
+        if (views[v].projection != R360_OUT_RECTILINEAR && views[v].projection != R360_OUT_FISHEYE)
+            return R360_E_INVALID_ARG;
+        make_view(views[v], out_w, out_h, &(*out)[v]);
+    }
     return R360_OK;
 }
 

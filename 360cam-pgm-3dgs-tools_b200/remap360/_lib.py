@@ -17,6 +17,7 @@ DTYPE_U8, DTYPE_U16, DTYPE_F16, DTYPE_F32 = 0, 1, 2, 3
 INTERP = {"nearest": 0, "linear": 1, "bilinear": 1, "cubic": 2, "bicubic": 2, "lanczos4": 3}
 CONVENTION = {"halfpixel": 0, "v360": 1}
 PATH = {"auto": 0, "direct": 1, "tiled": 2}
+OUT_PROJECTION = {"rectilinear": 0, "fisheye": 1}
 MAX_LENSES = 4
 
 
@@ -28,7 +29,7 @@ class Images(Structure):
 
 class View(Structure):
     _fields_ = [("yaw_deg", c_double), ("pitch_deg", c_double), ("roll_deg", c_double),
-                ("hfov_deg", c_double), ("vfov_deg", c_double), ("src_slot", c_int32), ("reserved", c_int32)]
+                ("hfov_deg", c_double), ("vfov_deg", c_double), ("src_slot", c_int32), ("projection", c_int32)]
 
 
 class FisheyeCalib(Structure):

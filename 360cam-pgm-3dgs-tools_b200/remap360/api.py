@@ -37,6 +37,16 @@ class PerspectiveView:
     roll_deg: float = 0.0
     src_slot: int = 0          # dual fisheye: 0 = X lens image, 1 = Y lens image
     view_id: str = ""
+    projection: str = "rectilinear"   # "fisheye": equidistant fisheye output, hfov/vfov as v360's
+                                      # h_fov/v_fov of `output=fisheye` (PC:375-379, preset fisheyeXY)
+
+
+def fisheye_fov_from_dfov(d_fov_deg: float, width: int, height: int) -> Tuple[float, float]:
+    """(h_fov, v_fov) that v360 derives from ``d_fov`` for ``output=fisheye`` [upstream FFmpeg
+    vf_v360.c fov_from_dfov, unverified here: no ffmpeg in this image]: the diagonal of the frame
+    spans d_fov on an equidistant projection, so each side spans its share of the half-diagonal."""
+    d = 0.5 * (float(width) ** 2 + float(height) ** 2) ** 0.5
+    return d / float(width) * float(d_fov_deg), d / float(height) * float(d_fov_deg)
 
 
 @dataclass(frozen=True)
@@ -97,8 +107,10 @@ def _describe(t: torch.Tensor, what: str) -> Images:
 def _views_array(views: Sequence[PerspectiveView]):
     arr = (View * len(views))()
     for k, v in enumerate(views):
+        if v.projection not in _lib.OUT_PROJECTION:
+            raise ValueError("unknown view projection %r" % (v.projection,))
         arr[k] = View(float(v.yaw_deg), float(v.pitch_deg), float(v.roll_deg), float(v.hfov_deg),
-                      float(v.vfov_deg), int(v.src_slot), 0)
+                      float(v.vfov_deg), int(v.src_slot), _lib.OUT_PROJECTION[v.projection])
     return arr
 
 
@@ -116,7 +128,7 @@ def _undistort_array(items: Sequence[UndistortItem]):
 def _view_key(v):
     if isinstance(v, UndistortItem):
         return ("undistort", v.zoom, v.src_slot)
-    return (v.yaw_deg, v.pitch_deg, v.roll_deg, v.hfov_deg, v.vfov_deg, v.src_slot)
+    return (v.yaw_deg, v.pitch_deg, v.roll_deg, v.hfov_deg, v.vfov_deg, v.src_slot, v.projection)
 
 
 def _calib_array(calibs: Sequence[FisheyeCalibration]):

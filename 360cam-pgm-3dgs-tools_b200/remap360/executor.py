@@ -78,6 +78,16 @@ _INTERP = {"cubic": "cubic", "linear": "linear", "nearest": "nearest", "near": "
 _gpu_lock = threading.Lock()
 
 
+def _job_view(job: "ParsedJob"):
+    """The device view of a parsed job.  ``output=fisheye`` jobs carry ``d_fov`` (PC:375-379); v360
+    turns it into per-axis FOVs before building its map."""
+    from . import api
+    if job.projection == "fisheye":
+        hfov, vfov = api.fisheye_fov_from_dfov(job.hfov, job.width, job.height)
+        return api.PerspectiveView(job.yaw, job.pitch, hfov, vfov, roll_deg=job.roll, projection="fisheye")
+    return api.PerspectiveView(job.yaw, job.pitch, job.hfov, job.vfov, roll_deg=job.roll)
+
+
 def _write_image(path: pathlib.Path, image, jpeg_quality: int) -> None:
     import cv2
     path.parent.mkdir(parents=True, exist_ok=True)
@@ -107,7 +117,7 @@ def _run_still_group(source: pathlib.Path, jobs: List[ParsedJob], stop_event) ->
     results: List[Optional[Tuple[int, str]]] = [None] * len(jobs)
     buckets: Dict[Tuple[int, int, str], List[int]] = OrderedDict()
     for k, job in enumerate(jobs):
-        if job.projection != "rectilinear":
+        if job.projection not in ("rectilinear", "fisheye"):
             results[k] = (1, "v360 output=%s is not available in the CUDA backend yet" % job.projection)
             continue
         if job.interp not in _INTERP:
@@ -120,8 +130,7 @@ def _run_still_group(source: pathlib.Path, jobs: List[ParsedJob], stop_event) ->
             for k in idxs:
                 results[k] = (130, "")
             continue
-        views = [api.PerspectiveView(jobs[k].yaw, jobs[k].pitch, jobs[k].hfov, jobs[k].vfov, roll_deg=jobs[k].roll)
-                 for k in idxs]
+        views = [_job_view(jobs[k]) for k in idxs]
         try:
             with _gpu_lock:
                 if host.dtype == np.uint16:

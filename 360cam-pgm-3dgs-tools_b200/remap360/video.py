@@ -39,13 +39,13 @@ def run_video_jobs(source, jobs: Sequence, stop_event=None) -> List[Tuple[int, s
     import numpy as np
     import torch
     from . import api
-    from .executor import _INTERP, _write_image
+    from .executor import _INTERP, _job_view, _write_image
     from .stream import StreamingRemapper
 
     results: List[Optional[Tuple[int, str]]] = [None] * len(jobs)
     usable = []
     for k, job in enumerate(jobs):
-        if job.projection != "rectilinear":
+        if job.projection not in ("rectilinear", "fisheye"):
             results[k] = (1, "v360 output=%s is not available in the CUDA backend yet" % job.projection)
         elif job.interp not in _INTERP:
             results[k] = (1, "interp=%s is not available in the CUDA backend" % job.interp)
@@ -61,8 +61,7 @@ def run_video_jobs(source, jobs: Sequence, stop_event=None) -> List[Tuple[int, s
             first = jobs[usable[0]]
             wanted = _select_frames(n_in, in_fps, float(first.fps), first.start, first.end)
             size = (first.width, first.height)
-            views = [api.PerspectiveView(jobs[k].yaw, jobs[k].pitch, jobs[k].hfov, jobs[k].vfov, roll_deg=jobs[k].roll)
-                     for k in usable]
+            views = [_job_view(jobs[k]) for k in usable]
             ok, frame = cap.read()
             if not ok:
                 return [(1, "no frames in %s" % source)] * len(jobs)

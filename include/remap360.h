@@ -43,6 +43,9 @@ enum {
 /* ---- enums --------------------------------------------------------------------------- */
 enum { R360_U8 = 0, R360_U16 = 1, R360_F16 = 2, R360_F32 = 3 };
 
+/* What an output view is (r360_view.projection). */
+enum { R360_OUT_RECTILINEAR = 0, R360_OUT_FISHEYE = 1 };
+
 /* cv2 names at gs360_DualFisheyeDistortionCalibration.py:59-64; ffmpeg `interp=` at
  * gs360_360PerspCut.py:107-109.  Arithmetic is cv2.remap's (1/32-px fractions, A = -0.75). */
 enum { R360_NEAREST = 0, R360_LINEAR = 1, R360_CUBIC = 2, R360_LANCZOS4 = 3 };
@@ -88,7 +91,9 @@ typedef struct r360_view {
     double  vfov_deg;
     int32_t src_slot;        /* which image of a source group feeds this view (ERP: 0;
                                 dual fisheye: 0 = X lens, 1 = Y lens)                        */
-    int32_t reserved;
+    int32_t projection;      /* R360_OUT_RECTILINEAR (0) or R360_OUT_FISHEYE: the view is an
+                                equidistant fisheye image, hfov/vfov being v360's h_fov / v_fov of
+                                `output=fisheye` (gs360_360PerspCut.py:375-379, preset fisheyeXY) */
 } r360_view;
 
 /* Metashape equisolid-fisheye calibration, the fields of SensorCalibration

@@ -51,17 +51,41 @@ def _clamped_fov_rad(fov_deg: float) -> float:
     return math.radians(min(max(float(fov_deg), 1e-3), 179.9))
 
 
+def fisheye_fov_from_dfov(d_fov_deg: float, width: int, height: int) -> Tuple[float, float]:
+    """v360's (h_fov, v_fov) for ``output=fisheye:d_fov=...`` [upstream FFmpeg vf_v360.c
+    ``fov_from_dfov``; not verifiable here -- no ffmpeg binary in the image]."""
+    d = 0.5 * math.hypot(width, height)
+    return d / width * d_fov_deg, d / height * d_fov_deg
+
+
 def camera_rays(out_w: int, out_h: int, hfov_deg: float, vfov_deg: float,
-                yaw_deg: float, pitch_deg: float, roll_deg: float = 0.0) -> np.ndarray:
-    """Unit rays (h, w, 3), y up, after the view rotation (float64)."""
+                yaw_deg: float, pitch_deg: float, roll_deg: float = 0.0,
+                projection: str = "rectilinear") -> np.ndarray:
+    """Unit rays (h, w, 3), y up, after the view rotation (float64).
+
+    ``projection="fisheye"`` is v360's ``output=fisheye`` (gs360_360PerspCut.py:375-379, preset
+    fisheyeXY) [upstream ``fisheye_to_xyz``, unverified here]: flat coordinates
+    (h_fov/180 * u, v_fov/180 * v), angle from the view axis = 90 degrees x their length
+    (equidistant), azimuth = their direction."""
     u = ((np.arange(out_w, dtype=np.float64) + 0.5) / float(out_w)) * 2.0 - 1.0
     v = ((np.arange(out_h, dtype=np.float64) + 0.5) / float(out_h)) * 2.0 - 1.0
     uu, vv = np.meshgrid(u, v)
     rays = np.empty((out_h, out_w, 3), dtype=np.float64)
-    rays[..., 0] = math.tan(_clamped_fov_rad(hfov_deg) * 0.5) * uu
-    rays[..., 1] = math.tan(_clamped_fov_rad(vfov_deg) * 0.5) * (-vv)
-    rays[..., 2] = 1.0
-    rays /= np.linalg.norm(rays, axis=2, keepdims=True)
+    if projection == "fisheye":
+        fu = min(max(float(hfov_deg), 1e-3), 360.0) / 180.0 * uu
+        fv = min(max(float(vfov_deg), 1e-3), 360.0) / 180.0 * vv
+        alpha = 0.5 * math.pi * np.hypot(fu, fv)
+        phi = np.arctan2(fv, fu)
+        rays[..., 0] = np.sin(alpha) * np.cos(phi)
+        rays[..., 1] = -np.sin(alpha) * np.sin(phi)
+        rays[..., 2] = np.cos(alpha)
+    elif projection == "rectilinear":
+        rays[..., 0] = math.tan(_clamped_fov_rad(hfov_deg) * 0.5) * uu
+        rays[..., 1] = math.tan(_clamped_fov_rad(vfov_deg) * 0.5) * (-vv)
+        rays[..., 2] = 1.0
+        rays /= np.linalg.norm(rays, axis=2, keepdims=True)
+    else:
+        raise ValueError("unknown projection: %r" % (projection,))
     if roll_deg:
         rays = rays @ view_rotation(0.0, 0.0, roll_deg).T
     # pitch then yaw, written out as in gs360_GUI.py:351-374 / DF:1310-1339
@@ -77,14 +101,14 @@ def camera_rays(out_w: int, out_h: int, hfov_deg: float, vfov_deg: float,
 
 def erp_map64(src_w: int, src_h: int, out_w: int, out_h: int,
               yaw_deg: float, pitch_deg: float, hfov_deg: float, vfov_deg: float,
-              convention: str = "halfpixel", roll_deg: float = 0.0
+              convention: str = "halfpixel", roll_deg: float = 0.0, projection: str = "rectilinear"
               ) -> Tuple[np.ndarray, np.ndarray]:
     """Source pixel position (x, y) in an ERP of size src_w x src_h for every
     output pixel.  x is NOT wrapped into [0, W): it lies in [-0.5, W - 0.5) for
     ``halfpixel`` and [0, W - 1] for ``v360``; the sampler wraps taps."""
     if convention not in CONVENTIONS:
         raise ValueError("unknown convention: %r" % (convention,))
-    rays = camera_rays(out_w, out_h, hfov_deg, vfov_deg, yaw_deg, pitch_deg, roll_deg)
+    rays = camera_rays(out_w, out_h, hfov_deg, vfov_deg, yaw_deg, pitch_deg, roll_deg, projection)
     lon = np.arctan2(rays[..., 0], rays[..., 2])
     lat = np.arcsin(np.clip(rays[..., 1], -1.0, 1.0))
     if convention == "halfpixel":

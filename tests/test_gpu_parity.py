@@ -477,3 +477,32 @@ def test_undistort_argument_errors(r360):
         r360.undistort_fisheye(dev, [good], [r360.UndistortItem(1.0, 3)], path="direct")
     with pytest.raises(r360.Remap360Error):
         r360.undistort_fisheye(dev, [good], [])
+
+
+# ------------------------------------------------------------------------------------------
+# panorama -> equidistant fisheye views (v360 output=fisheye; preset fisheyeXY, PC:871-887)
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("path", ["direct", "tiled"])
+def test_fisheye_output_coordinates_and_pixels(r360, path):
+    rng = np.random.default_rng(31)
+    W, H, size = 2048, 1024, 360
+    src = _noise(rng, (H, W, 3), np.uint8)
+    hf, vf = geo.fisheye_fov_from_dfov(180.0, size, size)
+    assert r360.api.fisheye_fov_from_dfov(180.0, size, size) == (hf, vf)
+    specs = [(0.0, 0.0), (180.0, 0.0), (40.0, -25.0)]
+    views = [r360.PerspectiveView(y, p, hf, vf, projection="fisheye") for y, p in specs]
+    views.append(r360.PerspectiveView(10.0, 5.0, 100.0, 100.0))              # mixed with a rectilinear view
+    got = r360.sample_coordinates(views, (size, size), erp_size=(W, H), path=path)
+    out = _to_numpy(r360.remap_erp(_to_cuda(src)[None], views, (size, size), interp="cubic", path=path))[0]
+    for k, v in enumerate(views):
+        mx, my = geo.erp_map64(W, H, size, size, v.yaw_deg, v.pitch_deg, v.hfov_deg, v.vfov_deg,
+                               projection=v.projection)
+        dx = np.abs(got["x64"][k].cpu().numpy() - mx)
+        dx = np.minimum(dx, np.abs(dx - W))                                   # same point across the seam
+        assert dx.max() <= 2e-5 and np.abs(got["y64"][k].cpu().numpy() - my).max() <= 2e-5, (k, dx.max())
+        want = sampler.sample(src, mx, my, "cubic", "erp")
+        exact, within1, worst = _lsb_stats(out[k], want)
+        assert within1 >= PIXEL_OK_FRACTION and exact >= 0.999, (k, exact, within1, worst)
+    with pytest.raises(ValueError):
+        r360.remap_erp(_to_cuda(src)[None], [r360.PerspectiveView(0, 0, 90, 90, projection="cube")], (8, 8))

@@ -51,6 +51,33 @@ def test_run_jobs_writes_every_view_of_a_still(r360, tmp_path):
     assert rc == 1 and "failed to read" in err
 
 
+def test_fisheye_xy_preset_jobs_run(r360, tmp_path):
+    """Preset fisheyeXY: two `output=fisheye:d_fov=180` jobs per panorama (PC:871-887)."""
+    cv2 = pytest.importorskip("cv2")
+    from remap360 import executor, perspcut as pc
+    rng = np.random.default_rng(6)
+    src = rng.integers(0, 256, (256, 512, 3), dtype=np.uint8)
+    (tmp_path / "in").mkdir()
+    cv2.imwrite(str(tmp_path / "in" / "pano0001.png"), src)
+    args = pc.create_arg_parser().parse_args(["-i", str(tmp_path / "in"), "--preset", "fisheyeXY", "--ext", "png"])
+    args.size_explicit = args.hfov_explicit = args.focal_mm_explicit = False
+    args.input_is_video, args.video_bit_depth = False, 8
+    res = pc.build_view_jobs(args, [tmp_path / "in" / "pano0001.png"], tmp_path / "out")
+    jobs = []
+    for argv, src_name, dst_name in res.jobs:                    # shrink the 3600 px outputs for the test
+        argv = [a.replace("w=3600:h=3600", "w=120:h=120") for a in argv]
+        jobs.append((argv, src_name, dst_name))
+    done = list(executor.run_jobs(jobs, pc.stop_event, workers=1))
+    assert len(done) == 2 and all(rc == 0 for _job, (rc, _err) in done), done
+    hf, vf = geo.fisheye_fov_from_dfov(180.0, 120, 120)
+    for spec in res.view_specs:
+        got = cv2.imread(str(tmp_path / "out" / spec.output_name), cv2.IMREAD_UNCHANGED)
+        mx, my = geo.erp_map64(512, 256, 120, 120, spec.yaw_deg, spec.pitch_deg, hf, vf, projection="fisheye")
+        want = sampler.sample(src, mx, my, "cubic", "erp")
+        assert got.shape == want.shape
+        assert (np.abs(got.astype(int) - want.astype(int)) <= 1).mean() >= 0.999
+
+
 def test_dualfisheye_stage_matches_reference_lens_choice_and_oracle(r360, golden_df):
     from remap360 import dualfisheye as dfh
     cal = golden_df["sensors"]["0"]

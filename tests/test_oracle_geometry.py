@@ -172,3 +172,30 @@ def test_undistort_rejects_degenerate_focal():
     with pytest.raises(ValueError):
         g.undistort_map64(dict(width=8, height=8, f=0.0, cx=0, cy=0, k1=0, k2=0, k3=0, k4=0, p1=0, p2=0, b1=0, b2=0),
                           1.0, 190.0)
+
+
+# --- v360 output=fisheye (preset fisheyeXY, PC:375-379) -------------------------------------------
+
+def test_fisheye_output_is_equidistant_about_the_view_axis():
+    w = h = 101
+    hf, vf = g.fisheye_fov_from_dfov(180.0, w, h)
+    assert abs(hf - 180.0 / math.sqrt(2.0)) < 1e-9 and hf == vf
+    rays = g.camera_rays(w, h, hf, vf, 0.0, 0.0, projection="fisheye")
+    assert np.allclose(np.linalg.norm(rays, axis=2), 1.0)
+    c = w // 2
+    assert np.allclose(rays[c, c], (0.0, 0.0, 1.0), atol=1e-12)
+    # angle from the axis grows linearly with the distance from the centre: edge centre = h_fov / 2,
+    # corner pixel centres = d_fov / 2 scaled by (w - 1) / w
+    ang = np.degrees(np.arccos(np.clip(rays[..., 2], -1, 1)))
+    assert abs(ang[c, w - 1] - hf / 2 * (w - 1) / w) < 1e-9
+    assert abs(ang[0, 0] - 90.0 * (w - 1) / w) < 1e-9
+    k = np.arange(c, w)
+    assert np.allclose(np.diff(ang[c, k]), hf / w, atol=1e-9)
+    # +u looks right, +v (down in the image) looks down
+    assert rays[c, w - 1, 0] > 0 and rays[h - 1, c, 1] < 0
+    # yaw / pitch move the axis exactly as for rectilinear views
+    r2 = g.camera_rays(w, h, hf, vf, 90.0, 30.0, projection="fisheye")
+    r1 = g.camera_rays(3, 3, 10.0, 10.0, 90.0, 30.0)
+    assert np.allclose(r2[c, c], r1[1, 1], atol=1e-12)
+    with pytest.raises(ValueError):
+        g.camera_rays(4, 4, 90, 90, 0, 0, projection="nope")
