@@ -78,6 +78,27 @@ def main():
         rows.append({"case": "cfg5 dual fisheye u8 %s, 8 pairs x 10 views 1750^2" % interp, "ms": ms,
                      "fallback_tiles": plan.n_fallback, "tiles": plan.tiles_per_view * plan.n_views,
                      "Mpix_per_s": 8 * 10 * 1750 * 1750 / ms / 1e3, "pairs_per_s": 8 / ms * 1e3, "interp": interp})
+    # a12: both lenses 3840^2 -> undistorted 3840^2 (same template calibration)
+    items = [remap360.UndistortItem(1.0, 0), remap360.UndistortItem(1.0, 1)]
+    out_u = torch.empty((8, 2, 3840, 3840, 3), dtype=torch.uint8, device=dev)
+    for interp in ("cubic", "linear"):
+        ms = timeit(lambda: remap360.undistort_fisheye(pairs, [calib, calib], items, interp=interp, out=out_u))
+        plan = list(api._PLAN_CACHE.values())[-1]
+        rows.append({"case": "a12 undistort u8 %s, 8 pairs x 2 lenses 3840^2" % interp, "ms": ms,
+                     "fallback_tiles": plan.n_fallback, "tiles": plan.tiles_per_view * plan.n_views,
+                     "Mpix_per_s": 8 * 2 * 3840 * 3840 / ms / 1e3, "pairs_per_s": 8 / ms * 1e3, "interp": interp})
+    del pairs, out, out_u
+    torch.cuda.empty_cache()
+    erp_case("cfg2 u8 lanczos4 (generic sampler on the staged patch)", "full360coverage", torch.uint8, "lanczos4", 2)
+    # preset fisheyeXY: 2 equidistant fisheye views 3600^2, d_fov 180
+    hf, vf = remap360.api.fisheye_fov_from_dfov(180.0, 3600, 3600)
+    fviews = [remap360.PerspectiveView(y, 0.0, hf, vf, projection="fisheye") for y in (0.0, 180.0)]
+    src = torch.randint(0, 256, (8, H, W, 3), dtype=torch.uint8, device=dev)
+    out_f = torch.empty((8, 2, 3600, 3600, 3), dtype=torch.uint8, device=dev)
+    ms = timeit(lambda: remap360.remap_erp(src, fviews, (3600, 3600), interp="cubic", out=out_f))
+    plan = list(api._PLAN_CACHE.values())[-1]
+    rows.append({"case": "fisheyeXY u8 cubic, 8 frames x 2 views 3600^2", "ms": ms, "fallback_tiles": plan.n_fallback,
+                 "tiles": plan.tiles_per_view * plan.n_views, "Mpix_per_s": 8 * 2 * 3600 * 3600 / ms / 1e3})
     for r in rows:
         print(json.dumps(r))
 
