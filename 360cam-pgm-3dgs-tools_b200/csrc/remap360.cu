@@ -16,6 +16,7 @@
 #include "r360_common.cuh"
 #include "r360_direct.cuh"
 #include "r360_tiled.cuh"
+#include "r360_color.cuh"
 
 using namespace r360;
 
@@ -720,6 +721,44 @@ int r360_remap_undistort(const r360_images* src, const r360_images* dst, const r
     std::vector<ViewDev> vd;
     const int rc = build_undistort_views(items, n_items, calib, n_lenses, &vd);
     return rc != R360_OK ? rc : remap_direct(kProjUndistort, src, dst, calib, n_lenses, vd, opt, stream);
+}
+
+int r360_apply_lut(const r360_images* src, const r360_images* dst, const r360_lut3d* lut,
+                   int32_t output_space, int32_t channel_order, void* stream) {
+    int rc;
+    if ((rc = check_images(src)) != R360_OK) return rc;
+    if ((rc = check_images(dst)) != R360_OK) return rc;
+    if (!lut || !lut->table_device || lut->size < 2 || lut->size > 256) return R360_E_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(lut->table_device) % 16) return R360_E_INVALID_ARG;
+    if (output_space != R360_LUT_PASSTHROUGH && output_space != R360_LUT_SRGB) return R360_E_INVALID_ARG;
+    if (channel_order != R360_ORDER_BGR && channel_order != R360_ORDER_RGB) return R360_E_INVALID_ARG;
+    if (src->channels < 3) return R360_E_INVALID_ARG;                      // DF:693-697
+    if (src->width != dst->width || src->height != dst->height || src->channels != dst->channels ||
+        src->dtype != dst->dtype || src->count != dst->count)
+        return R360_E_INVALID_ARG;
+    if (src->dtype == R360_F16) return R360_E_UNSUPPORTED;
+    if (src->height > 65535 || src->count > 65535) return R360_E_INVALID_ARG;
+    LutParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
+    p.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
+    p.channels = src->channels; p.n_images = src->count; p.size = lut->size;
+    p.to_srgb = output_space == R360_LUT_SRGB; p.rgb_order = channel_order == R360_ORDER_RGB;
+    for (int c = 0; c < 3; ++c) {
+        p.dmin[c] = lut->domain_min[c];
+        p.span[c] = lut->domain_max[c] - lut->domain_min[c];                 // float32 subtraction, as DF:640
+        if (!(p.span[c] > 0.0f)) return R360_E_INVALID_ARG;                 // DF:556-558
+    }
+    p.table = reinterpret_cast<const float4*>(lut->table_device);
+    if ((rc = ensure_device_ready()) != R360_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const dim3 grid((src->width + 255) / 256, src->height, src->count);
+    if (src->dtype == R360_U8) lut_kernel<uint8_t><<<grid, 256, 0, s>>>(p);
+    else if (src->dtype == R360_U16) lut_kernel<uint16_t><<<grid, 256, 0, s>>>(p);
+    else lut_kernel<float><<<grid, 256, 0, s>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    R360_CUDA(cudaGetLastError());
+    return R360_OK;
 }
 
 int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, int32_t n_lenses,

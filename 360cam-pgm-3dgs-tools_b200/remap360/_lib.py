@@ -41,6 +41,11 @@ class Undistort(Structure):
     _fields_ = [("zoom", c_double), ("src_slot", c_int32), ("reserved", c_int32)]
 
 
+class Lut3D(Structure):
+    _fields_ = [("table_device", c_void_p), ("size", c_int32), ("reserved", c_int32),
+                ("domain_min", c_float * 3), ("domain_max", c_float * 3)]
+
+
 class Options(Structure):
     _fields_ = [("interp", c_int32), ("convention", c_int32), ("path", c_int32), ("fill_invalid", c_int32),
                 ("border_value", c_double), ("out_dtype", c_int32), ("reserved", c_int32)]
@@ -59,7 +64,7 @@ EXPORTS = ("r360_abi_version", "r360_error_string", "r360_last_cuda_error", "r36
            "r360_device_info", "r360_remap_erp", "r360_remap_fisheye", "r360_coords", "r360_launch_count",
            "r360_plan_workspace_bytes", "r360_plan_create_erp", "r360_plan_create_fisheye", "r360_plan_info",
            "r360_remap_planned", "r360_plan_coords", "r360_plan_destroy",
-           "r360_remap_undistort", "r360_coords_undistort", "r360_plan_create_undistort")
+           "r360_remap_undistort", "r360_coords_undistort", "r360_plan_create_undistort", "r360_apply_lut")
 
 
 def load() -> ctypes.CDLL:
@@ -101,6 +106,7 @@ def load() -> ctypes.CDLL:
     lib.r360_plan_create_undistort.argtypes = [POINTER(Images), POINTER(Images), POINTER(FisheyeCalib), c_int32,
                                                POINTER(Undistort), c_int32, POINTER(Options), c_void_p,
                                                ctypes.c_size_t, c_void_p, POINTER(c_void_p)]
+    lib.r360_apply_lut.argtypes = [POINTER(Images), POINTER(Images), POINTER(Lut3D), c_int32, c_int32, c_void_p]
     lib.r360_plan_info.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32)]
     lib.r360_remap_planned.argtypes = [c_void_p, POINTER(Images), POINTER(Images), c_void_p]
     lib.r360_plan_coords.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

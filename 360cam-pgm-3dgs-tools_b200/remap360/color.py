@@ -1,0 +1,121 @@
+"""Input colour pipeline of the dual-fisheye stage on the GPU: ``.cube`` 3-D LUT (trilinear) and the
+optional Rec.709 -> sRGB re-encoding that the reference applies to every lens image right after
+reading it (cli_tools/gs360_DualFisheyeDistortionCalibration.py:494-725; GUI default
+``use_input_lut=True``).  The file parser runs on the host; the per-pixel work is the
+``r360_apply_lut`` kernel."""
+
+from __future__ import annotations
+
+import ctypes
+import pathlib
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .api import _describe, _stream_handle
+
+OUTPUT_SPACES = {"passthrough": 0, "srgb": 1}
+
+
+def normalize_lut_output_color_space(value) -> str:
+    """DF:481-491 (``native`` is a legacy alias of ``passthrough``)."""
+    text = str(value or "passthrough").strip().lower()
+    if text == "native":
+        return "passthrough"
+    if text in OUTPUT_SPACES:
+        return text
+    raise ValueError("Unsupported --lut-output-color-space: {}".format(value))
+
+
+@dataclass
+class CubeLUT:
+    """DF:99-105, plus the device copy the kernel reads (float4 per node, red fastest)."""
+    size: int
+    table: "object"                       # numpy float32 [size, size, size, 3], indexed [b, g, r]
+    domain_min: Tuple[float, float, float]
+    domain_max: Tuple[float, float, float]
+    _device: Optional[torch.Tensor] = None
+
+    def device_table(self, device) -> torch.Tensor:
+        device = torch.device(device)
+        if self._device is None or self._device.device != device:
+            nodes = torch.from_numpy(self.table).reshape(-1, 3)
+            padded = torch.zeros((nodes.shape[0], 4), dtype=torch.float32)
+            padded[:, :3] = nodes
+            self._device = padded.to(device)
+        return self._device
+
+
+def load_cube_lut(lut_path) -> CubeLUT:
+    """Parse a ``.cube`` file the way DF:494-565 does: TITLE / comments skipped, LUT_3D_SIZE,
+    DOMAIN_MIN / DOMAIN_MAX, then size^3 rows of three floats; same error messages."""
+    import numpy as np
+    lut_path = pathlib.Path(lut_path)
+    if not lut_path.is_file():
+        raise FileNotFoundError("LUT file not found: {}".format(lut_path))
+    size, lo, hi, rows = None, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0], []
+    with lut_path.open("r", encoding="utf-8", errors="ignore") as fh:
+        for raw in fh:
+            line = raw.strip()
+            if not line or line.startswith("#"):
+                continue
+            key = line.upper()
+            parts = line.split()
+            if key.startswith("TITLE"):
+                continue
+            if key.startswith("LUT_3D_SIZE"):
+                if len(parts) < 2:
+                    raise ValueError("Invalid LUT_3D_SIZE line: {}".format(line))
+                size = int(parts[1])
+            elif key.startswith("DOMAIN_MIN") or key.startswith("DOMAIN_MAX"):
+                if len(parts) != 4:
+                    raise ValueError("Invalid {} line: {}".format(key[:10], line))
+                (lo if key.startswith("DOMAIN_MIN") else hi)[:] = [float(t) for t in parts[1:]]
+            elif len(parts) == 3:
+                rows.append((float(parts[0]), float(parts[1]), float(parts[2])))
+    if size is None:
+        raise ValueError("LUT_3D_SIZE is missing in {}".format(lut_path))
+    if size <= 1:
+        raise ValueError("LUT_3D_SIZE must be > 1 in {}".format(lut_path))
+    if len(rows) != size ** 3:
+        raise ValueError("LUT row count mismatch in {}: got {}, expected {}".format(lut_path, len(rows), size ** 3))
+    dmin, dmax = np.asarray(lo, dtype=np.float32), np.asarray(hi, dtype=np.float32)
+    if np.any(dmax - dmin <= 0.0):
+        raise ValueError("Invalid LUT domain range in {}".format(lut_path))
+    table = np.asarray(rows, dtype=np.float32).reshape((size, size, size, 3))
+    return CubeLUT(size=size, table=table, domain_min=tuple(float(v) for v in dmin),
+                   domain_max=tuple(float(v) for v in dmax))
+
+
+def apply_input_color_pipeline(images: torch.Tensor, lut: Optional[CubeLUT], lut_output_color_space: str = "srgb",
+                               *, channel_order: str = "bgr", out: Optional[torch.Tensor] = None,
+                               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """[N, H, W, C] (or [..., H, W, C]) uint8 / uint16 / float32 CUDA images -> same shape and dtype.
+    ``lut is None`` returns the input untouched, like DF:691-692.  ``out`` may alias ``images``."""
+    if lut is None:
+        return images
+    space = normalize_lut_output_color_space(lut_output_color_space)
+    if channel_order not in ("bgr", "rgb"):
+        raise ValueError("channel_order must be 'bgr' or 'rgb'")
+    if images.dim() < 3 or images.shape[-1] < 3:
+        raise ValueError("LUT-based input conversion requires at least 3-channel RGB image input")
+    if not images.is_contiguous():
+        raise ValueError("images must be contiguous")
+    flat = images.reshape((-1,) + tuple(images.shape[-3:]))
+    if out is None:
+        out = torch.empty_like(images)
+    elif out.shape != images.shape or out.dtype != images.dtype or not out.is_contiguous():
+        raise ValueError("out must match images")
+    src, dst = _describe(flat, "images"), _describe(out.reshape(flat.shape), "out")
+    table = lut.device_table(images.device)
+    desc = _lib.Lut3D(table.data_ptr(), int(lut.size), 0, (ctypes.c_float * 3)(*lut.domain_min),
+                      (ctypes.c_float * 3)(*lut.domain_max))
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.load().r360_apply_lut(ctypes.byref(src), ctypes.byref(dst), ctypes.byref(desc),
+                                              OUTPUT_SPACES[space], 1 if channel_order == "rgb" else 0,
+                                              _stream_handle(stream, images.device)))
+    if stream is not None:
+        table.record_stream(stream)
+    return out

@@ -188,6 +188,34 @@ int r360_remap_undistort(const r360_images* src, const r360_images* dst,
                          const r360_options* opt, void* stream);
 
 /*
+ * Input colour pipeline of the dual-fisheye tool: .cube 3-D LUT (trilinear, RGB) followed by an
+ * optional Rec.709 -> linear -> sRGB re-encoding, applied to every lens image before the remap
+ * when --input-lut / --input-color-profile osmo360-dlogm is set.  Replaces
+ * apply_input_color_pipeline (gs360_DualFisheyeDistortionCalibration.py:684-725: image_to_float01
+ * :599-609, apply_cube_lut_trilinear :625-681, rec709_to_srgb :568-596, float01_to_image :612-622).
+ * float32 arithmetic in the reference's operation order; src and dst may be the same images.
+ *
+ *   table_device   size^3 nodes of 4 floats (R, G, B, unused), node (r, g, b) at index
+ *                  (b * size + g) * size + r -- the order of a .cube file (red fastest);
+ *   output_space   R360_LUT_PASSTHROUGH: clip to [0, 1]; R360_LUT_SRGB: rec709_to_srgb;
+ *   channel_order  R360_ORDER_BGR (what cv2.imread returns; the reference flips it, DF:700-701)
+ *                  or R360_ORDER_RGB;  channels beyond the first three are copied through.
+ *   U8, U16 and F32 images; src and dst layouts must agree.
+ */
+enum { R360_LUT_PASSTHROUGH = 0, R360_LUT_SRGB = 1 };
+enum { R360_ORDER_BGR = 0, R360_ORDER_RGB = 1 };
+typedef struct r360_lut3d {
+    const float* table_device;
+    int32_t size;
+    int32_t reserved;
+    float   domain_min[3];
+    float   domain_max[3];
+} r360_lut3d;
+
+int r360_apply_lut(const r360_images* src, const r360_images* dst, const r360_lut3d* lut,
+                   int32_t output_space, int32_t channel_order, void* stream);
+
+/*
  * Test/debug: the source coordinates the kernels sample at, without sampling.  Writes, for
  * view v and output pixel (j, i), element [(v * out_h + j) * out_w + i] of each non-null
  * device array:

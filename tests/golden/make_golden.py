@@ -27,6 +27,9 @@ undistort.json          fisheye -> undistorted fisheye (DF:1008-1170): the auto 
 undistort_maps.npz      ``estimate_auto_undistort_zoom`` and strided ``build_remap_cache`` maps
                         + validity for the template calibration (auto and fixed zoom) and
                         the synthetic one; a small full-resolution case for cv2 parity
+color_pipeline.npz      ``apply_input_color_pipeline`` (DF:684-725) on random uint8 / uint16 / 4-channel
+                        images with two synthetic .cube LUTs (size 5 with a shifted domain, size 17),
+                        passthrough and srgb; also the LUT text files as parsed by ``load_cube_lut``
 cv2_remap.npz           ``cv2.remap`` outputs (the routine the reference calls,
                         DF:2001-2008) for small random sources x dtypes x
                         interpolations x borders
@@ -227,6 +230,49 @@ def dump_undistort(df):
     (HERE / "undistort.json").write_text(json.dumps(meta, indent=1, sort_keys=True) + "\n")
 
 
+def _write_cube(path, size, rng, domain=None, title=True):
+    lines = []
+    if title:
+        lines += ['TITLE "synthetic %d"' % size, "# generated by tests/golden/make_golden.py"]
+    lines.append("LUT_3D_SIZE %d" % size)
+    if domain is not None:
+        lines.append("DOMAIN_MIN %g %g %g" % tuple(domain[0]))
+        lines.append("DOMAIN_MAX %g %g %g" % tuple(domain[1]))
+    grid = np.linspace(0.0, 1.0, size)
+    for b in grid:
+        for g in grid:
+            for r in grid:                                    # red fastest, like every .cube file
+                v = np.array([r ** 0.8 + 0.05 * g, 0.9 * g + 0.1 * b * b, b ** 1.3 - 0.04 * r]) + rng.normal(0, 0.01, 3)
+                lines.append("%.6f %.6f %.6f" % tuple(v))
+    path.write_text("\n".join(lines) + "\n")
+
+
+def dump_color(df):
+    import tempfile
+    rng = np.random.default_rng(4242)
+    arrays = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = pathlib.Path(tmp)
+        luts = {"s5": (5, ((-0.05, 0.0, 0.02), (1.1, 0.95, 1.0))), "s17": (17, None)}
+        for name, (size, domain) in luts.items():
+            _write_cube(tmp / (name + ".cube"), size, rng, domain)
+            arrays["cube_%s_text" % name] = np.array((tmp / (name + ".cube")).read_text())
+            lut = df.load_cube_lut(tmp / (name + ".cube"))
+            arrays["cube_%s_table" % name] = lut.table
+            arrays["cube_%s_min" % name], arrays["cube_%s_max" % name] = lut.domain_min, lut.domain_max
+            for dt, ch in (("uint8", 3), ("uint16", 3), ("uint8", 4)):
+                img = rng.integers(0, np.iinfo(dt).max + 1, (48, 64, ch)).astype(dt)
+                if dt == "uint8" and ch == 3:                 # every code value of one channel, and the knees
+                    img[0, :, :] = np.arange(64)[:, None] * 4
+                    img[1, :, 0] = np.arange(64) * 4 + 3
+                arrays["img_%s_c%d_%s" % (dt, ch, name)] = img
+                for space in ("passthrough", "srgb"):
+                    arrays["out_%s_c%d_%s_%s" % (dt, ch, name, space)] = df.apply_input_color_pipeline(img, lut, space)
+    v = np.linspace(0, 1, 4097).astype(np.float32)
+    arrays["rec709_to_srgb_in"], arrays["rec709_to_srgb_out"] = v, df.rec709_to_srgb(v)
+    np.savez_compressed(HERE / "color_pipeline.npz", **arrays)
+
+
 def dump_cv2():
     import cv2
     rng = np.random.default_rng(20261017)
@@ -270,6 +316,7 @@ def main():
     dump_perspcut(pc)
     dump_dualfisheye(df)
     dump_undistort(df)
+    dump_color(df)
     dump_cv2()
     for p in sorted(HERE.glob("*.json")) + sorted(HERE.glob("*.npz")):
         print("%9d  %s" % (p.stat().st_size, p.name))
