@@ -30,6 +30,11 @@ undistort_maps.npz      ``estimate_auto_undistort_zoom`` and strided ``build_rem
 color_pipeline.npz      ``apply_input_color_pipeline`` (DF:684-725) on random uint8 / uint16 / 4-channel
                         images with two synthetic .cube LUTs (size 5 with a shifted domain, size 17),
                         passthrough and srgb; also the LUT text files as parsed by ``load_cube_lut``
+df_cli.json             the DualFisheye CLI (DF:124-449, :2067-2853): every argparse action of
+df_cli_outputs.npz      ``parse_arguments``; stdout / stderr / exit code of ``main()`` for dry runs and
+                        usage errors (temp paths replaced by <TMP>); and one real run on two tiny
+                        smooth X/Y pairs (LUT, undistorted fisheye, 10 views + masks as PNG) whose
+                        input and output images are stored for the end-to-end parity test
 cv2_remap.npz           ``cv2.remap`` outputs (the routine the reference calls,
                         DF:2001-2008) for small random sources x dtypes x
                         interpolations x borders
@@ -273,6 +278,132 @@ def dump_color(df):
     np.savez_compressed(HERE / "color_pipeline.npz", **arrays)
 
 
+TINY_XML = """<?xml version="1.0" encoding="UTF-8"?>
+<document version="2.3.0"><chunk label="Chunk 1" enabled="true"><sensors next_id="1">
+<sensor id="0" label="unknown" type="equisolid_fisheye"><resolution width="{w}" height="{h}"/>
+<calibration type="equisolid_fisheye" class="adjusted"><resolution width="{w}" height="{h}"/>
+<f>{f}</f><cx>0.4</cx><cy>-0.3</cy><k1>0.06</k1><k2>-0.004</k2><k3>0.0007</k3></calibration>
+</sensor></sensors></chunk></document>
+"""
+
+
+def _smooth_image(rng, h, w, dtype=np.uint8):
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.empty((h, w, 3))
+    for c in range(3):
+        a = rng.uniform(0.5, 2.5, 4)
+        ph = rng.uniform(0, 6.28, 4)
+        img[..., c] = (0.5 + 0.2 * np.sin(a[0] * xx / w * 6.28 + ph[0]) * np.cos(a[1] * yy / h * 6.28 + ph[1])
+                       + 0.15 * np.sin(a[2] * (xx + yy) / (w + h) * 6.28 + ph[2]) + 0.1 * np.cos(a[3] * yy / h * 3.14 + ph[3]))
+    top = np.iinfo(dtype).max
+    return np.clip(np.rint(img * top), 0, top).astype(dtype)
+
+
+def _run_df_main(df, argv, tmp):
+    import contextlib
+    import io
+    out, err = io.StringIO(), io.StringIO()
+    old_argv, code = sys.argv, 0
+    sys.argv = ["gs360_DualFisheyeDistortionCalibration.py"] + argv
+    try:
+        with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+            try:
+                df.main()
+            except SystemExit as exc:
+                code = exc.code if isinstance(exc.code, int) else 1
+    finally:
+        sys.argv = old_argv
+    norm = lambda t: t.replace(str(tmp), "<TMP>")
+    return {"argv": [norm(a) for a in argv], "stdout": norm(out.getvalue()), "stderr": norm(err.getvalue()), "exit": code}
+
+
+def dump_df_cli(df):
+    import argparse
+    import tempfile
+    import cv2
+    # (1) the parser
+    captured = {}
+    real_parse = argparse.ArgumentParser.parse_args
+
+    def spy(self, *a, **k):
+        captured["parser"] = self
+        return real_parse(self, ["--input-dir", "x"])
+    argparse.ArgumentParser.parse_args = spy
+    try:
+        df.parse_arguments()
+    finally:
+        argparse.ArgumentParser.parse_args = real_parse
+    actions = []
+    for act in captured["parser"]._actions:
+        if not act.option_strings or act.dest == "help":
+            continue
+        default = act.default
+        if act.dest == "camera_xml":
+            default = "<TEMPLATES>/" + pathlib.Path(default).name
+        elif act.dest == "dlogm_lut":
+            default = "<TEMPLATES>/" + pathlib.Path(default).name
+        elif act.dest == "workers":
+            default = "<CPU_COUNT>"
+        actions.append({"flags": list(act.option_strings), "dest": act.dest, "default": default,
+                        "type": getattr(act.type, "__name__", None), "choices": list(act.choices) if act.choices else None,
+                        "action": type(act).__name__, "required": bool(act.required)})
+    meta = {"actions": actions, "runs": {}}
+    arrays = {}
+    rng = np.random.default_rng(99)
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = pathlib.Path(tmp).resolve()
+        frames = tmp / "frames"
+        frames.mkdir()
+        W = H = 160
+        (tmp / "cal.xml").write_text(TINY_XML.format(w=W, h=H, f=44.0))
+        arrays["cal_xml"] = np.array((tmp / "cal.xml").read_text())
+        for name in ("a_X", "a_Y", "b_X", "b_Y", "c_X"):
+            img = _smooth_image(rng, H, W)
+            cv2.imwrite(str(frames / (name + ".png")), img)
+            arrays["in_" + name] = img
+        (frames / "notes.txt").write_text("not an image")
+        masks = tmp / "masks"
+        masks.mkdir()
+        for name in ("a_X", "a_Y", "b_X", "b_Y"):
+            m = (rng.random((H, W)) > 0.5).astype(np.uint8) * 255
+            cv2.imwrite(str(masks / (name + ".png")), m)
+            arrays["mask_" + name] = m
+        (tmp / "emptymasks").mkdir()
+        _write_cube(tmp / "look.cube", 5, rng, None)
+        arrays["cube_text"] = np.array((tmp / "look.cube").read_text())
+        base = ["--input-dir", str(frames), "--camera-xml", str(tmp / "cal.xml"), "--perspective-size", "48", "--workers", "2"]
+        runs = {
+            "dry_default": base + ["--dry-run"],
+            "dry_all_outputs": base + ["--dry-run", "--save-fisheye-output", "--save-color-corrected-output",
+                                       "--mask-input-dir", str(masks), "--input-lut", str(tmp / "look.cube"),
+                                       "--perspective-ext", "PNG", "--undistort-zoom", "1.2", "--limit", "3",
+                                       "--report-json", "r.json"],
+            "err_no_input": ["--camera-xml", str(tmp / "cal.xml")],
+            "err_missing_dir": ["--input-dir", str(tmp / "nope"), "--camera-xml", str(tmp / "cal.xml")],
+            "err_all_disabled": base + ["--no-perspective"],
+            "err_suffixes": base + ["--suffixes", "_X"],
+            "err_zoom": base + ["--undistort-zoom", "-1"],
+            "err_workers": base + ["--workers", "0"],
+            "err_masks_missing": base + ["--mask-input-dir", str(tmp / "emptymasks")],
+            "err_xml_missing": ["--input-dir", str(frames), "--camera-xml", str(tmp / "absent.xml")],
+            "err_color_profile_lut_missing": base + ["--input-color-profile", "osmo360-dlogm", "--dlogm-lut", str(tmp / "none.cube")],
+            "real": base + ["--save-fisheye-output", "--save-color-corrected-output", "--mask-input-dir", str(masks),
+                            "--input-lut", str(tmp / "look.cube"), "--perspective-ext", "png", "--interpolation", "linear",
+                            "--mask-value", "7"],
+        }
+        for name, argv in runs.items():
+            meta["runs"][name] = _run_df_main(df, argv, tmp)
+        for sub in ("frames_perspective_colmap/Images", "frames_perspective_colmap/Masks", "frames_undistorted",
+                    "frames_colorcorrected"):
+            d = tmp / sub
+            files = sorted(p.name for p in d.iterdir()) if d.is_dir() else []
+            meta.setdefault("real_files", {})[sub] = files
+            for fn in files:
+                arrays["out_%s_%s" % (sub.replace("/", "_"), fn)] = cv2.imread(str(d / fn), cv2.IMREAD_UNCHANGED)
+    (HERE / "df_cli.json").write_text(json.dumps(meta, indent=1, sort_keys=True) + "\n")
+    np.savez_compressed(HERE / "df_cli_outputs.npz", **arrays)
+
+
 def dump_cv2():
     import cv2
     rng = np.random.default_rng(20261017)
@@ -317,6 +448,7 @@ def main():
     dump_dualfisheye(df)
     dump_undistort(df)
     dump_color(df)
+    dump_df_cli(df)
     dump_cv2()
     for p in sorted(HERE.glob("*.json")) + sorted(HERE.glob("*.npz")):
         print("%9d  %s" % (p.stat().st_size, p.name))
