@@ -13,7 +13,7 @@
 
 namespace r360 {
 
-__device__ WeightTables g_tables;
+__device__ __align__(16) WeightTables g_tables;
 
 __device__ __forceinline__ int sat_short(int v) { return min(max(v, -32768), 32767); }
 

@@ -29,6 +29,7 @@
 #include "r360_direct.cuh"
 #include "r360_sample.cuh"
 #include "r360_fast_u8.cuh"
+#include "r360_fast_u16.cuh"
 
 namespace r360 {
 
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
 
     constexpr bool kFastU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
                              (INTERP == kLinear || INTERP == kCubic);
+    constexpr bool kFastU16 = std::is_same<TIn, uint16_t>::value && (INTERP == kLinear || INTERP == kCubic);
     const int tid = threadIdx.x;
     const int n_tiles = P.tiles_x * P.tiles_y;
     const int total = P.n_groups * P.n_views * n_tiles;             // the host keeps this below 2^31
@@ -542,6 +544,10 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                 if (kFastU8) {
                     si.bias = patch_bias_u8c3(si.patch_saddr, pitch, xb0, py0);
                     if (INTERP == kCubic) si.bias -= 3u + (uint32_t)pitch;
+                }
+                if (kFastU16) {
+                    si.bias = patch_bias_u16c3(si.patch_saddr, pitch, xb0, py0);
+                    if (INTERP == kCubic) si.bias -= 6u + (uint32_t)pitch;
                 }
                 si.size = charge; si.mode = mode; si.pitch = pitch; si.xb0 = xb0; si.py0 = py0;
                 si.full_tile = (i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height) ? 1 : 0;
@@ -737,6 +743,20 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                     pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
                     uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
                     o[0] = w0; o[1] = w1; o[2] = w2;
+                    done = true;
+                }
+            }
+            if constexpr (kFastU16) {
+                if (P.channels == 3) {
+                    const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float acc[3];
+                        if constexpr (INTERP == kLinear) bilinear_u16c3(bias, pitch, round_bits(sxf[q]), round_bits(syf[q]), acc);
+                        else bicubic_u16c3(bias, pitch, g_tables.cubic_1d, round_bits(sxf[q]), round_bits(syf[q]), acc);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) stage_row[q * 3 + c] = Finish<TIn, TOut>::run(acc[c]);
+                    }
                     done = true;
                 }
             }
