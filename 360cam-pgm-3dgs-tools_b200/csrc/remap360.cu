@@ -572,10 +572,20 @@ struct TiledLauncher {
         T.plans = pl->d_plans;
 
         auto kernel = remap_tiled_kernel<INTERP, TIn, TOut>;
-        static thread_local int configured_smem = -1;     // per instantiation and thread
-        if (configured_smem < pl->smem_bytes) {
-            R360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->smem_bytes));
-            configured_smem = pl->smem_bytes;
+        {
+            // opt this instantiation in to the device's full shared memory once per device (the attribute is
+            // per context; plans of different channel counts need different amounts of the same kernel)
+            static std::mutex mu;
+            static bool configured[64] = {};
+            int dev = 0;
+            R360_CUDA(cudaGetDevice(&dev));
+            std::lock_guard<std::mutex> lock(mu);
+            if (dev >= 0 && dev < 64 && !configured[dev]) {
+                int optin = 0;
+                R360_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+                R360_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+                configured[dev] = true;
+            }
         }
         // work items are indexed with 32-bit ints inside the kernel: chunk the groups if needed
         const long long per_group = (long long)pl->pr.n_views * pl->n_tiles;

@@ -506,3 +506,35 @@ def test_fisheye_output_coordinates_and_pixels(r360, path):
         assert within1 >= PIXEL_OK_FRACTION and exact >= 0.999, (k, exact, within1, worst)
     with pytest.raises(ValueError):
         r360.remap_erp(_to_cuda(src)[None], [r360.PerspectiveView(0, 0, 90, 90, projection="cube")], (8, 8))
+
+
+def test_concurrent_callers_with_different_layouts(r360):
+    """Host threads driving the same kernel instantiation with different shared-memory needs (1- and
+    3-channel bicubic) on their own streams: results equal the single-threaded ones."""
+    import threading
+    rng = np.random.default_rng(8)
+    W, H, size = 1024, 512, 160
+    views = _views(r360, [(0, 0), (120, 20), (180, 0)], fov=100.0)
+    srcs = {c: _noise(rng, (H, W, c), np.uint8) for c in (1, 3, 4)}
+    want = {c: _to_numpy(r360.remap_erp(_to_cuda(srcs[c])[None], views, (size, size), interp="cubic")) for c in srcs}
+    errors = []
+
+    def work(c):
+        try:
+            stream = torch.cuda.Stream()
+            dev = _to_cuda(srcs[c])[None]
+            for _ in range(6):
+                with torch.cuda.stream(stream):
+                    got = r360.remap_erp(dev, views, (size, size), interp="cubic", stream=stream)
+                stream.synchronize()
+                if not np.array_equal(_to_numpy(got), want[c]):
+                    errors.append("mismatch for %d channels" % c)
+        except Exception as exc:   # noqa: BLE001
+            errors.append("%d channels: %r" % (c, exc))
+
+    threads = [threading.Thread(target=work, args=(c,)) for c in (1, 3, 4, 3, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
