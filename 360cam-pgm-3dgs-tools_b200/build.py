@@ -18,6 +18,7 @@ HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "remap360" / "libremap360.so"
 STAMP = HERE / "remap360" / ".libremap360.stamp"
+CODEC_OUT = HERE / "remap360" / "libr360codec.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -36,7 +37,8 @@ def _nvcc() -> str:
 
 def _sources():
     return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) +
-                  list(CSRC.glob("*.h")) + [HERE.parent / "include" / "remap360.h", pathlib.Path(__file__)])
+                  list(CSRC.glob("*.h")) + list((HERE / "codec").glob("*.cpp")) +
+                  list((HERE.parent / "include").glob("*.h")) + [pathlib.Path(__file__)])
 
 
 def _digest() -> str:
@@ -49,7 +51,7 @@ def _digest() -> str:
 
 def build_library(force: bool = False, verbose: bool = False) -> pathlib.Path:
     digest = _digest()
-    if not force and OUT.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
+    if not force and OUT.exists() and CODEC_OUT.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return OUT
     build_dir = HERE / "build"
     build_dir.mkdir(exist_ok=True)
@@ -57,6 +59,10 @@ def build_library(force: bool = False, verbose: bool = False) -> pathlib.Path:
     cmds = [
         ["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-c", str(CSRC / "weights.cpp"), "-o", str(wobj)],
         [_nvcc(), *NVCC_FLAGS, "-shared", str(CSRC / "remap360.cu"), str(wobj), "-o", str(OUT)],
+        # JPEG codec glue over nvJPEG (library code, linked statically so that nothing but the CUDA driver is
+        # needed at run time); no device code of ours in it
+        [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I", str(HERE.parent / "include"),
+         str(HERE / "codec" / "jpeg_codec.cpp"), "-lnvjpeg_static", "-lculibos", "-o", str(CODEC_OUT)],
     ]
     for cmd in cmds:
         res = subprocess.run(cmd, capture_output=True, text=True)

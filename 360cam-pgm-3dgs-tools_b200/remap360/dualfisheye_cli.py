@@ -7,10 +7,10 @@ exit code 1), the ``[INFO]`` banner (DF:2386-2470), the ``[DRY]`` / ``[OK ]`` / 
 ``<input>_perspective_colmap`` / ``_undistorted`` / ``_colorcorrected``, DF:2207-2239); exit code 2 when
 any pair failed.
 
-What runs where: file decode / encode stay on the host (``--workers`` threads); per pair ONE upload of
-both lens images, then on the device the input colour pipeline (``r360_apply_lut``), the optional
-fisheye -> undistorted fisheye remap, the ten perspective views and their masks (nearest, border 0), and
-one download per output group.  The reference does the same work with NumPy + ``cv2.remap`` on the CPU
+What runs where: file decode and PNG / TIFF encode stay on the host (``--workers`` threads); per pair ONE
+upload of both lens images, then on the device the input colour pipeline (``r360_apply_lut``), the optional
+fisheye -> undistorted fisheye remap, the ten perspective views and their masks (nearest, border 0), the
+JPEG encode of the views (nvJPEG, remap360/codec.py), and one download per output group.  The reference does the same work with NumPy + ``cv2.remap`` on the CPU
 (``process_pair_task``, DF:1910-2064).
 
 Not built: the pose / COLMAP / Metashape-XML export behind ``--camera-extrinsics-xml``,
@@ -360,8 +360,8 @@ def match_masks(mask_dir: pathlib.Path, jobs: Sequence[PairJob]) -> None:
 class PairRenderer:
     """Device side of one run: cached view sets per sensor pair, one call per X/Y pair."""
 
-    def __init__(self, plan: RunPlan, specs, zooms: Dict[str, float]):
-        self.plan, self.specs, self.zooms = plan, specs, zooms
+    def __init__(self, plan: RunPlan, specs, zooms: Dict[str, float], jpeg_views: bool = False):
+        self.plan, self.specs, self.zooms, self.jpeg_views = plan, specs, zooms, jpeg_views
         self._views: Dict[Tuple[str, str], tuple] = {}
 
     def views_for(self, sensor_x: str, sensor_y: str):
@@ -414,8 +414,15 @@ class PairRenderer:
         if plan.want_persp:
             views, cals, _info = self.views_for(job.sensor_x, job.sensor_y)
             size = (int(a.perspective_size), int(a.perspective_size))
-            out["views"] = down(api.remap_fisheye(pair, cals, views, size, interp=interp, border_value=bv,
-                                                  fill_invalid=fill)[0])
+            rendered = api.remap_fisheye(pair, cals, views, size, interp=interp, border_value=bv, fill_invalid=fill)[0]
+            jc = None
+            if self.jpeg_views and rendered.dtype == torch.uint8 and rendered.shape[-1] in (1, 3):
+                from .executor import _gpu_codec
+                jc = _gpu_codec()
+            if jc is not None:          # JPEG views leave the device already encoded (4:4:4, --perspective-jpeg-quality)
+                out["views"] = [jc.encode(img, int(a.perspective_jpeg_quality)) for img in rendered]
+            else:
+                out["views"] = down(rendered)
             if plan.mask_dir is not None:
                 if mask_x is None or mask_y is None:
                     raise RuntimeError("Mask source missing for pair '{}'.".format(job.base))
@@ -430,6 +437,9 @@ class PairRenderer:
 def _write(path: pathlib.Path, image, jpeg_quality: Optional[int] = None) -> None:
     import cv2
     path.parent.mkdir(parents=True, exist_ok=True)
+    if isinstance(image, (bytes, bytearray)):          # encoded on the GPU
+        path.write_bytes(image)
+        return
     params: List[int] = []
     if jpeg_quality is not None and path.suffix.lower() in (".jpg", ".jpeg"):
         params = [int(cv2.IMWRITE_JPEG_QUALITY), int(max(1, min(100, jpeg_quality)))]
@@ -508,7 +518,7 @@ def run(plan: RunPlan) -> int:
                 counts["processed"] += 2
             ok_bases.add(job.base)
     elif not plan.metadata_only and jobs:
-        renderer = PairRenderer(plan, specs, zooms)
+        renderer = PairRenderer(plan, specs, zooms, jpeg_views=persp_ext in (".jpg", ".jpeg"))
         quality = int(a.perspective_jpeg_quality)
 
         def load(job: PairJob):

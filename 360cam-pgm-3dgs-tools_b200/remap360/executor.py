@@ -8,6 +8,7 @@ uploaded once."""
 
 from __future__ import annotations
 
+import os
 import pathlib
 import threading
 import traceback
@@ -100,14 +101,41 @@ def _write_image(path: pathlib.Path, image, jpeg_quality: int) -> None:
         raise JobError("failed to write %s" % path)
 
 
+def _gpu_codec():
+    """The calling thread's nvJPEG codec, or None when R360_CPU_CODEC is set or the library is unusable
+    (OpenCV's codec writes the same file format)."""
+    if os.environ.get("R360_CPU_CODEC"):
+        return None
+    try:
+        from . import codec
+        return codec.JpegCodec.for_thread()
+    except Exception:
+        return None
+
+
+def _is_jpeg(path: pathlib.Path) -> bool:
+    return path.suffix.lower() in (".jpg", ".jpeg")
+
+
 def _run_still_group(source: pathlib.Path, jobs: List[ParsedJob], stop_event) -> List[Tuple[int, str]]:
-    """All views of one still image: one decode, one upload, one batched launch per output size."""
+    """All views of one still image: one decode, one upload, one batched launch per output size.
+    JPEG sources are decoded and JPEG views encoded on the GPU (remap360/codec.py) when possible."""
     import cv2
     import numpy as np
     import torch
     from . import api
 
-    image = cv2.imread(str(source), cv2.IMREAD_UNCHANGED)
+    jc = _gpu_codec()
+    image = dev_image = None
+    if jc is not None and _is_jpeg(source):
+        try:
+            with _gpu_lock:
+                dev_image = jc.decode(source.read_bytes())          # [H, W, C] uint8, BGR like cv2
+            image = np.empty(tuple(dev_image.shape), dtype=np.uint8)   # shape / dtype carrier only
+        except Exception:
+            dev_image = None                                         # e.g. progressive JPEG: OpenCV reads it
+    if dev_image is None:
+        image = cv2.imread(str(source), cv2.IMREAD_UNCHANGED)
     if image is None:
         return [(1, "failed to read %s" % source)] * len(jobs)
     if image.ndim == 2:
@@ -133,18 +161,31 @@ def _run_still_group(source: pathlib.Path, jobs: List[ParsedJob], stop_event) ->
         views = [_job_view(jobs[k]) for k in idxs]
         try:
             with _gpu_lock:
-                if host.dtype == np.uint16:
+                if dev_image is not None:
+                    dev = dev_image
+                elif host.dtype == np.uint16:
                     dev = torch.from_numpy(host.view(np.int16)).cuda().view(torch.uint16)
                 else:
                     dev = torch.from_numpy(host).cuda()
                 out = api.remap_erp(dev[None], views, (w, h), interp=interp)[0]
-                if out.dtype == torch.uint16:
-                    out_host = out.view(torch.int16).cpu().numpy().view(np.uint16)
-                else:
-                    out_host = out.cpu().numpy()
+                encoded = {}
+                if jc is not None and out.dtype == torch.uint8 and out.shape[-1] in (1, 3):
+                    for n, k in enumerate(idxs):
+                        if _is_jpeg(jobs[k].output):
+                            encoded[n] = jc.encode(out[n], jobs[k].jpeg_quality)
+                out_host = None
+                if len(encoded) < len(idxs):
+                    if out.dtype == torch.uint16:
+                        out_host = out.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+                    else:
+                        out_host = out.contiguous().cpu().numpy()
             for n, k in enumerate(idxs):
-                img = out_host[n]
-                _write_image(jobs[k].output, img[..., 0] if img.shape[2] == 1 else img, jobs[k].jpeg_quality)
+                if n in encoded:
+                    jobs[k].output.parent.mkdir(parents=True, exist_ok=True)
+                    jobs[k].output.write_bytes(encoded[n])
+                else:
+                    img = out_host[n]
+                    _write_image(jobs[k].output, img[..., 0] if img.shape[2] == 1 else img, jobs[k].jpeg_quality)
                 results[k] = (0, "")
         except Exception as exc:  # report per job, like a failing ffmpeg process would
             text = "%s: %s" % (type(exc).__name__, exc)

@@ -51,6 +51,36 @@ def test_run_jobs_writes_every_view_of_a_still(r360, tmp_path):
     assert rc == 1 and "failed to read" in err
 
 
+@pytest.mark.parametrize("cpu_codec", [False, True])
+def test_jpeg_in_jpeg_out_through_the_gpu_codec(r360, tmp_path, monkeypatch, cpu_codec):
+    """JPEG panorama -> JPEG views: decoded / encoded by nvJPEG (default) or OpenCV (R360_CPU_CODEC); both
+    must give the oracle's views to JPEG accuracy, and the dual-fisheye CLI writes decodable JPEG views."""
+    cv2 = pytest.importorskip("cv2")
+    from remap360 import executor, perspcut as pc
+    if cpu_codec:
+        monkeypatch.setenv("R360_CPU_CODEC", "1")
+    else:
+        assert executor._gpu_codec() is not None
+    yy, xx = np.mgrid[0:512, 0:1024].astype(np.float64)
+    src = np.stack([127 + 90 * np.sin(xx / 1024 * 6.2832 * (k + 1)) * np.cos(yy / 512 * 3.1416 * (k + 1)) for k in range(3)],
+                   axis=-1).astype(np.uint8)
+    (tmp_path / "in").mkdir()
+    cv2.imwrite(str(tmp_path / "in" / "pano.jpg"), src, [cv2.IMWRITE_JPEG_QUALITY, 98])
+    decoded = cv2.imread(str(tmp_path / "in" / "pano.jpg"))
+    args = pc.create_arg_parser().parse_args(["-i", str(tmp_path / "in"), "--size", "200"])
+    args.size_explicit, args.hfov_explicit, args.focal_mm_explicit = True, False, False
+    args.input_is_video, args.video_bit_depth = False, 8
+    res = pc.build_view_jobs(args, [tmp_path / "in" / "pano.jpg"], tmp_path / "out")
+    done = list(executor.run_jobs(res.jobs, pc.stop_event, workers=1))
+    assert len(done) == 8 and all(rc == 0 for _job, (rc, _err) in done), done
+    for spec in res.view_specs:
+        got = cv2.imread(str(tmp_path / "out" / spec.output_name))
+        mx, my = geo.erp_map64(1024, 512, 200, 200, spec.yaw_deg, spec.pitch_deg, spec.hfov_deg, spec.vfov_deg)
+        want = sampler.sample(decoded, mx, my, "cubic", "erp")
+        mse = np.mean((got.astype(float) - want.astype(float)) ** 2)
+        assert got.shape == want.shape and 10 * np.log10(255.0 ** 2 / max(mse, 1e-9)) > 38.0
+
+
 def test_fisheye_xy_preset_jobs_run(r360, tmp_path):
     """Preset fisheyeXY: two `output=fisheye:d_fov=180` jobs per panorama (PC:871-887)."""
     cv2 = pytest.importorskip("cv2")
