@@ -363,6 +363,7 @@ class PairRenderer:
     def __init__(self, plan: RunPlan, specs, zooms: Dict[str, float], jpeg_views: bool = False):
         self.plan, self.specs, self.zooms, self.jpeg_views = plan, specs, zooms, jpeg_views
         self._views: Dict[Tuple[str, str], tuple] = {}
+        self._codec = None
 
     def views_for(self, sensor_x: str, sensor_y: str):
         key = (sensor_x, sensor_y)
@@ -417,8 +418,10 @@ class PairRenderer:
             rendered = api.remap_fisheye(pair, cals, views, size, interp=interp, border_value=bv, fill_invalid=fill)[0]
             jc = None
             if self.jpeg_views and rendered.dtype == torch.uint8 and rendered.shape[-1] in (1, 3):
-                from .executor import _gpu_codec
-                jc = _gpu_codec()
+                if self._codec is None:
+                    from .executor import _gpu_codec
+                    self._codec = _gpu_codec() or False          # False: tried, not available
+                jc = self._codec or None
             if jc is not None:          # JPEG views leave the device already encoded (4:4:4, --perspective-jpeg-quality)
                 out["views"] = [jc.encode(img, int(a.perspective_jpeg_quality)) for img in rendered]
             else:

@@ -76,7 +76,30 @@ def parse_job_argv(argv: Sequence[str]) -> ParsedJob:
 
 _INTERP = {"cubic": "cubic", "linear": "linear", "nearest": "nearest", "near": "nearest",
            "lanczos": "lanczos4"}          # v360 `lanczos` -> the cv2-compatible 8x8 Lanczos kernel
-_gpu_lock = threading.Lock()
+_gpu_slots = threading.BoundedSemaphore(4)      # source groups resident on the device at once (memory bound)
+_pool_lock = threading.Lock()
+_idle_workers: list = []          # (stream, codec or None) pairs, reused across run_jobs calls
+
+
+class _DeviceWorker:
+    """A CUDA stream plus an nvJPEG codec, borrowed by one host thread at a time: decode, remap and encode
+    of different sources overlap, and the (expensive) codec objects outlive the thread pools."""
+
+    def __enter__(self):
+        import torch
+        with _pool_lock:
+            item = _idle_workers.pop() if _idle_workers else None
+        if item is None:
+            item = (torch.cuda.Stream(), _gpu_codec())
+        self._item = item
+        self.stream = item[0]
+        self.codec = None if os.environ.get("R360_CPU_CODEC") else item[1]
+        return self
+
+    def __exit__(self, *exc):
+        with _pool_lock:
+            _idle_workers.append(self._item)
+        return False
 
 
 def _job_view(job: "ParsedJob"):
@@ -108,7 +131,7 @@ def _gpu_codec():
         return None
     try:
         from . import codec
-        return codec.JpegCodec.for_thread()
+        return codec.JpegCodec()
     except Exception:
         return None
 
@@ -125,12 +148,22 @@ def _run_still_group(source: pathlib.Path, jobs: List[ParsedJob], stop_event) ->
     import torch
     from . import api
 
-    jc = _gpu_codec()
+    with _DeviceWorker() as worker:
+        return _run_still_group_on(worker, source, jobs, stop_event)
+
+
+def _run_still_group_on(worker, source: pathlib.Path, jobs: List[ParsedJob], stop_event) -> List[Tuple[int, str]]:
+    import cv2
+    import numpy as np
+    import torch
+    from . import api
+
+    jc, stream = worker.codec, worker.stream
     image = dev_image = None
     if jc is not None and _is_jpeg(source):
         try:
-            with _gpu_lock:
-                dev_image = jc.decode(source.read_bytes())          # [H, W, C] uint8, BGR like cv2
+            with torch.cuda.stream(stream):
+                dev_image = jc.decode(source.read_bytes(), stream=stream)   # [H, W, C] uint8, BGR like cv2
             image = np.empty(tuple(dev_image.shape), dtype=np.uint8)   # shape / dtype carrier only
         except Exception:
             dev_image = None                                         # e.g. progressive JPEG: OpenCV reads it
@@ -160,25 +193,26 @@ def _run_still_group(source: pathlib.Path, jobs: List[ParsedJob], stop_event) ->
             continue
         views = [_job_view(jobs[k]) for k in idxs]
         try:
-            with _gpu_lock:
+            with _gpu_slots, torch.cuda.stream(stream):
                 if dev_image is not None:
                     dev = dev_image
                 elif host.dtype == np.uint16:
                     dev = torch.from_numpy(host.view(np.int16)).cuda().view(torch.uint16)
                 else:
                     dev = torch.from_numpy(host).cuda()
-                out = api.remap_erp(dev[None], views, (w, h), interp=interp)[0]
+                out = api.remap_erp(dev[None], views, (w, h), interp=interp, stream=stream)[0]
                 encoded = {}
                 if jc is not None and out.dtype == torch.uint8 and out.shape[-1] in (1, 3):
                     for n, k in enumerate(idxs):
                         if _is_jpeg(jobs[k].output):
-                            encoded[n] = jc.encode(out[n], jobs[k].jpeg_quality)
+                            encoded[n] = jc.encode(out[n], jobs[k].jpeg_quality, stream=stream)
                 out_host = None
                 if len(encoded) < len(idxs):
                     if out.dtype == torch.uint16:
                         out_host = out.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
                     else:
                         out_host = out.contiguous().cpu().numpy()
+                stream.synchronize()
             for n, k in enumerate(idxs):
                 if n in encoded:
                     jobs[k].output.parent.mkdir(parents=True, exist_ok=True)
