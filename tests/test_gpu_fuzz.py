@@ -1,0 +1,103 @@
+"""Randomised parity sweep (``-m gpu``): random source sizes (aligned and unaligned rows), channel counts, sample
+types, output sizes that are not multiples of the tile, yaw / pitch / roll / FOV anywhere including the poles and the
+seam, both output projections, every interpolation -- tiled path against direct path against the oracle."""
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import geometry as geo  # noqa: E402
+from oracle import sampler  # noqa: E402
+
+
+def _cuda(a):
+    if a.dtype == np.uint16:
+        return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+    return torch.from_numpy(a).cuda()
+
+
+def _host(t):
+    t = t.contiguous()
+    return t.view(torch.int16).cpu().numpy().view(np.uint16) if t.dtype == torch.uint16 else t.cpu().numpy()
+
+
+def _close_fraction(a, b):
+    if a.dtype in (np.float16, np.float32):
+        scale = np.maximum(np.abs(b.astype(np.float64)), 2.0 ** -14) * (2.0 ** -10 if a.dtype == np.float16 else 2.0 ** -22)
+        return float((np.abs(a.astype(np.float64) - b.astype(np.float64)) <= scale).mean())
+    return float((np.abs(a.astype(np.int64) - b.astype(np.int64)) <= 1).mean())
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_erp_configurations(seed):
+    import remap360 as r360
+    rng = np.random.default_rng(1000 + seed)
+    channels = int(rng.choice([1, 3, 3, 3, 4]))
+    dtype = [np.uint8, np.uint8, np.uint16, np.float32, np.float16][int(rng.integers(0, 5))]
+    W = int(rng.choice([96, 250, 512, 777, 1024, 2048]))
+    H = max(8, W // 2 + int(rng.integers(-3, 4)))
+    ow, oh = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+    interp = ["nearest", "linear", "cubic", "lanczos4"][int(rng.integers(0, 4))]
+    convention = "halfpixel" if rng.random() < 0.8 else "v360"
+    if dtype in (np.float32, np.float16):
+        src = rng.random((H, W, channels), dtype=np.float32).astype(dtype)
+    else:
+        src = rng.integers(0, np.iinfo(dtype).max + 1, (H, W, channels)).astype(dtype)
+    views = []
+    for _ in range(int(rng.integers(1, 5))):
+        proj = "fisheye" if rng.random() < 0.2 else "rectilinear"
+        fov_hi = 300.0 if proj == "fisheye" else 175.0
+        views.append(r360.PerspectiveView(float(rng.uniform(-200, 200)), float(rng.choice([rng.uniform(-90, 90), 90.0, -90.0, 0.0])),
+                                          float(rng.uniform(5, fov_hi)), float(rng.uniform(5, fov_hi)),
+                                          roll_deg=float(rng.choice([0.0, rng.uniform(-180, 180)])), projection=proj))
+    dev = _cuda(src)[None]
+    direct = _host(r360.remap_erp(dev, views, (ow, oh), interp=interp, convention=convention, path="direct"))[0]
+    tiled = _host(r360.remap_erp(dev, views, (ow, oh), interp=interp, convention=convention, path="tiled"))[0]
+    assert direct.shape == (len(views), oh, ow, channels)
+    # the two device paths: identical up to 1/32-px bin flips
+    assert _close_fraction(tiled, direct) >= 0.995, (seed, interp, dtype, W, H, ow, oh, views)
+    for k, v in enumerate(views):
+        mx, my = geo.erp_map64(W, H, ow, oh, v.yaw_deg, v.pitch_deg, v.hfov_deg, v.vfov_deg, convention, v.roll_deg,
+                               v.projection)
+        want = sampler.sample(src, mx, my, interp, "erp")
+        assert _close_fraction(direct[k], want) >= 0.995, (seed, k, interp, dtype, W, H, ow, oh, v)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_fisheye_configurations(seed):
+    import remap360 as r360
+    rng = np.random.default_rng(5000 + seed)
+    dtype = [np.uint8, np.uint16][int(rng.integers(0, 2))]
+    W, H = int(rng.choice([200, 333, 640])), int(rng.choice([200, 301, 480]))
+    cal = dict(width=W, height=H, f=float(rng.uniform(0.2, 0.45) * W), cx=float(rng.uniform(-4, 4)), cy=float(rng.uniform(-4, 4)),
+               k1=float(rng.uniform(-0.05, 0.1)), k2=float(rng.uniform(-0.01, 0.01)), k3=float(rng.uniform(-0.002, 0.002)),
+               k4=float(rng.uniform(-3e-4, 3e-4)), p1=float(rng.uniform(-1e-3, 1e-3)), p2=float(rng.uniform(-1e-3, 1e-3)),
+               b1=float(rng.uniform(-2, 2)), b2=float(rng.uniform(-1, 1)))
+    fov = float(rng.uniform(120, 200))
+    calib = r360.FisheyeCalibration(**cal, lens_fov_deg=fov)
+    interp = ["nearest", "linear", "cubic", "lanczos4"][int(rng.integers(0, 4))]
+    bv, fill = int(rng.integers(0, 255)), bool(rng.integers(0, 2))
+    pair = rng.integers(0, np.iinfo(dtype).max + 1, (1, 2, H, W, 3)).astype(dtype)
+    ow, oh = int(rng.integers(8, 150)), int(rng.integers(8, 150))
+    views = [r360.PerspectiveView(float(rng.uniform(-120, 120)), float(rng.uniform(-80, 80)), float(rng.uniform(20, 150)),
+                                  float(rng.uniform(20, 150)), src_slot=int(rng.integers(0, 2))) for _ in range(3)]
+    outs = {p: _host(r360.remap_fisheye(_cuda(pair), [calib, calib], views, (ow, oh), interp=interp, border_value=bv,
+                                         fill_invalid=fill, path=p))[0] for p in ("direct", "tiled")}
+    assert _close_fraction(outs["tiled"], outs["direct"]) >= 0.995
+    for k, v in enumerate(views):
+        mx, my, ok = geo.fisheye_map64(cal, v.yaw_deg, v.pitch_deg, v.hfov_deg, v.vfov_deg, ow, oh, fov)
+        want = sampler.sample(pair[0, v.src_slot], mx, my, interp, "constant", bv)
+        if fill:
+            want = sampler.apply_invalid_fill(want, ok, bv)
+        assert _close_fraction(outs["direct"][k], want) >= 0.99, (seed, k, interp, dtype, v)
+        # undistort with a random zoom through the same calibration
+    item = [r360.UndistortItem(float(rng.uniform(0.7, 1.5)), int(rng.integers(0, 2)))]
+    und = {p: _host(r360.undistort_fisheye(_cuda(pair), [calib, calib], item, interp=interp, border_value=bv,
+                                           fill_invalid=fill, path=p))[0, 0] for p in ("direct", "tiled")}
+    mx, my, ok, _ = geo.undistort_map64(cal, item[0].zoom, fov)
+    want = sampler.sample(pair[0, item[0].src_slot], mx, my, interp, "constant", bv)
+    if fill:
+        want = sampler.apply_invalid_fill(want, ok, bv)
+    assert _close_fraction(und["direct"], want) >= 0.99 and _close_fraction(und["tiled"], und["direct"]) >= 0.995
