@@ -365,6 +365,12 @@ class PairRenderer:
         self._views: Dict[Tuple[str, str], tuple] = {}
         self._codec = None
 
+    def _jpeg_codec(self):
+        if self._codec is None:
+            from .executor import _gpu_codec
+            self._codec = _gpu_codec() or False                  # False: tried, not available
+        return self._codec or None
+
     def views_for(self, sensor_x: str, sensor_y: str):
         key = (sensor_x, sensor_y)
         if key not in self._views:
@@ -380,6 +386,26 @@ class PairRenderer:
         import torch
         from . import api, color
         plan, a = self.plan, self.plan.args
+        pair = None
+        if isinstance(image_x, bytes) and isinstance(image_y, bytes):
+            # JPEG frames arrive undecoded: nvJPEG writes them straight into the pair tensor
+            jc = self._jpeg_codec()
+            try:
+                if jc is None:
+                    raise RuntimeError("no GPU codec")
+                wx, hx, cx = jc.info(image_x)
+                if jc.info(image_y) != (wx, hx, cx) or cx != 3:
+                    raise RuntimeError("X/Y differ")
+                pair = torch.empty((1, 2, hx, wx, 3), dtype=torch.uint8, device="cuda")
+                jc.decode(image_x, out=pair[0, 0])
+                jc.decode(image_y, out=pair[0, 1])
+                image_x = image_y = np.empty((hx, wx, 3), dtype=np.uint8)       # shape / dtype carriers
+            except Exception:
+                import cv2
+                pair = None
+                image_x, image_y = (cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_UNCHANGED) for b in (image_x, image_y))
+                if image_x is None or image_y is None:
+                    raise RuntimeError("Failed to read image: {}".format(job.x_path if image_x is None else job.y_path))
         if image_x.shape != image_y.shape or image_x.dtype != image_y.dtype:
             raise RuntimeError("X/Y images differ in size or type: {} vs {}".format(image_x.shape, image_y.shape))
         if image_x.dtype not in (np.uint8, np.uint16):
@@ -396,7 +422,8 @@ class PairRenderer:
             host = t.view(torch.int16).cpu().numpy().view(np.uint16) if t.dtype == torch.uint16 else t.cpu().numpy()
             return [img[..., 0] if img.shape[-1] == 1 else img for img in host]
 
-        pair = up([image_x, image_y])[None]                              # [1, 2, H, W, C]
+        if pair is None:
+            pair = up([image_x, image_y])[None]                          # [1, 2, H, W, C]
         if plan.lut is not None:
             color.apply_input_color_pipeline(pair, plan.lut, plan.lut_space, out=pair)
         out: Dict[str, list] = {}
@@ -418,10 +445,7 @@ class PairRenderer:
             rendered = api.remap_fisheye(pair, cals, views, size, interp=interp, border_value=bv, fill_invalid=fill)[0]
             jc = None
             if self.jpeg_views and rendered.dtype == torch.uint8 and rendered.shape[-1] in (1, 3):
-                if self._codec is None:
-                    from .executor import _gpu_codec
-                    self._codec = _gpu_codec() or False          # False: tried, not available
-                jc = self._codec or None
+                jc = self._jpeg_codec()
             if jc is not None:          # JPEG views leave the device already encoded (4:4:4, --perspective-jpeg-quality)
                 out["views"] = [jc.encode(img, int(a.perspective_jpeg_quality)) for img in rendered]
             else:
@@ -523,11 +547,14 @@ def run(plan: RunPlan) -> int:
     elif not plan.metadata_only and jobs:
         renderer = PairRenderer(plan, specs, zooms, jpeg_views=persp_ext in (".jpg", ".jpeg"))
         quality = int(a.perspective_jpeg_quality)
+        gpu_decode = renderer._jpeg_codec() is not None
 
         def load(job: PairJob):
             masks = (None, None)
             if plan.mask_dir is not None:
                 masks = (_read(job.x_mask, "mask image"), _read(job.y_mask, "mask image"))
+            if gpu_decode and all(p.suffix.lower() in (".jpg", ".jpeg") for p in (job.x_path, job.y_path)):
+                return job.x_path.read_bytes(), job.y_path.read_bytes(), masks[0], masks[1]
             return _read(job.x_path), _read(job.y_path), masks[0], masks[1]
 
         def finish(job: PairJob, out: Dict[str, list]):

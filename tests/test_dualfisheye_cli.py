@@ -125,3 +125,29 @@ def test_real_run_writes_what_the_reference_wrote(gold, tmp_path):
                 assert d.max() <= 1 and (d == 0).mean() >= 0.999, (sub, fn, d.max())
             else:
                 assert (d <= 2).mean() >= 0.995, (sub, fn, (d <= 2).mean(), d.max())
+
+
+@pytest.mark.gpu
+def test_jpeg_frames_are_decoded_and_views_encoded_on_the_gpu(gold, tmp_path, monkeypatch):
+    """JPEG X/Y frames in, JPEG views out: the nvJPEG run and the OpenCV-codec run give the same views to JPEG
+    accuracy, and both report the reference's lines."""
+    cv2 = pytest.importorskip("cv2")
+    meta, arrays = gold
+    tmp = tmp_path.resolve()
+    _materialise(tmp, arrays)
+    for p in sorted((tmp / "frames").glob("*.png")):
+        cv2.imwrite(str(p.with_suffix(".jpg")), cv2.imread(str(p)), [cv2.IMWRITE_JPEG_QUALITY, 97])
+        p.unlink()
+    base = ["--input-dir", "<TMP>/frames", "--camera-xml", "<TMP>/cal.xml", "--perspective-size", "64", "--workers", "2"]
+    outs = {}
+    for mode in ("gpu", "cpu"):
+        if mode == "cpu":
+            monkeypatch.setenv("R360_CPU_CODEC", "1")
+        code, out, err = _run(base + ["--perspective-output-dir", "<TMP>/out_" + mode], tmp)
+        assert (code, err) == (0, "") and "[DONE] processed=4 skipped=0 total=4 persp_outputs=20" in out
+        outs[mode] = {p.name: cv2.imread(str(p)) for p in sorted((tmp / ("out_" + mode) / "Images").glob("*.jpg"))}
+        assert len(outs[mode]) == 20
+    for name, img in outs["gpu"].items():
+        other = outs["cpu"][name]
+        mse = np.mean((img.astype(float) - other.astype(float)) ** 2)
+        assert img.shape == other.shape == (64, 64, 3) and 10 * np.log10(255.0 ** 2 / max(mse, 1e-9)) > 36.0, name
