@@ -71,19 +71,60 @@ def preset_views(preset, size):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons of one GPU, sampled every 10 ms on a host thread while the timed region
+    runs (B200_PROFILING.md's clocks line).  NVML directly (the library behind nvidia-smi; no process start-up
+    inside a region that lasts ~100 ms), `nvidia-smi -lms` as the fallback.  Only samples whose host
+    timestamp falls inside [mark_start, mark_end] are summarised."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                   ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [t.strip() for t in vis.split(",") if t.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def __enter__(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                        bits = int(reasons_fn(handle))
+                        self.rows.append((time.monotonic(), mhz, max_mhz,
+                                          [name for name, bit in self.REASON_BITS if bits & bit]))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                ["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -92,32 +133,46 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if len(r) < 7:
+                continue
+            try:
+                self.rows.append((time.monotonic(), float(r[0]), float(r[1]),
+                                  [name for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                               "sw_power_cap"), r[3:7]) if flag.lower().startswith("active")]))
+            except ValueError:
+                continue
+
+    def wait_ready(self, timeout=5.0):
+        """Block until the first sample has arrived (nvidia-smi needs a moment to start)."""
+        end = time.monotonic() + timeout
+        while not self.rows and time.monotonic() < end:
+            time.sleep(0.005)
+
+    def mark_start(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def __exit__(self, *exc):
+        self._stop.set()
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+        if self.thread:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            if len(r) < 7:
-                continue
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        rows = [r for r in self.rows if (self.t0 is None or r[0] >= self.t0) and (self.t1 is None or r[0] <= self.t1)]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        reasons = sorted({name for r in rows for name in r[3]})
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows),
+                "reasons": reasons, "samples": len(rows), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------
@@ -256,20 +311,25 @@ def main():
 
     def timed(interp, steps, warmup, sample_clocks):
         """K steps bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks."""
-        for _ in range(warmup):
-            step(interp)
-        barrier()
-        l0 = remap360.launch_count()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
             sampler.__enter__()
+        for _ in range(warmup):
+            step(interp)
+        if sampler:
+            sampler.wait_ready()
+        barrier()
+        l0 = remap360.launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        if sampler:
+            sampler.mark_start()
         ev[0].record()
         for k in range(steps):
             step(interp)
             ev[k + 1].record()
         barrier()
         if sampler:
+            sampler.mark_end()
             sampler.__exit__(None, None, None)
         per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
         total = ev[0].elapsed_time(ev[steps])
