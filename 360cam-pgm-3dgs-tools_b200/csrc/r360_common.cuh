@@ -19,6 +19,9 @@ constexpr int kMaxLenses = 4;
 // kProjUndistort: fisheye image -> "undistorted" fisheye image (DF:1008-1051); its views carry the
 // normalised sensor-plane coordinates (x / zoom, y / zoom, 1) instead of a world ray.
 enum Proj : int { kProjErp = 0, kProjFisheye = 1, kProjUndistort = 2 };
+// Radial law of a fisheye source: r = 2 f sin(theta / 2) (Metashape calibrations, v360 `equisolid`) or
+// r = f theta (v360 `fisheye`, the --fisheye-projection equidistant of gs360_Video2Frames.py:466-473).
+enum LensModel : int { kLensEquisolid = 0, kLensEquidistant = 1 };
 enum Interp : int { kNearest = 0, kLinear = 1, kCubic = 2, kLanczos4 = 3 };
 
 // A view is a linear map from output pixel indices to an (unnormalised) world ray:
@@ -51,6 +54,8 @@ struct LensDev {         // one fisheye calibration
     double xmax, ymax;   // width - 1, height - 1
     double cos_theta_max;
     double sin_half_theta_max;   // kProjUndistort: valid <=> min(r / 2, 1) <= sin(theta_max / 2)
+    int32_t model;               // LensModel
+    int32_t pad;
 };
 
 struct ImageSetDev {
@@ -144,8 +149,15 @@ __device__ __forceinline__ bool fisheye_xy(const LensDev& L, double dx, double d
                                            double& x, double& y) {
     const double n2 = fma(dx, dx, fma(dy, dy, dz * dz));
     const double n = sqrt(n2);
-    const double den = n * (n + dz);
-    const double s = den > 1e-24 * n2 ? sqrt(2.0 / den) : 0.0;
+    double s;
+    if (L.model == kLensEquidistant) {
+        // theta / rho with rho = hypot(dx, dy) / n: the ray's angle from the axis spread linearly over the radius
+        const double h = sqrt(fma(dx, dx, dy * dy));
+        s = h > 1e-12 * n ? atan2(h, dz) / h : (dz > 0.0 ? 1.0 / n : 0.0);
+    } else {
+        const double den = n * (n + dz);
+        s = den > 1e-24 * n2 ? sqrt(2.0 / den) : 0.0;
+    }
     const double xn = dx * s;
     const double yn = -dy * s;
     brown_to_sensor(L, xn, yn, x, y);

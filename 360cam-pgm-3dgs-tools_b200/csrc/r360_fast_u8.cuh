@@ -16,7 +16,23 @@
 #define R360_CUBIC_LDS64 0   // measured on B200: 103 vs 105 Gpix/s -- fewer wavefronts, but the selects cost more
 #endif
 
+#ifndef R360_TABLE_SWIZZLE
+#define R360_TABLE_SWIZZLE 0
+#endif
+
 namespace r360 {
+
+// Position of the (fy, fx) entry inside a plane of the shared-memory weight table.  The entry's 16-byte
+// bank group is its index mod 8; neighbouring lanes walk fx in a near-arithmetic progression whose
+// step is often a multiple of 2, 4 or 8 bins, which piles a quarter-warp onto few bank groups.
+// Adding fx / 8 to the low three bits spreads every power-of-two step over all eight groups.
+__host__ __device__ __forceinline__ uint32_t table_entry_index(uint32_t fy, uint32_t fx) {
+#if R360_TABLE_SWIZZLE
+    return (fy << 5) + (fx & 24u) + ((fx + (fx >> 3)) & 7u);
+#else
+    return (fy << 5) + fx;
+#endif
+}
 
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
     uint32_t v;
@@ -92,7 +108,7 @@ __device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, 
     uint32_t a8 = addr & ~7u;
     const bool odd = (addr & 4u) != 0;
 #endif
-    const uint32_t wt = table_saddr + ((fy << 5) + fx) * 16u;
+    const uint32_t wt = table_saddr + table_entry_index(fy, fx) * 16u;
     const uint4 wa = lds128(wt), wb = lds128(wt + 16384u);      // plane of rows 0,1 | plane of rows 2,3: (w0|w1<<16, w2|w3<<16) each
     const uint32_t wrow[4][2] = {{wa.x, wa.y}, {wa.z, wa.w}, {wb.x, wb.y}, {wb.z, wb.w}};
     int r = 16384, g = 16384, b = 16384;

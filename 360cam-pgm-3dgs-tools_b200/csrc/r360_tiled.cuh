@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
         // Two planes (tap rows 0,1 | rows 2,3) with a 16-byte entry stride: a warp's 32 random entries
         // then spread over all 8 bank groups instead of the 4 a 32-byte stride would reach.
         for (int q = tid; q < kTableBytes / 16; q += kTiledThreads)
-            reinterpret_cast<int4*>(table)[(q >> 1) + (q & 1) * (kTableBytes / 32)] = __ldg(src + q);
+            reinterpret_cast<int4*>(table)[table_entry_index((uint32_t)q >> 6, ((uint32_t)q >> 1) & 31u) + (q & 1) * (kTableBytes / 32)] = __ldg(src + q);
     }
     __syncthreads();
 

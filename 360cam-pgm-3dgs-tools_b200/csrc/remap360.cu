@@ -168,6 +168,8 @@ void make_lens(const r360_fisheye_calib& c, LensDev* L) {
     const double half = std::fmax(1.0, std::fmin(360.0, c.lens_fov_deg)) * 0.5;   // DF:1800
     L->cos_theta_max = std::cos(half * (M_PI / 180.0));
     L->sin_half_theta_max = std::sin(half * 0.5 * (M_PI / 180.0));
+    L->model = c.model == R360_LENS_EQUIDISTANT ? kLensEquidistant : kLensEquisolid;
+    L->pad = 0;
 }
 
 // Fisheye -> undistorted fisheye (DF:1021-1029): the output pixel (i, j) has normalised coordinates

@@ -18,6 +18,7 @@ INTERP = {"nearest": 0, "linear": 1, "bilinear": 1, "cubic": 2, "bicubic": 2, "l
 CONVENTION = {"halfpixel": 0, "v360": 1}
 PATH = {"auto": 0, "direct": 1, "tiled": 2}
 OUT_PROJECTION = {"rectilinear": 0, "fisheye": 1}
+LENS_MODEL = {"equisolid": 0, "equidistant": 1}
 MAX_LENSES = 4
 
 
@@ -34,7 +35,8 @@ class View(Structure):
 
 class FisheyeCalib(Structure):
     _fields_ = [(n, c_double) for n in ("width", "height", "f", "cx", "cy", "k1", "k2", "k3", "k4",
-                                        "p1", "p2", "b1", "b2", "lens_fov_deg")]
+                                        "p1", "p2", "b1", "b2", "lens_fov_deg")] + \
+               [("model", c_int32), ("reserved", c_int32)]
 
 
 class Undistort(Structure):
@@ -114,8 +116,8 @@ def load() -> ctypes.CDLL:
     lib.r360_plan_destroy.restype = None
     lib.r360_debug_weight_tables.argtypes = [c_void_p, c_void_p]
     lib.r360_debug_weight_tables_lanczos4.argtypes = [c_void_p, c_void_p]
-    if lib.r360_abi_version() != 1:
-        raise ImportError("libremap360.so has ABI version %d, expected 1" % lib.r360_abi_version())
+    if lib.r360_abi_version() != 2:
+        raise ImportError("libremap360.so has ABI version %d, expected 2" % lib.r360_abi_version())
     _lib = lib
     return lib
 

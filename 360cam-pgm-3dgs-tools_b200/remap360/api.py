@@ -76,6 +76,7 @@ class FisheyeCalibration:
     b1: float = 0.0
     b2: float = 0.0
     lens_fov_deg: float = 190.0
+    model: str = "equisolid"         # or "equidistant" (v360 input=fisheye, V2F:466-473)
 
 
 _TORCH_TO_R360 = {torch.uint8: _lib.DTYPE_U8, torch.uint16: _lib.DTYPE_U16,
@@ -134,7 +135,10 @@ def _view_key(v):
 def _calib_array(calibs: Sequence[FisheyeCalibration]):
     arr = (FisheyeCalib * len(calibs))()
     for k, c in enumerate(calibs):
-        arr[k] = FisheyeCalib(*(float(getattr(c, name)) for name, _ in FisheyeCalib._fields_))
+        if c.model not in _lib.LENS_MODEL:
+            raise ValueError("unknown lens model %r" % (c.model,))
+        arr[k] = FisheyeCalib(*(float(getattr(c, name)) for name, _ in FisheyeCalib._fields_[:14]),
+                              _lib.LENS_MODEL[c.model], 0)
     return arr
 
 
@@ -221,7 +225,7 @@ def get_plan(src: Images, dst: Images, views: Sequence[PerspectiveView], opt: Op
     key = (device.index, _layout_key(src, src.data % 16 == 0 if src.data else True),
            _layout_key(dst, dst.data % 16 == 0 if dst.data else True),
            tuple(_view_key(v) for v in views),
-           None if calibs is None else tuple(tuple(getattr(c, n) for n, _ in FisheyeCalib._fields_) for c in calibs),
+           None if calibs is None else tuple(tuple(getattr(c, n) for n, _ in FisheyeCalib._fields_[:15]) for c in calibs),
            (opt.interp, opt.convention, opt.fill_invalid, opt.border_value, opt.out_dtype))
     plan = _PLAN_CACHE.get(key)
     if plan is not None:

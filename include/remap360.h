@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define R360_ABI_VERSION 1
+#define R360_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------- */
 enum {
@@ -96,8 +96,16 @@ typedef struct r360_view {
                                 `output=fisheye` (gs360_360PerspCut.py:375-379, preset fisheyeXY) */
 } r360_view;
 
+/* Radial law of a fisheye source (r360_fisheye_calib.model).  EQUISOLID r = 2 f sin(theta/2): the
+ * Metashape calibrations of the dual-fisheye tool and v360 `input=equisolid`.  EQUIDISTANT
+ * r = f theta: v360 `input=fisheye`, i.e. --fisheye-projection equidistant of
+ * gs360_Video2Frames.py:466-487. */
+enum { R360_LENS_EQUISOLID = 0, R360_LENS_EQUIDISTANT = 1 };
+
 /* Metashape equisolid-fisheye calibration, the fields of SensorCalibration
- * (gs360_DualFisheyeDistortionCalibration.py:67-85) that the projection uses. */
+ * (gs360_DualFisheyeDistortionCalibration.py:67-85) that the projection uses.  An ideal lens of
+ * v360's `ih_fov` / `iv_fov` (gs360_Video2Frames.py:483-487) is the same record with zero
+ * distortion terms: f + b1 = (W/2) / r(ih_fov/2), f = (H/2) / r(iv_fov/2), r the radial law. */
 typedef struct r360_fisheye_calib {
     double width, height;    /* sensor resolution the calibration refers to                 */
     double f, cx, cy;
@@ -105,6 +113,8 @@ typedef struct r360_fisheye_calib {
     double p1, p2;
     double b1, b2;
     double lens_fov_deg;     /* usable lens FOV (DF --lens-fov-deg, default 190)            */
+    int32_t model;           /* R360_LENS_EQUISOLID (0) or R360_LENS_EQUIDISTANT            */
+    int32_t reserved;
 } r360_fisheye_calib;
 
 /* One output of the fisheye -> undistorted-fisheye remap (DF --save-fisheye-output): which lens

@@ -152,7 +152,10 @@ def fisheye_map64(calib: Mapping[str, float], yaw_rel_deg: float, pitch_deg: flo
     rho = np.sqrt(rx * rx + ry * ry)
     scale = np.zeros_like(rho)
     nz = rho > 1e-12
-    scale[nz] = 2.0 * np.sin(theta[nz] * 0.5) / rho[nz]
+    if calib.get("model", "equisolid") == "equidistant":      # v360 input=fisheye: r = f * theta
+        scale[nz] = theta[nz] / rho[nz]
+    else:
+        scale[nz] = 2.0 * np.sin(theta[nz] * 0.5) / rho[nz]
     xn = rx * scale
     yn = -ry * scale
     xd, yd = brown_distort(xn, yn, calib)
@@ -164,6 +167,58 @@ def fisheye_map64(calib: Mapping[str, float], yaw_rel_deg: float, pitch_deg: flo
     valid &= (mx >= 0.0) & (mx <= calib["width"] - 1)
     valid &= (my >= 0.0) & (my <= calib["height"] - 1)
     return mx, my, valid
+
+
+def ideal_fisheye_calib(width: int, height: int, projection: str, ih_fov_deg: float,
+                        iv_fov_deg: float = None, convention: str = "halfpixel") -> Dict[str, float]:
+    """An undistorted lens that fills a width x height image with ``ih_fov`` x ``iv_fov`` degrees: the source
+    model behind ``v360=<fisheye|equisolid>:rectilinear:ih_fov=..:iv_fov=..`` (V2F:466-487) as a record of
+    :func:`fisheye_map64`.  v360 normalises the image to [-1, 1] by ``r(fov / 2)`` with r(theta) = theta
+    (``fisheye``, equidistant) or sin(theta / 2) (``equisolid``) *[upstream vf_v360.c, unverified here]*;
+    ``halfpixel`` puts +-1 on the image edges (pixel index = (u + 1) W / 2 - 0.5), ``v360`` on the centres
+    of the outermost pixels (index = (u + 1) (W - 1) / 2)."""
+    iv_fov_deg = ih_fov_deg if iv_fov_deg is None else iv_fov_deg
+    if projection not in ("equidistant", "equisolid"):
+        raise ValueError("projection must be 'equidistant' or 'equisolid'")
+
+    def radius(fov_deg):
+        half = math.radians(max(1.0, min(360.0, float(fov_deg))) * 0.5)
+        return half if projection == "equidistant" else 2.0 * math.sin(half * 0.5)
+
+    if convention == "v360":
+        half_w, half_h, shift = (width - 1) * 0.5, (height - 1) * 0.5, 0.0
+    else:
+        half_w, half_h, shift = width * 0.5, height * 0.5, -0.5
+    fy = half_h / radius(iv_fov_deg)
+    fx = half_w / radius(ih_fov_deg)
+    return {"width": float(width), "height": float(height), "f": fy, "b1": fx - fy, "b2": 0.0,
+            "cx": half_w + shift - width * 0.5, "cy": half_h + shift - height * 0.5,
+            "k1": 0.0, "k2": 0.0, "k3": 0.0, "k4": 0.0, "p1": 0.0, "p2": 0.0, "model": projection}
+
+
+def v360_fisheye_input_map64(width: int, height: int, projection: str, ih_fov_deg: float, iv_fov_deg: float,
+                             hfov_deg: float, vfov_deg: float, out_w: int, out_h: int,
+                             yaw_deg: float = 0.0, pitch_deg: float = 0.0, convention: str = "halfpixel"):
+    """Independent statement of the same mapping, written the way v360 does it (normalised (uf, vf) in
+    [-1, 1], no focal length): used by the tests to cross-check :func:`ideal_fisheye_calib`."""
+    rays = camera_rays(out_w, out_h, hfov_deg, vfov_deg, yaw_deg, pitch_deg)
+    rx, ry, rz = rays[..., 0], rays[..., 1], rays[..., 2]
+    h = np.sqrt(rx * rx + ry * ry)
+    theta = np.arctan2(h, rz)
+    lh = np.where(h > 0.0, h, 1.0)
+    if projection == "equidistant":
+        rad = theta
+        ru = math.radians(ih_fov_deg * 0.5)
+        rv = math.radians(iv_fov_deg * 0.5)
+    else:
+        rad = np.sin(theta * 0.5)
+        ru = math.sin(math.radians(ih_fov_deg * 0.25))
+        rv = math.sin(math.radians(iv_fov_deg * 0.25))
+    uf = rx / lh * rad / ru
+    vf = -ry / lh * rad / rv
+    if convention == "v360":
+        return (uf + 1.0) * (width - 1) * 0.5, (vf + 1.0) * (height - 1) * 0.5
+    return (uf + 1.0) * width * 0.5 - 0.5, (vf + 1.0) * height * 0.5 - 0.5
 
 
 def undistort_map64(calib: Mapping[str, float], zoom: float, lens_fov_deg: float,

@@ -35,6 +35,8 @@ df_cli_outputs.npz      ``parse_arguments``; stdout / stderr / exit code of ``ma
                         usage errors (temp paths replaced by <TMP>); and one real run on two tiny
                         smooth X/Y pairs (LUT, undistorted fisheye, 10 views + masks as PNG) whose
                         input and output images are stored for the end-to-end parity test
+v2f_fisheye.json        the ``v360=<fisheye|equisolid>:rectilinear:...`` filter string and view FOVs that
+                        gs360_Video2Frames.py builds for --fisheye-perspective (V2F:467-487)
 cv2_remap.npz           ``cv2.remap`` outputs (the routine the reference calls,
                         DF:2001-2008) for small random sources x dtypes x
                         interpolations x borders
@@ -436,10 +438,40 @@ def dump_cv2():
     np.savez_compressed(HERE / "cv2_remap.npz", **arrays)
 
 
+def dump_v2f(reference_dir):
+    """The v360 filter string gs360_Video2Frames.py builds for --fisheye-perspective (V2F:467-487).  The code
+    sits inside main(); the block is cut out of the reference's source text and executed as it stands."""
+    import textwrap
+    import types
+    src = (pathlib.Path(reference_dir) / "cli_tools" / "gs360_Video2Frames.py").read_text()
+    start = src.index("        focal_mm = max(args.fisheye_focal_mm, 1e-6)")
+    end = src.index("        vf_chain = [v360_filter", start)
+    block = textwrap.dedent(src[start:end])
+    import gs360_360PerspCut as pc
+    cases = []
+    for projection in ("equidistant", "equisolid", "bogus"):
+        for input_fov, focal, size in ((190.0, 8.0, 1600), (220.0, 12.0, 1024), (400.0, 0.5, 3), (0.2, 300.0, 2000),
+                                       (180.0, 17.5, 1750)):
+            env = {"args": types.SimpleNamespace(fisheye_focal_mm=focal, fisheye_size=size,
+                                                 fisheye_projection=projection, fisheye_input_fov=input_fov),
+                   "fov_from_focal_mm": pc.fov_from_focal_mm, "v_fov_from_hfov": pc.v_fov_from_hfov,
+                   "FISHEYE_SENSOR_WIDTH_MM": 36.0}
+            exec(block, env)
+            cases.append({"projection": projection, "input_fov": input_fov, "focal_mm": focal, "size": size,
+                          "filter": env["v360_filter"], "hfov_deg": env["hfov_deg"], "vfov_deg": env["vfov_deg"]})
+    (HERE / "v2f_fisheye.json").write_text(json.dumps({"cases": cases}, indent=1) + "\n")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("reference", nargs="?", default="/root/reference")
+    ap.add_argument("--only", default="", help="regenerate one family only (v2f)")
     ns = ap.parse_args()
+    if ns.only == "v2f":
+        sys.dont_write_bytecode = True
+        sys.path.insert(0, str(pathlib.Path(ns.reference) / "cli_tools"))
+        dump_v2f(ns.reference)
+        return
     sys.dont_write_bytecode = True
     sys.path.insert(0, str(pathlib.Path(ns.reference) / "cli_tools"))
     import gs360_360PerspCut as pc
@@ -450,6 +482,7 @@ def main():
     dump_color(df)
     dump_df_cli(df)
     dump_cv2()
+    dump_v2f(ns.reference)
     for p in sorted(HERE.glob("*.json")) + sorted(HERE.glob("*.npz")):
         print("%9d  %s" % (p.stat().st_size, p.name))
 

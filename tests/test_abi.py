@@ -57,7 +57,7 @@ def test_library_contains_sm100a_code_only(lib):
 
 def test_error_strings_and_defaults(lib):
     from remap360 import _lib
-    assert lib.r360_abi_version() == 1
+    assert lib.r360_abi_version() == 2
     assert lib.r360_error_string(0) == b"ok"
     assert b"invalid" in lib.r360_error_string(-1)
     opt = _lib.default_options()
