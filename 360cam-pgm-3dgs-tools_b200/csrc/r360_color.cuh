@@ -101,4 +101,58 @@ __global__ void __launch_bounds__(256) lut_kernel(const __grid_constant__ LutPar
     for (int c = 3; c < p.channels; ++c) d[c] = s[c];
 }
 
+// ---- video colour step ---------------------------------------------------------------------------------
+// The cutter's video branch puts `colorspace=iall=bt709:all=smpte170m[:trc=iec61966-2-1]` in front of the
+// remap (gs360_360PerspCut.py:299-309; gs360_Video2Frames.py:462-464 after it).  In R'G'B' terms that filter
+// is: decode the source transfer curve, change primaries with a 3x3 matrix on linear light, encode with
+// the destination curve.  One thread per pixel, float32; the matrix comes from the host (float64
+// chromaticity algebra, rounded once).
+enum Trc : int { kTrcBt709 = 0, kTrcSrgb = 1, kTrcLinear = 2 };      // bt709 == smpte170m == bt2020 curve
+
+struct ColorConvertParams {
+    ImageSetDev src, dst;
+    int channels, n_images;
+    int in_trc, out_trc;
+    int rgb_order;           // 0: memory order B, G, R; 1: R, G, B
+    float m[9];              // linear RGB -> linear RGB, row-major
+};
+
+__device__ __forceinline__ float trc_decode(int trc, float v) {      // code value -> linear light (odd extension)
+    const float a = fabsf(v);
+    float l;
+    if (trc == kTrcBt709) l = a < 0.081242858f ? a * (1.0f / 4.5f) : powf((a + 0.09929682f) * (1.0f / 1.09929682f), 1.0f / 0.45f);
+    else if (trc == kTrcSrgb) l = a <= 0.04045f ? a * (1.0f / 12.92f) : powf((a + 0.055f) * (1.0f / 1.055f), 2.4f);
+    else l = a;
+    return copysignf(l, v);
+}
+__device__ __forceinline__ float trc_encode(int trc, float l) {
+    const float a = fabsf(l);
+    float v;
+    if (trc == kTrcBt709) v = a < 0.018053968f ? 4.5f * a : 1.09929682f * powf(a, 0.45f) - 0.09929682f;
+    else if (trc == kTrcSrgb) v = a <= 0.0031308f ? 12.92f * a : 1.055f * powf(a, 1.0f / 2.4f) - 0.055f;
+    else v = a;
+    return copysignf(v, l);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) color_convert_kernel(const __grid_constant__ ColorConvertParams p) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y, n = blockIdx.z;
+    if (x >= p.src.width) return;
+    const T* s = reinterpret_cast<const T*>(p.src.data + (long long)n * p.src.image_stride + (long long)y * p.src.pitch) +
+                 (long long)x * p.channels;
+    T* d = reinterpret_cast<T*>(p.dst.data + (long long)n * p.dst.image_stride + (long long)y * p.dst.pitch) +
+           (long long)x * p.channels;
+    const int ir = p.rgb_order ? 0 : 2, ib = 2 - ir;
+    const float r = trc_decode(p.in_trc, Unit01<T>::load(s[ir])), g = trc_decode(p.in_trc, Unit01<T>::load(s[1])),
+                b = trc_decode(p.in_trc, Unit01<T>::load(s[ib]));
+    const float ro = fmaf(p.m[0], r, fmaf(p.m[1], g, p.m[2] * b));
+    const float go = fmaf(p.m[3], r, fmaf(p.m[4], g, p.m[5] * b));
+    const float bo = fmaf(p.m[6], r, fmaf(p.m[7], g, p.m[8] * b));
+    d[ir] = Unit01<T>::store(clip01(trc_encode(p.out_trc, ro)));
+    d[1] = Unit01<T>::store(clip01(trc_encode(p.out_trc, go)));
+    d[ib] = Unit01<T>::store(clip01(trc_encode(p.out_trc, bo)));
+    for (int c = 3; c < p.channels; ++c) d[c] = s[c];
+}
+
 }  // namespace r360

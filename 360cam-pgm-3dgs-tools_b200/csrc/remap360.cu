@@ -773,6 +773,43 @@ int r360_apply_lut(const r360_images* src, const r360_images* dst, const r360_lu
     return R360_OK;
 }
 
+int r360_convert_color(const r360_images* src, const r360_images* dst, const r360_color_convert* cc,
+                       int32_t channel_order, void* stream) {
+    int rc;
+    if ((rc = check_images(src)) != R360_OK) return rc;
+    if ((rc = check_images(dst)) != R360_OK) return rc;
+    if (!cc) return R360_E_INVALID_ARG;
+    if (cc->in_trc < R360_TRC_BT709 || cc->in_trc > R360_TRC_LINEAR || cc->out_trc < R360_TRC_BT709 ||
+        cc->out_trc > R360_TRC_LINEAR)
+        return R360_E_INVALID_ARG;
+    if (channel_order != R360_ORDER_BGR && channel_order != R360_ORDER_RGB) return R360_E_INVALID_ARG;
+    if (src->channels < 3) return R360_E_INVALID_ARG;
+    if (src->width != dst->width || src->height != dst->height || src->channels != dst->channels ||
+        src->dtype != dst->dtype || src->count != dst->count)
+        return R360_E_INVALID_ARG;
+    if (src->dtype == R360_F16) return R360_E_UNSUPPORTED;
+    if (src->height > 65535 || src->count > 65535) return R360_E_INVALID_ARG;
+    ColorConvertParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
+    p.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
+    p.channels = src->channels; p.n_images = src->count;
+    p.in_trc = cc->in_trc; p.out_trc = cc->out_trc; p.rgb_order = channel_order == R360_ORDER_RGB;
+    for (int k = 0; k < 9; ++k) {
+        if (!std::isfinite(cc->matrix[k])) return R360_E_INVALID_ARG;
+        p.m[k] = cc->matrix[k];
+    }
+    if ((rc = ensure_device_ready()) != R360_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const dim3 grid((src->width + 255) / 256, src->height, src->count);
+    if (src->dtype == R360_U8) color_convert_kernel<uint8_t><<<grid, 256, 0, s>>>(p);
+    else if (src->dtype == R360_U16) color_convert_kernel<uint16_t><<<grid, 256, 0, s>>>(p);
+    else color_convert_kernel<float><<<grid, 256, 0, s>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    R360_CUDA(cudaGetLastError());
+    return R360_OK;
+}
+
 int r360_coords(int32_t src_w, int32_t src_h, const r360_fisheye_calib* calib, int32_t n_lenses,
                 const r360_view* views, int32_t n_views, int32_t out_w, int32_t out_h,
                 const r360_options* opt_in, float* map_x32, float* map_y32, double* map_x64, double* map_y64,

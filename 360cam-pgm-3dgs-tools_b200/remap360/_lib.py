@@ -19,6 +19,7 @@ CONVENTION = {"halfpixel": 0, "v360": 1}
 PATH = {"auto": 0, "direct": 1, "tiled": 2}
 OUT_PROJECTION = {"rectilinear": 0, "fisheye": 1}
 LENS_MODEL = {"equisolid": 0, "equidistant": 1}
+TRC = {"bt709": 0, "smpte170m": 0, "iec61966-2-1": 1, "srgb": 1, "linear": 2}
 MAX_LENSES = 4
 
 
@@ -48,6 +49,10 @@ class Lut3D(Structure):
                 ("domain_min", c_float * 3), ("domain_max", c_float * 3)]
 
 
+class ColorConvert(Structure):
+    _fields_ = [("in_trc", c_int32), ("out_trc", c_int32), ("matrix", c_float * 9), ("reserved", c_int32)]
+
+
 class Options(Structure):
     _fields_ = [("interp", c_int32), ("convention", c_int32), ("path", c_int32), ("fill_invalid", c_int32),
                 ("border_value", c_double), ("out_dtype", c_int32), ("reserved", c_int32)]
@@ -66,7 +71,8 @@ EXPORTS = ("r360_abi_version", "r360_error_string", "r360_last_cuda_error", "r36
            "r360_device_info", "r360_remap_erp", "r360_remap_fisheye", "r360_coords", "r360_launch_count",
            "r360_plan_workspace_bytes", "r360_plan_create_erp", "r360_plan_create_fisheye", "r360_plan_info",
            "r360_remap_planned", "r360_plan_coords", "r360_plan_destroy",
-           "r360_remap_undistort", "r360_coords_undistort", "r360_plan_create_undistort", "r360_apply_lut")
+           "r360_remap_undistort", "r360_coords_undistort", "r360_plan_create_undistort", "r360_apply_lut",
+           "r360_convert_color")
 
 
 def load() -> ctypes.CDLL:
@@ -109,6 +115,7 @@ def load() -> ctypes.CDLL:
                                                POINTER(Undistort), c_int32, POINTER(Options), c_void_p,
                                                ctypes.c_size_t, c_void_p, POINTER(c_void_p)]
     lib.r360_apply_lut.argtypes = [POINTER(Images), POINTER(Images), POINTER(Lut3D), c_int32, c_int32, c_void_p]
+    lib.r360_convert_color.argtypes = [POINTER(Images), POINTER(Images), POINTER(ColorConvert), c_int32, c_void_p]
     lib.r360_plan_info.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32)]
     lib.r360_remap_planned.argtypes = [c_void_p, POINTER(Images), POINTER(Images), c_void_p]
     lib.r360_plan_coords.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -119,3 +119,78 @@ def apply_input_color_pipeline(images: torch.Tensor, lut: Optional[CubeLUT], lut
     if stream is not None:
         table.record_stream(stream)
     return out
+
+
+# ---- video colour step ----------------------------------------------------------------------------------
+# `colorspace=iall=bt709:all=smpte170m[:trc=iec61966-2-1]` (PC:299-309, V2F:462-464).
+
+# CIE xy chromaticities of the primaries (R, G, B) and D65 white, as in ITU-R BT.709 / SMPTE 170M
+_PRIMARIES = {
+    "bt709": ((0.640, 0.330), (0.300, 0.600), (0.150, 0.060)),
+    "smpte170m": ((0.630, 0.340), (0.310, 0.595), (0.155, 0.070)),
+}
+_D65 = (0.3127, 0.3290)
+
+
+def rgb_to_xyz_matrix(primaries: str):
+    """Linear RGB -> CIE XYZ for a set of primaries with D65 white (float64)."""
+    import numpy as np
+    xy = _PRIMARIES[primaries]
+    cols = np.array([[x / y, 1.0, (1.0 - x - y) / y] for x, y in xy], dtype=np.float64).T
+    white = np.array([_D65[0] / _D65[1], 1.0, (1.0 - _D65[0] - _D65[1]) / _D65[1]])
+    return cols * np.linalg.solve(cols, white)
+
+
+def primaries_matrix(src: str, dst: str):
+    """Linear RGB(src primaries) -> linear RGB(dst primaries); both D65, so no chromatic adaptation."""
+    import numpy as np
+    if src == dst:
+        return np.eye(3)
+    return np.linalg.solve(rgb_to_xyz_matrix(dst), rgb_to_xyz_matrix(src))
+
+
+def parse_colorspace_filter(text: str):
+    """``colorspace=iall=bt709:all=smpte170m[:trc=iec61966-2-1][:range=..][:format=..]`` -> (in_primaries, in_trc,
+    out_primaries, out_trc).  ``iall`` / ``all`` set primaries, transfer and matrix together; ``trc`` overrides
+    the output transfer.  ``range`` and ``format`` concern the YUV representation only and have no R'G'B' effect."""
+    if not text.startswith("colorspace="):
+        raise ValueError("not a colorspace filter: %r" % text)
+    opts = dict(kv.split("=", 1) for kv in text[len("colorspace="):].split(":") if "=" in kv)
+    src, dst = opts.get("iall", "bt709"), opts.get("all", "bt709")
+    for name in (src, dst):
+        if name not in _PRIMARIES:
+            raise ValueError("unsupported colour space %r" % name)
+    out_trc = opts.get("trc", dst)
+    if out_trc not in _lib.TRC:
+        raise ValueError("unsupported transfer %r" % out_trc)
+    return src, src, dst, out_trc
+
+
+def convert_video_color(images: torch.Tensor, *, keep_rec709: bool = False, filter_text: Optional[str] = None,
+                        channel_order: str = "bgr", out: Optional[torch.Tensor] = None,
+                        stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """The cutter's video colour step on [.., H, W, C] uint8 / uint16 / float32 CUDA frames (``out`` may alias
+    ``images``): BT.709 -> SMPTE 170M primaries, re-encoded as sRGB unless ``keep_rec709`` (PC:303-305).
+    ``filter_text`` takes the job's own ``colorspace=...`` string instead."""
+    if filter_text is None:
+        filter_text = "colorspace=iall=bt709:all=smpte170m" + ("" if keep_rec709 else ":trc=iec61966-2-1")
+    src_p, in_trc, dst_p, out_trc = parse_colorspace_filter(filter_text)
+    if channel_order not in ("bgr", "rgb"):
+        raise ValueError("channel_order must be 'bgr' or 'rgb'")
+    if images.dim() < 3 or images.shape[-1] < 3:
+        raise ValueError("colour conversion requires at least 3-channel input")
+    if not images.is_contiguous():
+        raise ValueError("images must be contiguous")
+    flat = images.reshape((-1,) + tuple(images.shape[-3:]))
+    if out is None:
+        out = torch.empty_like(images)
+    elif out.shape != images.shape or out.dtype != images.dtype or not out.is_contiguous():
+        raise ValueError("out must match images")
+    src, dst = _describe(flat, "images"), _describe(out.reshape(flat.shape), "out")
+    m = primaries_matrix(src_p, dst_p)
+    desc = _lib.ColorConvert(_lib.TRC[in_trc], _lib.TRC[out_trc], (ctypes.c_float * 9)(*[float(v) for v in m.reshape(-1)]), 0)
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.load().r360_convert_color(ctypes.byref(src), ctypes.byref(dst), ctypes.byref(desc),
+                                                  1 if channel_order == "rgb" else 0,
+                                                  _stream_handle(stream, images.device)))
+    return out

@@ -37,6 +37,7 @@ class ParsedJob:
     end: Optional[float]
     jpeg_quality: int
     pix_fmt: Optional[str]
+    colorspace: Optional[str] = None     # the job's `colorspace=...` filter (video sources, PC:299-309)
 
 
 class JobError(RuntimeError):
@@ -60,6 +61,7 @@ def parse_job_argv(argv: Sequence[str]) -> ParsedJob:
     if kv.get("input") != "equirect":
         raise JobError("unsupported v360 input: %s" % kv.get("input"))
     fps = next((float(f.split("=", 1)[1]) for f in vf.split(",") if f.startswith("fps=")), None)
+    colorspace = next((f for f in vf.split(",") if f.startswith("colorspace=")), None)
     q = opt("-q:v")
     proj = kv.get("output", "rectilinear")
     if proj == "fisheye":
@@ -71,7 +73,7 @@ def parse_job_argv(argv: Sequence[str]) -> ParsedJob:
                      pitch=float(kv.get("pitch", 0.0)), roll=float(kv.get("roll", 0.0)), hfov=hfov, vfov=vfov,
                      interp=kv.get("interp", "cubic"), video=fps is not None, fps=fps,
                      start=float(opt("-ss")) if opt("-ss") else None, end=float(opt("-to")) if opt("-to") else None,
-                     jpeg_quality=95 if q == "2" else 100, pix_fmt=opt("-pix_fmt"))
+                     jpeg_quality=95 if q == "2" else 100, pix_fmt=opt("-pix_fmt"), colorspace=colorspace)
 
 
 _INTERP = {"cubic": "cubic", "linear": "linear", "nearest": "nearest", "near": "nearest",

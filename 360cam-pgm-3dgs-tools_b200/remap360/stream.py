@@ -9,7 +9,7 @@ once and all of its views are cut from the copy in HBM."""
 from __future__ import annotations
 
 from collections import deque
-from typing import Deque, Iterable, Iterator, List, Optional, Sequence, Tuple
+from typing import Callable, Deque, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -40,7 +40,8 @@ class StreamingRemapper:
 
     def __init__(self, views: Sequence[PerspectiveView], size: Tuple[int, int], frame_shape: Tuple[int, int, int],
                  dtype: torch.dtype = torch.uint8, *, interp: str = "cubic", convention: str = "halfpixel",
-                 out_dtype: Optional[torch.dtype] = None, device=None, depth: int = 3, path: str = "auto"):
+                 out_dtype: Optional[torch.dtype] = None, device=None, depth: int = 3, path: str = "auto",
+                 frame_filter: Optional[Callable[[torch.Tensor, torch.cuda.Stream], None]] = None):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.views = list(views)
@@ -48,6 +49,9 @@ class StreamingRemapper:
         self.interp, self.convention, self.path = interp, convention, path
         self.device = torch.device(device if device is not None else "cuda")
         self.out_dtype = out_dtype or dtype
+        # in-place per-frame step on the uploaded frame [1, H, W, C], run on the kernel stream before the
+        # remap (the cutter's video colour step, PC:299-309)
+        self.frame_filter = frame_filter
         with torch.cuda.device(self.device):
             self._free: List[_Slot] = [_Slot(frame_shape, dtype, len(self.views), self.size, self.out_dtype, self.device)
                                        for _ in range(depth)]
@@ -68,6 +72,8 @@ class StreamingRemapper:
             slot.dev_in[0].copy_(src, non_blocking=True)
             slot.ev_h2d.record(self.s_h2d)
         self.s_kernel.wait_event(slot.ev_h2d)
+        if self.frame_filter is not None:
+            self.frame_filter(slot.dev_in, self.s_kernel)
         remap_erp(slot.dev_in, self.views, self.size, interp=self.interp, convention=self.convention,
                   out=slot.dev_out, out_dtype=self.out_dtype, path=self.path, stream=self.s_kernel)
         slot.ev_kernel.record(self.s_kernel)

@@ -5,12 +5,14 @@ The reference starts one ffmpeg process per view, each decoding the whole video 
 once with OpenCV, pushed through the streaming remapper (pinned ring, H2D / kernel / D2H
 overlapped) and every view of a frame is written as ``<stem>_%07d_<view>.<ext>`` numbered from 0.
 
-Scope note: ffmpeg's ``colorspace=iall=bt709:all=smpte170m[:trc=iec61966-2-1]`` step
-(gs360_360PerspCut.py:299-309) is NOT applied -- frames are remapped in the decoder's BGR output
-(listed as "next" in DESIGN.md section 2)."""
+The jobs' ``colorspace=iall=bt709:all=smpte170m[:trc=iec61966-2-1]`` step (gs360_360PerspCut.py:299-309)
+runs on the device, in place on the uploaded frame, right before the remap -- the position it has in the
+reference's filter chain (``r360_convert_color``; ``R360_VIDEO_COLOR=0`` leaves frames in the decoder's
+BGR output)."""
 
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 
@@ -65,7 +67,14 @@ def run_video_jobs(source, jobs: Sequence, stop_event=None) -> List[Tuple[int, s
             ok, frame = cap.read()
             if not ok:
                 return [(1, "no frames in %s" % source)] * len(jobs)
-            remapper = StreamingRemapper(views, size, frame.shape, torch.uint8, interp=_INTERP[first.interp])
+            frame_filter = None
+            if first.colorspace and os.environ.get("R360_VIDEO_COLOR", "1") != "0":
+                from .color import convert_video_color
+
+                def frame_filter(dev_frame, stream, _text=first.colorspace):
+                    convert_video_color(dev_frame, filter_text=_text, channel_order="bgr", out=dev_frame, stream=stream)
+            remapper = StreamingRemapper(views, size, frame.shape, torch.uint8, interp=_INTERP[first.interp],
+                                         frame_filter=frame_filter)
 
             def frames():
                 nonlocal frame

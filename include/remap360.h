@@ -226,6 +226,28 @@ int r360_apply_lut(const r360_images* src, const r360_images* dst, const r360_lu
                    int32_t output_space, int32_t channel_order, void* stream);
 
 /*
+ * Video colour step of the cutter: `colorspace=iall=bt709:all=smpte170m[:trc=iec61966-2-1]`, the filter
+ * gs360_360PerspCut.py:299-309 puts in front of v360 for video sources (gs360_Video2Frames.py:462-464 puts
+ * it after).  On R'G'B' frames that filter amounts to: decode `in_trc`, multiply linear RGB by `matrix`
+ * (a change of primaries: BT.709 -> SMPTE 170M for the call above), encode `out_trc`, clip to the code
+ * range.  float32 arithmetic; ffmpeg's own implementation is 15-bit fixed point behind look-up tables and is
+ * not in this image, so results are stated against the formula, not against ffmpeg.
+ *
+ *   TRC_BT709 is also the SMPTE 170M curve (same constants); TRC_SRGB is IEC 61966-2-1; TRC_LINEAR none.
+ *   U8, U16 and F32 images, >= 3 channels (extra channels are copied); src and dst may be the same images.
+ */
+enum { R360_TRC_BT709 = 0, R360_TRC_SRGB = 1, R360_TRC_LINEAR = 2 };
+typedef struct r360_color_convert {
+    int32_t in_trc;
+    int32_t out_trc;
+    float   matrix[9];       /* row-major, linear RGB -> linear RGB */
+    int32_t reserved;
+} r360_color_convert;
+
+int r360_convert_color(const r360_images* src, const r360_images* dst, const r360_color_convert* cc,
+                       int32_t channel_order, void* stream);
+
+/*
  * Test/debug: the source coordinates the kernels sample at, without sampling.  Writes, for
  * view v and output pixel (j, i), element [(v * out_h + j) * out_w + i] of each non-null
  * device array:

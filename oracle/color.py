@@ -86,3 +86,63 @@ def apply_pipeline(image: np.ndarray, table: np.ndarray, domain_min, domain_max,
     out = image.copy()
     out[..., :3] = res
     return out
+
+
+# ---- video colour step (PC:299-309): formula-level statement, float64 --------------------------------
+# ffmpeg's `colorspace` filter is third-party, unversioned and absent from this image;
+# this states what the filter computes on R'G'B' values (ITU-R BT.709 / SMPTE 170M / IEC 61966-2-1 curves,
+# D65 primaries change) -- parity unpinned against ffmpeg itself, like the rest of that boundary.
+
+_BT709_ALPHA, _BT709_BETA = 1.09929682680944, 0.018053968510807
+
+
+def trc_decode64(name: str, v: np.ndarray) -> np.ndarray:
+    a = np.abs(np.asarray(v, dtype=np.float64))
+    if name in ("bt709", "smpte170m"):
+        lin = np.where(a < 4.5 * _BT709_BETA, a / 4.5, ((a + (_BT709_ALPHA - 1.0)) / _BT709_ALPHA) ** (1.0 / 0.45))
+    elif name in ("srgb", "iec61966-2-1"):
+        lin = np.where(a <= 0.04045, a / 12.92, ((a + 0.055) / 1.055) ** 2.4)
+    else:
+        lin = a
+    return np.copysign(lin, v)
+
+
+def trc_encode64(name: str, lin: np.ndarray) -> np.ndarray:
+    a = np.abs(np.asarray(lin, dtype=np.float64))
+    if name in ("bt709", "smpte170m"):
+        v = np.where(a < _BT709_BETA, 4.5 * a, _BT709_ALPHA * a ** 0.45 - (_BT709_ALPHA - 1.0))
+    elif name in ("srgb", "iec61966-2-1"):
+        v = np.where(a <= 0.0031308, 12.92 * a, 1.055 * a ** (1.0 / 2.4) - 0.055)
+    else:
+        v = a
+    return np.copysign(v, lin)
+
+
+def xyz_from_rgb64(primaries) -> np.ndarray:
+    """primaries = ((xr, yr), (xg, yg), (xb, yb)); D65 white."""
+    cols = np.array([[x / y, 1.0, (1.0 - x - y) / y] for x, y in primaries], dtype=np.float64).T
+    white = np.array([0.3127 / 0.3290, 1.0, (1.0 - 0.3127 - 0.3290) / 0.3290])
+    return cols * np.linalg.solve(cols, white)
+
+
+BT709_PRIMARIES = ((0.640, 0.330), (0.300, 0.600), (0.150, 0.060))
+SMPTE170M_PRIMARIES = ((0.630, 0.340), (0.310, 0.595), (0.155, 0.070))
+
+
+def video_color_step64(image_rgb: np.ndarray, out_trc: str = "iec61966-2-1") -> np.ndarray:
+    """R'G'B' image (RGB order, uint8 / uint16 / float) -> same dtype: BT.709 decode, 709 -> 170M primaries,
+    encode with ``out_trc`` (``smpte170m`` when --keep-rec709), clip, round half to even."""
+    dt = image_rgb.dtype
+    scale = 255.0 if dt == np.uint8 else 65535.0 if dt == np.uint16 else 1.0
+    v = image_rgb[..., :3].astype(np.float64) / scale
+    if scale == 1.0:
+        v = np.clip(v, 0.0, 1.0)
+    m = np.linalg.solve(xyz_from_rgb64(SMPTE170M_PRIMARIES), xyz_from_rgb64(BT709_PRIMARIES))
+    lin = trc_decode64("bt709", v) @ m.T
+    enc = np.clip(trc_encode64(out_trc, lin), 0.0, 1.0)
+    out = image_rgb.copy()
+    if scale == 1.0:
+        out[..., :3] = enc.astype(dt)
+    else:
+        out[..., :3] = np.rint(enc * scale).astype(dt)
+    return out
