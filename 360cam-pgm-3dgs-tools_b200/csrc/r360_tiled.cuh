@@ -31,6 +31,10 @@
 #include "r360_fast_u8.cuh"
 #include "r360_fast_u16.cuh"
 
+#ifndef R360_LINEAR_MAP_B
+#define R360_LINEAR_MAP_B 0     // bilinear 8-bit RGB on the lane-per-column mapping of the bicubic path (experiment)
+#endif
+
 namespace r360 {
 
 constexpr int kTile = 32;
@@ -643,7 +647,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             }
         }
         __syncwarp();
-        if constexpr (kFastU8 && INTERP == kCubic) {
+        if constexpr (kFastU8 && (INTERP == kCubic || R360_LINEAR_MAP_B)) {
             // ---- bicubic 8-bit RGB: lane = pixel column, 4 rows per lane -------------------------------
             // Sixteen taps per pixel make this path shared-memory bound; with adjacent lanes on adjacent
             // pixels the tap loads of a warp fall into neighbouring words (few bank conflicts), and the
@@ -668,7 +672,9 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                     dy = fmaf(dy, s, c2.z); dy = fmaf(dy, s, c2.y); dy = fmaf(dy, s, c2.x); dy = fmaf(dy, s, c1.w); dy = fmaf(dy, s, c1.z);
                     const float sx = __double2float_rn(ax_r + (double)dx), sy = __double2float_rn(ay_r + (double)dy);
                     ax_r += axj; ay_r += ayj;
-                    const uint32_t own = bicubic_u8c3(bias, pitch, tab, round_bits(sx), round_bits(sy));
+                    uint32_t own;
+                if constexpr (INTERP == kCubic) own = bicubic_u8c3(bias, pitch, tab, round_bits(sx), round_bits(sy));
+                else own = bilinear_u8c3(bias, pitch, round_bits(sx), round_bits(sy));
                     const uint32_t nxt = __shfl_down_sync(0xffffffffu, own, 1);
                     const uint32_t word = (own >> (8 * m)) | (nxt << (24 - 8 * m));
                     if (m < 3) {

@@ -13,10 +13,9 @@ fisheye -> undistorted fisheye remap, the ten perspective views and their masks 
 JPEG encode of the views (nvJPEG, remap360/codec.py), and one download per output group.  The reference does the same work with NumPy + ``cv2.remap`` on the CPU
 (``process_pair_task``, DF:1910-2064).
 
-Not built: the pose / COLMAP / Metashape-XML export behind ``--camera-extrinsics-xml``,
-``--pointcloud-ply`` and ``--metadata-only`` (pure CPU bookkeeping outside the remap path; SURVEY 8f
-rank 4).  Those flags are accepted and validated like the reference's, and the export step reports
-itself as failed (``[ERR] perspective camera metadata export failed``, exit code 2)."""
+The pose / COLMAP / Metashape-XML export behind ``--camera-extrinsics-xml``, ``--pointcloud-ply`` and
+``--metadata-only`` (DF:1348-1686, :2812-2833) is host bookkeeping in ``remap360/pose_export.py``; it uses the
+lens choice of the remap (made on the device) and writes the same files as the reference."""
 
 from __future__ import annotations
 
@@ -487,9 +486,15 @@ def run(plan: RunPlan) -> int:
     errors: List[str] = []
     counts = {"processed": 0, "skipped": 0, "color": 0, "persp": 0, "mask": 0}
     jobs: List[PairJob] = []
+    label_pairs = []
     if plan.metadata_only:
-        # the label pairing of DF:917-963 only feeds the metadata export, which is not built
-        pass
+        # no images are read: the X/Y pairs are the camera labels of the extrinsics XML (DF:2477-2499)
+        from . import pose_export
+        labels = set(pose_export.camera_transform_map(plan.extrinsics_xml)) if plan.extrinsics_xml is not None else None
+        label_pairs = pose_export.metadata_only_pairs(plan.camera_to_sensor, plan.sensors, plan.suffixes[0],
+                                                      plan.suffixes[1], labels)
+        if not label_pairs:
+            raise UsageError("No valid X/Y camera label pairs found in extrinsics XML.")
     for index, (base, x_path, y_path) in enumerate(plan.pairs, start=1):
         sx, sy = sensor_for_file(x_path, plan), sensor_for_file(y_path, plan)
         if sx is None or sy is None:
@@ -618,14 +623,66 @@ def run(plan: RunPlan) -> int:
                 except Exception as exc:
                     fail(wjob, exc)
 
-    if plan.extrinsics_xml is not None or plan.metadata_only:
-        errors.append("[ERR] perspective camera metadata export failed ({})".format(
-            "pose / COLMAP export is not part of the CUDA remap backend"))
-        print(errors[-1], file=sys.stderr)
+    if plan.extrinsics_xml is not None:
+        try:
+            if plan.metadata_only:
+                resolved, done_bases = label_pairs, {rec[1] for rec in label_pairs}
+            else:
+                resolved = [(j.index, j.base, j.x_path, j.y_path, j.sensor_x, j.sensor_y) for j in jobs]
+                done_bases = ok_bases
+            export_camera_metadata(plan, resolved, done_bases, specs, persp_ext)
+        except Exception as exc:
+            errors.append("[ERR] perspective camera metadata export failed ({})".format(exc))
+            print(errors[-1], file=sys.stderr)
     print("[DONE] processed={} skipped={} total={} persp_outputs={} mask_outputs={} color_outputs={} errors={}".format(
         counts["processed"], counts["skipped"], 2 * len(plan.pairs), counts["persp"], counts["mask"], counts["color"],
         len(errors)))
     return 2 if errors else 0
+
+
+def export_camera_metadata(plan: RunPlan, resolved_pairs, ok_bases, specs, persp_ext: str) -> None:
+    """DF:1599-1686: poses of every written view from the aligned fisheye cameras, then the Metashape XML and the
+    COLMAP text model next to the images (``[DRY][META]`` line only on a dry run)."""
+    from . import pose_export
+    a = plan.args
+    if bool(a.no_perspective) and not plan.metadata_only:
+        raise ValueError("--camera-extrinsics-xml requires perspective output to be enabled.")
+    if not plan.extrinsics_xml.is_file():
+        raise ValueError("Camera extrinsics XML not found: {}".format(plan.extrinsics_xml))
+    class _LensChoice(dict):
+        """(sensor X, sensor Y) -> {view id: "X" | "Y"}: the remap's own lens choice, made on the device the first
+        time a sensor pair is asked for (the reference reads it from its map cache, DF:1380-1397)."""
+        def get(self, key, default=None):
+            if key not in self:
+                _views, _cals, info = dfh.choose_lenses(plan.sensors[key[0]], plan.sensors[key[1]], specs,
+                                                        float(a.lens_x_yaw_deg), float(a.lens_y_yaw_deg),
+                                                        float(a.lens_fov_deg))
+                self[key] = {vid: rec["lens_key"] for vid, rec in info.items()}
+            return self[key]
+
+    lens_keys = _LensChoice()
+    frames = pose_export.perspective_pose_frames(pose_export.camera_transform_map(plan.extrinsics_xml), resolved_pairs,
+                                                 ok_bases, specs, lens_keys, persp_ext, float(a.lens_x_yaw_deg),
+                                                 float(a.lens_y_yaw_deg))
+    cameras, images = pose_export.colmap_model(frames, int(a.perspective_size), float(a.perspective_focal_mm),
+                                               str(a.perspective_sensor_mm))
+    points = []
+    if plan.pointcloud is not None:
+        if not plan.pointcloud.is_file():
+            raise ValueError("Point cloud PLY not found: {}".format(plan.pointcloud))
+        points = pose_export.colmap_points_from_ply(plan.pointcloud)
+    out_xml = plan.persp_root / str(a.perspective_metashape_xml_name)
+    out_colmap = plan.persp_root / "Sparse" / "0"
+    if a.dry_run:
+        print("[DRY][META] frames={} images={} xml={} colmap={} masks={} points={}".format(
+            len(frames), plan.images_dir, out_xml, out_colmap, plan.masks_dir, len(points)))
+        return
+    pose_export.write_metashape_perspective_xml(out_xml, cameras, images)
+    pose_export.write_colmap_text_model(out_colmap, cameras, images, points)
+    print("[OK] Perspective images root: {}".format(plan.images_dir))
+    print("[OK] Perspective Metashape XML: {}".format(out_xml))
+    print("[OK] Perspective COLMAP text: {} (images={}, points={})".format(out_colmap, len(images), len(points)))
+    print("[OK] Perspective masks root: {}".format(plan.masks_dir))
 
 
 def main(argv: Optional[Sequence[str]] = None) -> int:

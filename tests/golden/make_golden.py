@@ -35,6 +35,9 @@ df_cli_outputs.npz      ``parse_arguments``; stdout / stderr / exit code of ``ma
                         usage errors (temp paths replaced by <TMP>); and one real run on two tiny
                         smooth X/Y pairs (LUT, undistorted fisheye, 10 views + masks as PNG) whose
                         input and output images are stored for the end-to-end parity test
+df_metadata.json        pose / COLMAP / Metashape-XML export of the dual-fisheye tool on synthetic aligned projects:
+                        cameras as loaded (chunk / component similarity), label pairs, pose frames, the COLMAP
+                        model, the written files, and stdout / files of ``main()`` runs with --metadata-only
 v2f_fisheye.json        the ``v360=<fisheye|equisolid>:rectilinear:...`` filter string and view FOVs that
                         gs360_Video2Frames.py builds for --fisheye-perspective (V2F:467-487)
 cv2_remap.npz           ``cv2.remap`` outputs (the routine the reference calls,
@@ -438,6 +441,134 @@ def dump_cv2():
     np.savez_compressed(HERE / "cv2_remap.npz", **arrays)
 
 
+def _extrinsics_xml_text(n_pairs=3, with_chunk_transform=True, two_sensors=False):
+    """A synthetic aligned dual-fisheye project: the template's sensor block(s), X/Y cameras with 4x4 transforms,
+    a chunk similarity (rotation / translation / scale children), a component transform given as 16 numbers, one
+    disabled camera and one camera without a transform."""
+    rng = np.random.default_rng(2024)
+
+    def rot(ax, ay, az):
+        cx, sx, cy, sy, cz, sz = math.cos(ax), math.sin(ax), math.cos(ay), math.sin(ay), math.cos(az), math.sin(az)
+        rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        return rz @ ry @ rx
+
+    calib = ("<calibration type=\"equisolid_fisheye\" class=\"adjusted\"><resolution width=\"3840\" height=\"3840\"/>"
+             "<f>1049.9268186384606</f><cx>-0.053481903280599763</cx><cy>-0.040449115818567277</cy>"
+             "<k1>0.10190869149858893</k1><k2>0.00079808296648272998</k2><k3>-0.00031893309097734927</k3></calibration>")
+    sensors = ["<sensor id=\"%d\" label=\"unknown\" type=\"equisolid_fisheye\"><resolution width=\"3840\" height=\"3840\"/>%s</sensor>"
+               % (k, calib) for k in range(2 if two_sensors else 1)]
+    cams = []
+    cid = 0
+    for n in range(n_pairs):
+        base = rot(*(rng.random(3) * 2.0 - 1.0))
+        centre = rng.random(3) * 10.0 - 5.0
+        for lens, flip in (("X", np.eye(3)), ("Y", rot(0.0, math.pi, 0.0))):
+            m = np.eye(4)
+            m[:3, :3] = base @ flip
+            m[:3, 3] = centre + (0.01 if lens == "Y" else 0.0)
+            sid = 1 if (two_sensors and lens == "Y") else 0
+            cams.append("<camera id=\"%d\" sensor_id=\"%d\" component_id=\"0\" label=\"frame%04d_%s\"><transform>%s</transform></camera>"
+                        % (cid, sid, n + 1, lens, " ".join(repr(float(v)) for v in m.reshape(-1))))
+            cid += 1
+    cams.append("<camera id=\"%d\" sensor_id=\"0\" component_id=\"0\" label=\"frame9000_X\" enabled=\"false\"><transform>%s</transform></camera>"
+                % (cid, " ".join(repr(float(v)) for v in np.eye(4).reshape(-1))))
+    cams.append("<camera id=\"%d\" sensor_id=\"0\" component_id=\"0\" label=\"frame9001_X\"/>" % (cid + 1))
+    comp_m = np.eye(4)
+    comp_m[:3, :3] = 1.7 * rot(0.3, -0.2, 0.9)
+    comp_m[:3, 3] = [1.0, -2.0, 0.5]
+    comp = "<components next_id=\"1\" active_id=\"0\"><component id=\"0\" label=\"Component 1\"><transform>%s</transform></component></components>" \
+           % " ".join(repr(float(v)) for v in comp_m.reshape(-1))
+    chunk_tf = ""
+    if with_chunk_transform:
+        r = rot(-0.4, 0.25, 0.1)
+        chunk_tf = ("<transform><rotation locked=\"false\">%s</rotation><translation locked=\"false\">3.5 -1.25 0.75</translation>"
+                    "<scale locked=\"true\">2.5</scale></transform>") % " ".join(repr(float(v)) for v in r.reshape(-1))
+    return ("<?xml version=\"1.0\" encoding=\"UTF-8\"?>\n<document version=\"2.3.0\"><chunk label=\"Chunk 1\" enabled=\"true\">"
+            "<sensors next_id=\"2\">%s</sensors>%s<cameras next_id=\"%d\" next_group_id=\"0\">%s</cameras>%s</chunk></document>\n"
+            % ("".join(sensors), comp, cid + 2, "".join(cams), chunk_tf))
+
+
+def _ply_bytes(binary, with_color=True, n=7):
+    import struct
+    rng = np.random.default_rng(77)
+    pts = rng.random((n, 3)) * 20.0 - 10.0
+    cols = rng.integers(0, 256, (n, 3))
+    head = ["ply", "format %s 1.0" % ("binary_little_endian" if binary else "ascii"), "comment synthetic",
+            "element vertex %d" % n, "property float x", "property float y", "property double z"]
+    if with_color:
+        head += ["property uchar red", "property uchar green", "property uchar blue"]
+    head += ["element face 0", "property list uchar int vertex_indices", "end_header"]
+    blob = ("\n".join(head) + "\n").encode("ascii")
+    for p3, c3 in zip(pts, cols):
+        if binary:
+            blob += struct.pack("<ffd", *p3) + (struct.pack("<BBB", *[int(v) for v in c3]) if with_color else b"")
+        else:
+            blob += (" ".join([repr(float(np.float32(p3[0]))), repr(float(np.float32(p3[1]))), repr(float(p3[2]))] +
+                              ([str(int(v)) for v in c3] if with_color else [])) + "\n").encode("ascii")
+    return blob
+
+
+def dump_df_metadata(df):
+    """Pose / COLMAP / Metashape-XML export of the dual-fisheye tool (DF:917-963, :1348-1686, :2812-2833) on
+    synthetic aligned projects: library-level results and whole ``main()`` runs with --metadata-only."""
+    import base64
+    import tempfile
+    out = {"inputs": {}, "cases": [], "cli": []}
+    with tempfile.TemporaryDirectory() as tmp_s:
+        tmp = pathlib.Path(tmp_s)
+        variants = {"chunk": dict(with_chunk_transform=True), "component": dict(with_chunk_transform=False),
+                    "two_sensors": dict(with_chunk_transform=True, two_sensors=True)}
+        plys = {"binary_color": _ply_bytes(True, True), "ascii_color": _ply_bytes(False, True), "binary_plain": _ply_bytes(True, False)}
+        for name, blob in plys.items():
+            (tmp / (name + ".ply")).write_bytes(blob)
+            out["inputs"][name + ".ply"] = base64.b64encode(blob).decode("ascii")
+        specs = df.build_sfm10_specs(output_size=320, focal_mm=14.0, sensor_mm="36 36", yaw_delta_deg=40.0, pitch_delta_deg=40.0)
+        lens_of = {"A": "X", "A_U": "X", "A_D": "X", "B": "X", "J": "X", "E": "Y", "F": "Y", "F_U": "Y", "F_D": "Y", "G": "Y"}
+        for vname, kw in variants.items():
+            text = _extrinsics_xml_text(**kw)
+            xml_path = tmp / (vname + ".xml")
+            xml_path.write_text(text)
+            out["inputs"][vname + ".xml"] = text
+            cams = df.msxml_converter.load_metashape_cameras(xml_path)
+            sensor_map, camera_to_sensor = df.load_metashape_calibration(xml_path)
+            labels = set(df.build_camera_transform_map(xml_path).keys())
+            pairs = df.build_metadata_only_resolved_pairs(camera_to_sensor, sensor_map, "_X", "_Y", labels)
+            cache = {(p[4], p[5]): {vid: {"lens_key": k} for vid, k in lens_of.items()} for p in pairs}
+            frames = df.build_perspective_pose_frames(xml_path, pairs, {p[1] for p in pairs[:2]}, specs, cache, ".jpg", 0.0, 180.0)
+            cameras, images = df.build_colmap_model_from_pose_frames(frames, 320, 14.0, "36 24")
+            case = {"xml": vname + ".xml", "cameras_loaded": [[cid, label, mat] for cid, label, mat in cams],
+                    "pairs": [[p[0], p[1], str(p[2]), str(p[3]), p[4], p[5]] for p in pairs],
+                    "frames": [{k: v for k, v in f.items()} for f in frames], "colmap_cameras": cameras,
+                    "colmap_images": images, "files": {}}
+            for pname in plys:
+                points = df.build_colmap_points_from_metashape_ply(tmp / (pname + ".ply"))
+                odir = tmp / ("out_" + vname + "_" + pname)
+                df.camera_converter.write_colmap_text_model(odir, cameras, images, points)
+                df.camera_converter.export_metashape_perspective_xml(odir / "persp.xml", cameras, images)
+                case["files"][pname] = {f.name: f.read_text() for f in sorted(odir.iterdir())}
+            out["cases"].append(case)
+        # whole-program runs (metadata only: no images are read)
+        root = tmp / "persp_out"
+        base = ["--metadata-only", "--camera-extrinsics-xml", str(tmp / "chunk.xml"), "--pointcloud-ply",
+                str(tmp / "binary_color.ply"), "--perspective-output-dir", str(root), "--perspective-size", "256"]
+        for extra in (["--dry-run"], [], ["--camera-extrinsics-xml", str(tmp / "two_sensors.xml"), "--perspective-ext", "png"]):
+            run = _run_df_main(df, base + extra, tmp)
+            run["files"] = {}
+            if root.exists():
+                for f in sorted(root.rglob("*")):
+                    if f.is_file():
+                        run["files"][str(f.relative_to(root))] = f.read_text()
+                        f.unlink()
+            out["cli"].append(run)
+        for bad in (["--metadata-only", "--camera-extrinsics-xml", str(tmp / "chunk.xml")],
+                    ["--metadata-only", "--pointcloud-ply", str(tmp / "binary_color.ply")],
+                    ["--metadata-only", "--camera-extrinsics-xml", str(tmp / "chunk.xml"), "--pointcloud-ply", str(tmp / "nope.ply")]):
+            out["cli"].append(_run_df_main(df, bad, tmp))
+    (HERE / "df_metadata.json").write_text(json.dumps(out, indent=1) + "\n")
+
+
 def dump_v2f(reference_dir):
     """The v360 filter string gs360_Video2Frames.py builds for --fisheye-perspective (V2F:467-487).  The code
     sits inside main(); the block is cut out of the reference's source text and executed as it stands."""
@@ -467,10 +598,14 @@ def main():
     ap.add_argument("reference", nargs="?", default="/root/reference")
     ap.add_argument("--only", default="", help="regenerate one family only (v2f)")
     ns = ap.parse_args()
-    if ns.only == "v2f":
+    if ns.only in ("v2f", "df_metadata"):
         sys.dont_write_bytecode = True
         sys.path.insert(0, str(pathlib.Path(ns.reference) / "cli_tools"))
-        dump_v2f(ns.reference)
+        if ns.only == "v2f":
+            dump_v2f(ns.reference)
+        else:
+            import gs360_DualFisheyeDistortionCalibration as df
+            dump_df_metadata(df)
         return
     sys.dont_write_bytecode = True
     sys.path.insert(0, str(pathlib.Path(ns.reference) / "cli_tools"))
@@ -483,6 +618,7 @@ def main():
     dump_df_cli(df)
     dump_cv2()
     dump_v2f(ns.reference)
+    dump_df_metadata(df)
     for p in sorted(HERE.glob("*.json")) + sorted(HERE.glob("*.npz")):
         print("%9d  %s" % (p.stat().st_size, p.name))
 

@@ -88,13 +88,16 @@ def test_default_template_calibration_is_the_reference_template(golden_df):
         assert getattr(sensors["0"], key) == value, key
 
 
-def test_metadata_export_is_reported_as_unavailable(gold, tmp_path):
+def test_metadata_export_failure_is_reported_like_the_reference(gold, tmp_path):
+    """An extrinsics XML without a <cameras> block: the export step fails with load_metashape_cameras' message, the
+    run ends with errors=1 and exit code 2 (DF:2829-2849)."""
     meta, arrays = gold
     tmp = tmp_path.resolve()
     _materialise(tmp, arrays)
     code, out, err = _run(["--input-dir", "<TMP>/frames", "--camera-xml", "<TMP>/cal.xml", "--dry-run",
                            "--camera-extrinsics-xml", "<TMP>/cal.xml"], tmp)
-    assert code == 2 and "metadata export failed" in err and "errors=1" in out
+    assert code == 2 and "errors=1" in out
+    assert err == "[ERR] perspective camera metadata export failed (missing <cameras> in XML)\n"      # MS:549-551
     code, out, err = _run(["--metadata-only", "--camera-extrinsics-xml", "<TMP>/cal.xml"], tmp)
     assert code == 1 and err == "[ERR] --metadata-only requires --pointcloud-ply.\n"
 
