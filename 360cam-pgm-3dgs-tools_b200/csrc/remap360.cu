@@ -415,6 +415,7 @@ struct r360_plan {
     PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback;
     // tensor-TMA descriptors depend on the source base pointer and batch size: small cache
     bool tensor_ok;
+    int box_family;
     mutable std::mutex tm_mutex;
     struct TmEntry { const void* data; int count; int64_t stride; TensorMaps maps; };
     mutable std::vector<TmEntry> tm_cache;
@@ -439,7 +440,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // Descriptors for every box shape over (row bytes / 4 as uint32, rows, images).
-int encode_tensor_maps(const r360_images& src, TensorMaps* out) {
+int encode_tensor_maps(const r360_images& src, int family, TensorMaps* out) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return R360_E_CUDA;
     const int es = elem_size(src.dtype);
@@ -450,13 +451,13 @@ int encode_tensor_maps(const r360_images& src, TensorMaps* out) {
     const cuuint32_t estr[3] = {1, 1, 1};
     for (int wk = 0; wk < kNumBoxWidths; ++wk)
         for (int hk = 0; hk < kNumBoxHeights; ++hk) {
-            const cuuint32_t box[3] = {(cuuint32_t)box_width_bytes(wk) / 4, (cuuint32_t)box_height_rows(hk), 1};
+            const cuuint32_t box[3] = {(cuuint32_t)box_width_bytes(wk, family) / 4, (cuuint32_t)box_height_rows(hk), 1};
             const CUresult r = enc(&out->m[wk * kNumBoxHeights + hk], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.data, dims,
                                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
                 std::snprintf(tl_cuda_error, sizeof(tl_cuda_error), "cuTensorMapEncodeTiled failed (%d) for box %dx%d",
-                              (int)r, box_width_bytes(wk), box_height_rows(hk));
+                              (int)r, box_width_bytes(wk, family), box_height_rows(hk));
                 return R360_E_CUDA;
             }
         }
@@ -517,6 +518,8 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
                        ((int64_t)src->width * src->channels * in_es) % 16 == 0;
     pl->bulk_store_ok = dst->pitch_bytes % 16 == 0 && dst->image_stride_bytes % 16 == 0;
     pl->tensor_ok = pl->bulk_load_ok && encode_tiled_fn() != nullptr && std::getenv("R360_NO_TENSOR_TMA") == nullptr;
+    pl->box_family = pl->use_table ? 1 : 0;      // lane-per-column bicubic path: rows on identical banks
+    if (const char* env = std::getenv("R360_BOX_FAMILY")) pl->box_family = std::atoi(env) == 1 ? 1 : 0;
     pl->ws = static_cast<unsigned char*>(workspace);
     pl->d_header = reinterpret_cast<PlanHeader*>(pl->ws + wl.header);
     pl->d_views = reinterpret_cast<ViewDev*>(pl->ws + wl.views);
@@ -536,6 +539,7 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     P.patch_budget = pl->patch_budget; P.bulk_load_ok = pl->bulk_load_ok; P.tensor_ok = pl->tensor_ok;
     P.fill_invalid = pl->pr.lp.fill_invalid;
     P.interp = pl->pr.interp;
+    P.box_family = pl->box_family;
     P.erp = pl->pr.lp.erp;
     std::memcpy(P.lens, pl->pr.lp.lens, sizeof(P.lens));
     P.views = pl->d_views; P.plans = pl->d_plans; P.header = pl->d_header; P.fallback = pl->d_fallback;
@@ -613,7 +617,7 @@ struct TiledLauncher {
                 if (!hit) {
                     r360_plan::TmEntry e;
                     e.data = chunk.data; e.count = chunk.count; e.stride = chunk.image_stride_bytes;
-                    const int erc = encode_tensor_maps(chunk, &e.maps);
+                    const int erc = encode_tensor_maps(chunk, pl->box_family, &e.maps);
                     if (erc != R360_OK) return erc;
                     if (pl->tm_cache.size() >= 8) pl->tm_cache.erase(pl->tm_cache.begin());
                     pl->tm_cache.push_back(e);
