@@ -321,12 +321,26 @@ __device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar_saddr, uint32_t par
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_s(smem_u32(bar), parity); }
 // Wait on a barrier given by its shared-memory address (cheaper in the per-tile loop).
+#ifndef R360_WAIT_STYLE
+#define R360_WAIT_STYLE 0
+#endif
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
     if (mbar_try_wait_s(bar_saddr, parity)) return;
+#if R360_WAIT_STYLE == 1
+    // bare poll: try_wait itself suspends the warp for a hardware time slice; a watchdog every 2^20 polls
+    for (unsigned spins = 1; !mbar_try_wait_s(bar_saddr, parity); ++spins)
+        if ((spins & 0xFFFFFu) == 0u && spins > 0x4000000u) __trap();
+#elif R360_WAIT_STYLE == 2
+    for (unsigned spins = 0; !mbar_try_wait_s(bar_saddr, parity); ++spins) {
+        __nanosleep(1024);
+        if (spins > 8000000u) __trap();
+    }
+#else
     for (unsigned spins = 0; !mbar_try_wait_s(bar_saddr, parity); ++spins) {
         __nanosleep(256);
         if (spins > 8000000u) __trap();
     }
+#endif
 }
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");

@@ -287,8 +287,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    saved_stdout_fd = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL writes its version banner to file descriptor 1 when the communicator is created: keep stdout for
+        # the one JSON line by pointing fd 1 at stderr until that line is printed
+        sys.stdout.flush()
+        saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     pviews = [remap360.PerspectiveView(y, p, hf, vf, view_id=vid) for vid, y, p, hf, vf in views]
@@ -420,7 +426,10 @@ def main():
                 "views_per_s": value * 1e6 / (ns.size * ns.size), "frames_per_s": value * 1e6 / (n_views * ns.size * ns.size),
                 "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "variants": variants}
-        print(json.dumps(line))
+        if saved_stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
