@@ -48,3 +48,17 @@ def sum_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def bind_to_gpu_cpus(device_index: int) -> bool:
+    """Pin the calling thread (and the pinned host memory it allocates afterwards, by first touch) to the CPUs
+    NVML reports as closest to the GPU.  One process per GPU shares the box's host memory and PCIe root complexes;
+    without this every rank's staging buffers can land on one socket.  Returns False when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:
+        return False

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--interp", default="cubic")
     ns = ap.parse_args()
     rank, world, local_rank = env_rank()
+    bound = os.environ.get("R360_NUMA_BIND", "0") == "1" and __import__("remap360.sharding", fromlist=["x"]).bind_to_gpu_cpus(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -109,7 +110,7 @@ def main():
     if rank == 0:
         pix_per_frame = len(views) * SIZE * SIZE
         line = {"config": "BASELINE configs[2]: 600-frame 8K u8 ERP sweep, fisheyelike (10 views 1600^2), %s" % ns.interp,
-                "n_gpus": world, "frames": ns.frames, "frames_per_rank": -(-ns.frames // world), "chunk": ns.chunk,
+                "n_gpus": world, "numa_bound": bool(bound), "cpus_allowed": len(os.sched_getaffinity(0)), "frames": ns.frames, "frames_per_rank": -(-ns.frames // world), "chunk": ns.chunk,
                 "resident": {"ms": resident_ms, "frames_per_s": ns.frames / (resident_ms * 1e-3),
                              "Mpix_per_s": ns.frames * pix_per_frame / (resident_ms * 1e-3) / 1e6,
                              "hbm_bytes_frames_per_rank": int(frames.numel())},
