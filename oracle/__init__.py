@@ -18,7 +18,9 @@ What is restated here (reference = /root/reference, cited file:line):
                     :2031-2038 (opencv-python, requirements.txt; 4.13.0 in this
                     image): 1/32-px fraction quantisation, a=-0.75 cubic,
                     15-bit fixed-point u8 tables, per-tap constant border.
-* ``remap_c.c``     the same sampler in plain C (fast enough for full frames).
+* ``color.py``      the dual-fisheye input colour pipeline (DF:568-725, pinned bit-exactly) and the
+                    formula of the cutter's video colour filter (PC:299-309).
+* ``footprint.py``  distinct source pixels touched per view set (the algorithmic bytes of the roofline).
 
 Pinning status
 --------------
@@ -30,10 +32,16 @@ Pinning status
   (fixtures in ``tests/golden/``).
 * view planner: PINNED against ``build_view_jobs`` outputs of the reference
   (fixtures in ``tests/golden/``).
-* ERP maps: PARITY UNPINNED at the ffmpeg boundary.  The reference's ERP
-  arithmetic lives in FFmpeg's ``v360`` filter (no pinned version, binary absent
-  from this image); the oracle follows the in-repo
-  float64 statement of the same geometry (gs360_GUI.py:377-424), and that code
-  is pinned only through the shared rotation helper that the dual-fisheye
-  fixtures exercise.
+* ERP maps: PINNED against the reference's in-repo geometry -- ``direction_from_uv``
+  / ``rotate_pitch`` / ``rotate_yaw`` / ``lonlat_to_xy`` (gs360_GUI.py:342-424) are
+  taken out of gs360_GUI.py's syntax tree (the module itself needs tkinter) and run
+  by ``tests/golden/make_golden.py``; ``tests/golden/gui_geometry.npz`` holds their
+  outputs for ten views (presets, seam, poles) and both the oracle and the kernels
+  are compared with it.  What stays UNPINNED is the boundary to FFmpeg's ``v360``
+  filter itself (third party, no pinned version, binary absent from this image,
+  SURVEY.md section 8c): its pixel-centre convention (available as ``convention="v360"``)
+  and its own cubic kernel cannot be checked here.
+* video colour step (``color.py``, formula level) and the v360 fisheye inputs /
+  outputs follow published formulas; same ffmpeg caveat.
+* ``remap_c.c`` is not written: the NumPy sampler finishes every test size in seconds.
 """

@@ -35,6 +35,9 @@ df_cli_outputs.npz      ``parse_arguments``; stdout / stderr / exit code of ``ma
                         usage errors (temp paths replaced by <TMP>); and one real run on two tiny
                         smooth X/Y pairs (LUT, undistorted fisheye, 10 views + masks as PNG) whose
                         input and output images are stored for the end-to-end parity test
+gui_geometry.npz        lon / lat and equirectangular pixel coordinates of 33 x 33 pixel centres of ten views,
+                        computed by the reference's own ``direction_from_uv`` / ``lonlat_to_xy`` (gs360_GUI.py:342-424,
+                        taken out of the file's syntax tree because the module needs tkinter to import)
 df_metadata.json        pose / COLMAP / Metashape-XML export of the dual-fisheye tool on synthetic aligned projects:
                         cameras as loaded (chunk / component similarity), label pairs, pose frames, the COLMAP
                         model, the written files, and stdout / files of ``main()`` runs with --metadata-only
@@ -569,6 +572,42 @@ def dump_df_metadata(df):
     (HERE / "df_metadata.json").write_text(json.dumps(out, indent=1) + "\n")
 
 
+def dump_gui_geometry(reference_dir):
+    """The in-repo float64 statement of the view geometry (gs360_GUI.py:342-395, :419-424), evaluated by the
+    reference's OWN functions.  gs360_GUI.py cannot be imported here (it needs tkinter), so the five pure functions
+    are taken out of its syntax tree and compiled as they stand."""
+    import ast
+    import typing
+    src = (pathlib.Path(reference_dir) / "gs360_GUI.py").read_text()
+    wanted = ("normalize_vector", "rotate_pitch", "rotate_yaw", "direction_from_uv", "lonlat_to_xy")
+    tree = ast.parse(src)
+    picked = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name in wanted]
+    assert sorted(n.name for n in picked) == sorted(wanted)
+    env = {"math": math, "Tuple": typing.Tuple, "Sequence": typing.Sequence, "Iterable": typing.Iterable, "List": typing.List}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), "gs360_GUI.py", "exec"), env)
+    views = [(0.0, 0.0, 104.2500326978036, 104.2500326978036), (45.0, 30.0, 104.2500326978036, 104.2500326978036),
+             (-135.0, -30.0, 104.2500326978036, 104.2500326978036), (180.0, 0.0, 93.2731514, 93.2731514),
+             (179.9, 0.0, 112.6198649, 112.6198649), (0.0, 90.0, 112.6198649, 112.6198649), (0.0, -90.0, 100.0, 80.0),
+             (123.4, 56.7, 60.0, 45.0), (-70.0, -60.0, 120.0, 90.0), (320.0, 0.0, 104.25, 104.25)]
+    n = 33                                              # 33 x 33 pixel centres of an n x n view: u = (2i + 1) / n - 1
+    uv = [(2 * i + 1) / n - 1.0 for i in range(n)]
+    out = {"views": np.array(views), "uv": np.array(uv)}
+    for (W, H) in ((7680, 3840), (3840, 1920)):
+        xs = np.empty((len(views), n, n)); ys = np.empty_like(xs); lons = np.empty_like(xs); lats = np.empty_like(xs)
+        for k, (yaw, pitch, hf, vf) in enumerate(views):
+            # the clamps of sample_view_segments (GUI:437-440)
+            hfr, vfr = math.radians(min(max(hf, 1e-3), 179.9)), math.radians(min(max(vf, 1e-3), 179.9))
+            for j, v in enumerate(uv):
+                for i, u in enumerate(uv):
+                    lon, lat = env["direction_from_uv"](u, v, hfr, vfr, math.radians(yaw), math.radians(pitch))
+                    x, y = env["lonlat_to_xy"](lon, lat, W, H)
+                    xs[k, j, i], ys[k, j, i], lons[k, j, i], lats[k, j, i] = x, y, lon, lat
+        out["x_%d" % W], out["y_%d" % W] = xs, ys
+        if W == 7680:
+            out["lon"], out["lat"] = lons, lats
+    np.savez_compressed(HERE / "gui_geometry.npz", **out)
+
+
 def dump_v2f(reference_dir):
     """The v360 filter string gs360_Video2Frames.py builds for --fisheye-perspective (V2F:467-487).  The code
     sits inside main(); the block is cut out of the reference's source text and executed as it stands."""
@@ -598,6 +637,9 @@ def main():
     ap.add_argument("reference", nargs="?", default="/root/reference")
     ap.add_argument("--only", default="", help="regenerate one family only (v2f)")
     ns = ap.parse_args()
+    if ns.only == "gui_geometry":
+        dump_gui_geometry(ns.reference)
+        return
     if ns.only in ("v2f", "df_metadata"):
         sys.dont_write_bytecode = True
         sys.path.insert(0, str(pathlib.Path(ns.reference) / "cli_tools"))
@@ -618,6 +660,7 @@ def main():
     dump_df_cli(df)
     dump_cv2()
     dump_v2f(ns.reference)
+    dump_gui_geometry(ns.reference)
     dump_df_metadata(df)
     for p in sorted(HERE.glob("*.json")) + sorted(HERE.glob("*.npz")):
         print("%9d  %s" % (p.stat().st_size, p.name))

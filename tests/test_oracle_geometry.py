@@ -199,3 +199,46 @@ def test_fisheye_output_is_equidistant_about_the_view_axis():
     assert np.allclose(r2[c, c], r1[1, 1], atol=1e-12)
     with pytest.raises(ValueError):
         g.camera_rays(4, 4, 90, 90, 0, 0, projection="nope")
+
+
+# --- the reference's own functions (gs360_GUI.py:342-424), recorded by tests/golden/make_golden.py ----------
+
+def _wrap_diff(a, b, period):
+    d = a - b
+    return d - period * np.rint(d / period)
+
+
+def test_erp_map_equals_the_reference_gui_functions(golden_dir):
+    """33 x 33 pixel centres of ten views (presets, seam, poles, odd angles): the oracle's halfpixel map is the
+    reference's edge-origin pixel coordinate minus 0.5; longitude modulo the panorama width, and not compared
+    where the ray points at a pole (there it is arbitrary)."""
+    gold = np.load(golden_dir / "gui_geometry.npz")
+    n = len(gold["uv"])
+    for W, H in ((7680, 3840), (3840, 1920)):
+        for k, (yaw, pitch, hf, vf) in enumerate(gold["views"]):
+            mx, my = g.erp_map64(W, H, n, n, yaw, pitch, hf, vf, "halfpixel")
+            ex, ey = gold["x_%d" % W][k] - 0.5, gold["y_%d" % W][k] - 0.5
+            assert np.abs(my - ey).max() < 1e-7, (W, yaw, pitch)
+            off_pole = np.abs(np.abs(gold["lat"][k]) - math.pi / 2) > 1e-6
+            assert off_pole.mean() > 0.99
+            assert np.abs(_wrap_diff(mx, ex, W))[off_pole].max() < 1e-6, (W, yaw, pitch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["direct", "tiled"])
+def test_device_coordinates_equal_the_reference_gui_functions(golden_dir, path):
+    """The kernels' float64 coordinates against the same recorded reference values (bar: 1e-3 px)."""
+    torch = pytest.importorskip("torch")
+    import remap360
+    gold = np.load(golden_dir / "gui_geometry.npz")
+    n = len(gold["uv"])
+    views = [remap360.PerspectiveView(y, p, hf, vf) for y, p, hf, vf in gold["views"]]
+    for W, H in ((7680, 3840), (3840, 1920)):
+        got = remap360.sample_coordinates(views, (n, n), erp_size=(W, H), convention="halfpixel", path=path)
+        x64, y64 = got["x64"].cpu().numpy(), got["y64"].cpu().numpy()
+        for k in range(len(views)):
+            ex, ey = gold["x_%d" % W][k] - 0.5, gold["y_%d" % W][k] - 0.5
+            # at a pole the row clamps and the longitude is arbitrary: compare away from it
+            off_pole = np.abs(np.abs(gold["lat"][k]) - math.pi / 2) > 1e-3
+            assert np.abs(np.clip(y64[k], 0, H - 1) - np.clip(ey, 0, H - 1)).max() < 1e-3
+            assert np.abs(_wrap_diff(x64[k], ex, W))[off_pole].max() < 1e-3, (W, k)
