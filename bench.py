@@ -379,6 +379,34 @@ def main():
         variants[other] = {"value": out_pix_step * world / (o_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": o_ms,
                            "roofline": roofline_for(other, o_steps)}
 
+        # content class (S) of SURVEY.md section 8(d): smooth band-limited frames (eight low-frequency sinusoids
+        # in lon / lat per channel, continuous across the seam) instead of noise; the kernels have no
+        # data-dependent control flow, so the number should not move
+        keep = frames[0].clone()
+        lon = torch.linspace(0.0, 2.0 * torch.pi, ERP_W + 1, device=dev)[:-1]
+        lat = torch.linspace(-0.5 * torch.pi, 0.5 * torch.pi, ERP_H, device=dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(4321 + rank)
+        smooth = torch.zeros((ERP_H, ERP_W, CHANNELS), dtype=torch.float32, device=dev)
+        for _ in range(8):
+            kx = torch.randint(1, 9, (CHANNELS,), device=dev, generator=gen).float()
+            ky = torch.randint(1, 9, (CHANNELS,), device=dev, generator=gen).float()
+            ph = torch.rand((2, CHANNELS), device=dev, generator=gen) * 2.0 * torch.pi
+            smooth += torch.sin(lon[None, :, None] * kx + ph[0]) * torch.cos(lat[:, None, None] * ky + ph[1])
+        smooth = ((smooth / 16.0 + 0.5).clamp_(0.0, 1.0) * 255.0).round_().to(torch.uint8)
+        for f in range(ns.frames):
+            frames[f] = smooth
+        s_ms, _, _, _ = timed(ns.interp, max(3, ns.steps // 4), 3, False)
+        variants["content_smooth"] = {"value": out_pix_step * world / (s_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                                      "ms_per_step": s_ms, "interp": ns.interp,
+                                      "content": "sum of 8 low-frequency sinusoids per channel, seam-continuous"}
+        for f in range(ns.frames):              # back to the seeded noise frames for the end-to-end leg
+            g = torch.Generator(device=dev)
+            g.manual_seed(1234 + rank * ns.frames + f)
+            frames[f] = torch.randint(0, 256, (ERP_H, ERP_W, CHANNELS), dtype=torch.uint8, device=dev, generator=g)
+        assert torch.equal(frames[0], keep)
+        del keep, smooth
+
     # ------------------------------------------------------------------ end to end (host buffers)
     e2e = None
     if not ns.no_e2e:
