@@ -16,6 +16,7 @@ the reference building its maps once and applying them to every frame (DF:1857-1
 from __future__ import annotations
 
 import ctypes
+import threading
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence, Tuple
@@ -209,6 +210,7 @@ class Plan:
 
 _PLAN_CACHE: "OrderedDict[tuple, Plan]" = OrderedDict()
 _PLAN_CACHE_SIZE = 32
+_PLAN_LOCK = threading.Lock()       # the job runners call in from several host threads
 
 
 def _layout_key(im: Images, aligned: bool):
@@ -227,10 +229,11 @@ def get_plan(src: Images, dst: Images, views: Sequence[PerspectiveView], opt: Op
            tuple(_view_key(v) for v in views),
            None if calibs is None else tuple(tuple(getattr(c, n) for n, _ in FisheyeCalib._fields_[:15]) for c in calibs),
            (opt.interp, opt.convention, opt.fill_invalid, opt.border_value, opt.out_dtype))
-    plan = _PLAN_CACHE.get(key)
-    if plan is not None:
-        _PLAN_CACHE.move_to_end(key)
-        return plan
+    with _PLAN_LOCK:
+        plan = _PLAN_CACHE.get(key)
+        if plan is not None:
+            _PLAN_CACHE.move_to_end(key)
+            return plan
     nbytes = lib.r360_plan_workspace_bytes(len(views), dst.width, dst.height)
     workspace = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
     handle = ctypes.c_void_p()
@@ -255,14 +258,17 @@ def get_plan(src: Images, dst: Images, views: Sequence[PerspectiveView], opt: Op
     tiles, nfb = ctypes.c_int32(), ctypes.c_int32()
     _lib.check(lib.r360_plan_info(handle, ctypes.byref(tiles), ctypes.byref(nfb)))
     plan = Plan(handle.value, workspace, tiles.value, nfb.value, len(views))
-    _PLAN_CACHE[key] = plan
-    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-        _PLAN_CACHE.popitem(last=False)
+    with _PLAN_LOCK:
+        # two threads may have built the same plan at once: both are valid, the later one stays cached
+        _PLAN_CACHE[key] = plan
+        while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+            _PLAN_CACHE.popitem(last=False)
     return plan
 
 
 def clear_plan_cache() -> None:
-    _PLAN_CACHE.clear()
+    with _PLAN_LOCK:
+        _PLAN_CACHE.clear()
 
 
 def _run(src: Images, dst: Images, views, opt: Options, path: str, device, stream, calibs=None) -> None:
