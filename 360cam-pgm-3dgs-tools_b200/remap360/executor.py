@@ -114,9 +114,21 @@ def _job_view(job: "ParsedJob"):
     return api.PerspectiveView(job.yaw, job.pitch, job.hfov, job.vfov, roll_deg=job.roll)
 
 
-def _write_image(path: pathlib.Path, image, jpeg_quality: int) -> None:
+def widen_for_pix_fmt(image, pix_fmt: Optional[str]):
+    """``-pix_fmt rgb48le`` (PC:346: PNG / TIFF views of a video whose source has more than 8 bits): the reference's
+    chain computes in 8-bit yuv444p (PC:306-309) and lets swscale widen the result, which replicates the byte
+    (v -> v * 257).  8-bit images for any other pixel format are written as they are."""
+    if pix_fmt == "rgb48le" and image.dtype.itemsize == 1:
+        import numpy as np
+        return image.astype(np.uint16) * np.uint16(257)
+    return image
+
+
+def _write_image(path: pathlib.Path, image, jpeg_quality: int, pix_fmt: Optional[str] = None) -> None:
     import cv2
     path.parent.mkdir(parents=True, exist_ok=True)
+    if path.suffix.lower() in (".png", ".tif", ".tiff"):
+        image = widen_for_pix_fmt(image, pix_fmt)
     params: List[int] = []
     if path.suffix.lower() in (".jpg", ".jpeg"):
         params = [int(cv2.IMWRITE_JPEG_QUALITY), int(jpeg_quality)]

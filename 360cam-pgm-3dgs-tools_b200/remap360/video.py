@@ -93,7 +93,7 @@ def run_video_jobs(source, jobs: Sequence, stop_event=None) -> List[Tuple[int, s
                 views_host = out.numpy()
                 for col, k in enumerate(usable):
                     path = str(jobs[k].output) % n if "%" in str(jobs[k].output) else str(jobs[k].output)
-                    _write_image(__import__("pathlib").Path(path), views_host[col], jobs[k].jpeg_quality)
+                    _write_image(__import__("pathlib").Path(path), views_host[col], jobs[k].jpeg_quality, jobs[k].pix_fmt)
             cancelled = stop_event is not None and stop_event.is_set()
             for k in usable:
                 results[k] = (130, "") if cancelled else (0, "")

@@ -124,3 +124,19 @@ def test_calibration_xml_loader(tmp_path, golden_df):
     got = sensors["0"]
     for key in ("width", "height", "f", "cx", "cy", "k1", "k2", "k3", "k4", "p1", "p2", "b1", "b2", "model_type"):
         assert getattr(got, key) == want[key], key
+
+
+def test_rgb48le_outputs_replicate_the_byte(tmp_path):
+    """PNG / TIFF views of a >8-bit video are 16-bit files holding the 8-bit result widened by swscale's rule."""
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    img = np.arange(3 * 4 * 3, dtype=np.uint8).reshape(3, 4, 3) * 7
+    wide = executor.widen_for_pix_fmt(img, "rgb48le")
+    assert wide.dtype == np.uint16 and np.array_equal(wide, img.astype(np.uint16) * 257)
+    assert wide.max() <= 65535 and executor.widen_for_pix_fmt(np.full((1, 1, 3), 255, np.uint8), "rgb48le").max() == 65535
+    assert executor.widen_for_pix_fmt(img, "rgb24") is img and executor.widen_for_pix_fmt(img, None) is img
+    executor._write_image(tmp_path / "v.png", img, 100, "rgb48le")
+    back = cv2.imread(str(tmp_path / "v.png"), cv2.IMREAD_UNCHANGED)
+    assert back.dtype == np.uint16 and np.array_equal(back, wide)
+    executor._write_image(tmp_path / "v.jpg", img, 100, "rgb48le")              # JPEG stays 8-bit
+    assert cv2.imread(str(tmp_path / "v.jpg"), cv2.IMREAD_UNCHANGED).dtype == np.uint8
