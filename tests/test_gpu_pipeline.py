@@ -143,3 +143,61 @@ def test_streaming_remapper_keeps_order_and_matches_batched_call(r360):
     pinned = [f.pin_memory() for f in frames[:3]]
     again = [res.clone() for res in sr.run(pinned)]
     assert all(torch.equal(again[k], ref[k]) for k in range(3))
+
+
+@pytest.mark.parametrize("ext,depth,keep", [("png", 8, False), ("png", 10, True), ("jpg", 8, False)])
+def test_video_source_is_decoded_once_colour_converted_and_cut(r360, tmp_path, monkeypatch, ext, depth, keep):
+    """A video source (PC's video branch): frames picked with ffmpeg's fps= rule, the job's colorspace filter applied
+    on the device before the remap, views written as <stem>_%07d_<id>.<ext> from 0; a >8-bit source asks for
+    rgb48le (16-bit PNG holding the widened 8-bit result)."""
+    cv2 = pytest.importorskip("cv2")
+    from remap360 import color, executor, perspcut as pc, video
+    path = tmp_path / "clip.avi"
+    wr = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"MJPG"), 12.0, (512, 256))
+    if not wr.isOpened():
+        pytest.skip("OpenCV cannot write MJPG AVI here")
+    yy, xx = np.mgrid[0:256, 0:512].astype(np.float64)
+    for n in range(12):
+        frame = np.stack([127 + 100 * np.sin((xx + 17 * n) / 512 * 6.2832 * (k + 1)) * np.cos(yy / 256 * 3.1416 * (k + 1))
+                          for k in range(3)], axis=-1).astype(np.uint8)
+        wr.write(frame)
+    wr.release()
+    cap = cv2.VideoCapture(str(path))
+    decoded = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        decoded.append(fr)
+    cap.release()
+    assert len(decoded) == 12
+    argv = ["-i", str(path), "--preset", "2views", "--size", "80", "--ext", ext, "-f", "4"] + (["--keep-rec709"] if keep else [])
+    args = pc.create_arg_parser().parse_args(argv)
+    args.size_explicit, args.hfov_explicit, args.focal_mm_explicit = True, False, False
+    args.input_is_video, args.video_bit_depth = True, depth
+    res = pc.build_view_jobs(args, [path], tmp_path / "out")
+    assert all("colorspace=iall=bt709:all=smpte170m" in " ".join(cmd) for cmd, _s, _d in res.jobs)
+    done = list(executor.run_jobs(res.jobs, pc.stop_event, workers=1))
+    assert len(done) == len(res.jobs) and all(rc == 0 for _job, (rc, err) in done), done
+    picked = video._select_frames(12, 12.0, 4.0, None, None)
+    assert picked == [0, 3, 6, 9] or len(picked) in (4, 5)
+    for spec in res.view_specs:
+        for n, src_idx in enumerate(picked):
+            name = spec.output_name % n if "%" in spec.output_name else spec.output_name
+            got = cv2.imread(str(tmp_path / "out" / name), cv2.IMREAD_UNCHANGED)
+            assert got is not None, name
+            conv = color.convert_video_color(torch.from_numpy(decoded[src_idx]).cuda()[None], keep_rec709=keep,
+                                             channel_order="bgr")[0].cpu().numpy()
+            mx, my = geo.erp_map64(512, 256, 80, 80, spec.yaw_deg, spec.pitch_deg, spec.hfov_deg, spec.vfov_deg)
+            want = sampler.sample(conv, mx, my, "cubic", "erp")
+            if ext == "png" and depth > 8:
+                assert got.dtype == np.uint16 and np.array_equal(got % 257, np.zeros_like(got))
+                got = (got // 257).astype(np.uint8)
+            assert got.dtype == np.uint8 and got.shape == want.shape
+            tol = 1 if ext == "png" else 12                      # JPEG views: codec error on top
+            assert (np.abs(got.astype(int) - want.astype(int)) <= tol).mean() >= 0.99, (name, ext)
+    assert not (tmp_path / "out" / (res.view_specs[0].output_name % len(picked))).exists()
+    # the colour step can be switched off: frames then stay in the decoder's BGR values
+    monkeypatch.setenv("R360_VIDEO_COLOR", "0")
+    done = list(executor.run_jobs(res.jobs[:1], pc.stop_event, workers=1))
+    assert done[0][1][0] == 0
