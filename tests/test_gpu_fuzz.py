@@ -2,6 +2,8 @@
 types, output sizes that are not multiples of the tile, yaw / pitch / roll / FOV anywhere including the poles and the
 seam, both output projections, every interpolation -- tiled path against direct path against the oracle."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -10,6 +12,10 @@ pytestmark = pytest.mark.gpu
 
 from oracle import geometry as geo  # noqa: E402
 from oracle import sampler  # noqa: E402
+
+# R360_FUZZ_SEEDS=300 widens the sweep (used once per round on the GPU box; the default keeps the suite short)
+N_ERP = int(os.environ.get("R360_FUZZ_SEEDS", "24"))
+N_FISHEYE = max(10, N_ERP // 2)
 
 
 def _cuda(a):
@@ -30,7 +36,7 @@ def _close_fraction(a, b):
     return float((np.abs(a.astype(np.int64) - b.astype(np.int64)) <= 1).mean())
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(N_ERP))
 def test_random_erp_configurations(seed):
     import remap360 as r360
     rng = np.random.default_rng(1000 + seed)
@@ -62,10 +68,16 @@ def test_random_erp_configurations(seed):
         mx, my = geo.erp_map64(W, H, ow, oh, v.yaw_deg, v.pitch_deg, v.hfov_deg, v.vfov_deg, convention, v.roll_deg,
                                v.projection)
         want = sampler.sample(src, mx, my, interp, "erp")
-        assert _close_fraction(direct[k], want) >= 0.995, (seed, k, interp, dtype, W, H, ow, oh, v)
+        # a ray that points exactly at a pole (the centre pixel of an odd-sized view with pitch = +-90) has no
+        # defined longitude: atan2(0, 0)-level noise decides the column, so that pixel is not compared
+        y_lo, y_hi = (-0.5, H - 0.5) if convention == "halfpixel" else (0.0, H - 1.0)
+        at_pole = (my <= y_lo + 1e-9) | (my >= y_hi - 1e-9)
+        assert at_pole.sum() <= 1
+        keep = ~at_pole
+        assert _close_fraction(direct[k][keep], want[keep]) >= 0.995, (seed, k, interp, dtype, W, H, ow, oh, v)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(N_FISHEYE))
 def test_random_fisheye_configurations(seed):
     import remap360 as r360
     rng = np.random.default_rng(5000 + seed)
@@ -76,6 +88,8 @@ def test_random_fisheye_configurations(seed):
                k4=float(rng.uniform(-3e-4, 3e-4)), p1=float(rng.uniform(-1e-3, 1e-3)), p2=float(rng.uniform(-1e-3, 1e-3)),
                b1=float(rng.uniform(-2, 2)), b2=float(rng.uniform(-1, 1)))
     fov = float(rng.uniform(120, 200))
+    if seed % 3 == 2:                                   # v360's equidistant lens law next to Metashape's equisolid
+        cal["model"] = "equidistant"
     calib = r360.FisheyeCalibration(**cal, lens_fov_deg=fov)
     interp = ["nearest", "linear", "cubic", "lanczos4"][int(rng.integers(0, 4))]
     bv, fill = int(rng.integers(0, 255)), bool(rng.integers(0, 2))
