@@ -16,6 +16,12 @@
 #define R360_CUBIC_LDS64 0   // measured on B200: 103 vs 105 Gpix/s -- fewer wavefronts, but the selects cost more
 #endif
 
+#ifndef R360_WHATIF
+#define R360_WHATIF 0       // 1 / 2 / 3: bound-finding experiments that produce WRONG pixels (never shipped)
+#endif
+#ifndef R360_PACK_SAT
+#define R360_PACK_SAT 1      // measured: 103.2 -> 104.8 Gpix/s, identical output
+#endif
 #ifndef R360_TABLE_SWIZZLE
 #define R360_TABLE_SWIZZLE 0
 #endif
@@ -34,6 +40,21 @@ __host__ __device__ __forceinline__ uint32_t table_entry_index(uint32_t fy, uint
 #endif
 }
 
+#ifndef R360_CXX_LOADS
+#define R360_CXX_LOADS 0
+#endif
+#if R360_CXX_LOADS
+// Shared-memory loads the compiler can see (ordinary loads from the dynamic shared array, addressed by the
+// 32-bit shared-window address): unlike `asm volatile` they may be scheduled ahead of the arithmetic and the
+// store of the previous pixel, which is where the instruction-level parallelism of the sampling loops comes from.
+extern __shared__ __align__(128) unsigned char r360_dyn_smem[];
+__device__ __forceinline__ const unsigned char* smem_at(uint32_t saddr) {
+    return r360_dyn_smem + (saddr - (uint32_t)__cvta_generic_to_shared(r360_dyn_smem));
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { return *reinterpret_cast<const uint32_t*>(smem_at(saddr)); }
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) { return *reinterpret_cast<const uint2*>(smem_at(saddr)); }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) { return *reinterpret_cast<const uint4*>(smem_at(saddr)); }
+#else
 __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
@@ -49,6 +70,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
     return v;
 }
+#endif
 __device__ __forceinline__ int dp2a_lo_s16_u8(uint32_t w_pair, uint32_t bytes, int acc) {
     int d;
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w_pair), "r"(bytes), "r"(acc));
@@ -109,9 +131,17 @@ __device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, 
     const bool odd = (addr & 4u) != 0;
 #endif
     const uint32_t wt = table_saddr + table_entry_index(fy, fx) * 16u;
+#if R360_WHATIF == 1 || R360_WHATIF == 3
+    // what-if (wrong results): no weight-table traffic -- bounds what a conflict-free / table-free design could gain
+    const uint4 wa = make_uint4(wt, fx, fy, wt ^ fy), wb = make_uint4(fy, wt, fx, wt + fx);
+#else
     const uint4 wa = lds128(wt), wb = lds128(wt + 16384u);      // plane of rows 0,1 | plane of rows 2,3: (w0|w1<<16, w2|w3<<16) each
+#endif
     const uint32_t wrow[4][2] = {{wa.x, wa.y}, {wa.z, wa.w}, {wb.x, wb.y}, {wb.z, wb.w}};
     int r = 16384, g = 16384, b = 16384;
+#if R360_WHATIF == 2 || R360_WHATIF == 3
+    uint32_t wq[4];
+#endif
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
 #if R360_CUBIC_LDS64
@@ -122,8 +152,16 @@ __device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, 
         const uint32_t q0 = odd ? lo.y : lo.x, q1 = odd ? hi.x : lo.y, q2 = odd ? hi.y : hi.x, q3 = odd ? w4 : hi.y;
         a8 += pitch;
 #else
+#if R360_WHATIF == 2 || R360_WHATIF == 3
+        // what-if (wrong results): one tap row loaded, reused for the other three -- bounds a design with 4x fewer tap loads
+        static_assert(true, "");
+        uint32_t q0, q1, q2, q3;
+        if (ky == 0) { q0 = lds32(a4); q1 = lds32(a4 + 4); q2 = lds32(a4 + 8); q3 = lds32(a4 + 12); wq[0] = q0; wq[1] = q1; wq[2] = q2; wq[3] = q3; }
+        else { q0 = wq[0] + ky; q1 = wq[1] ^ ky; q2 = wq[2] + ky; q3 = wq[3] ^ ky; }
+#else
         const uint32_t q0 = lds32(a4), q1 = lds32(a4 + 4), q2 = lds32(a4 + 8), q3 = lds32(a4 + 12);
         a4 += pitch;
+#endif
 #endif
         const uint32_t p0 = __funnelshift_r(q0, q1, sh);       // R0 G0 B0 R1
         const uint32_t p1 = __funnelshift_r(q1, q2, sh);       // G1 B1 R2 G2
@@ -135,10 +173,18 @@ __device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, 
         g = dp2a_hi_s16_u8(wrow[ky][1], gg, dp2a_lo_s16_u8(wrow[ky][0], gg, g));
         b = dp2a_hi_s16_u8(wrow[ky][1], bb, dp2a_lo_s16_u8(wrow[ky][0], bb, b));
     }
+#if R360_PACK_SAT
+    // saturate to 0..255 and pack in two instructions (cvt.pack.sat: bytes {a, b} on top of the low half of c)
+    uint32_t hi, out;                                  // d = (c << 16) | sat(a) << 8 | sat(b)
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(0), "r"(b >> 15), "r"(0));            // . . 0 B
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(g >> 15), "r"(r >> 15), "r"(hi));    // 0 B G R
+    return out;
+#else
     r = min(max(r >> 15, 0), 255);
     g = min(max(g >> 15, 0), 255);
     b = min(max(b >> 15, 0), 255);
     return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+#endif
 }
 
 // Four RGB pixels (each R | G<<8 | B<<16) -> three packed words = 12 output bytes.

@@ -442,9 +442,16 @@ struct TiledParams {
 };
 
 constexpr int kSlots = 4;                               // work items in flight per block
-constexpr int kConsumerWarps = 8;
+constexpr int kConsumerWarps = 8;                       // warps of the 4-rows-per-warp mapping (256 threads <-> 32 x 8 lanes)
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kTiledThreads = kConsumerThreads + 32;
+// Experiment switch: the 8-bit bicubic kernel with 16 consumer warps (two tile rows each on the lane-per-column
+// tiles; seam / fill / partial tiles stay with the first eight warps, the others only release the patch).
+// Measured on B200: 99.5 vs 103.0 Gpix/s with 8 warps -- the kernel is not short of warps.
+#ifndef R360_CUBIC_WARPS
+#define R360_CUBIC_WARPS 8
+#endif
+__host__ __device__ constexpr int consumer_warps(bool cubic_u8) { return cubic_u8 ? R360_CUBIC_WARPS : kConsumerWarps; }
+constexpr int kMaxTiledThreads = (R360_CUBIC_WARPS > kConsumerWarps ? R360_CUBIC_WARPS : kConsumerWarps) * 32 + 32;
 
 struct SlotInfo {            // per item, written by the producer
     uint32_t patch_saddr;    // shared-memory address of the patch
@@ -461,8 +468,9 @@ struct SlotInfo {            // per item, written by the producer
 static_assert(sizeof(SlotInfo) == 64, "SlotInfo layout");
 
 constexpr int kTableBytes = 32 * 32 * 16 * 2;
-// barriers (64) + slot info + per-warp row coefficients (32 rows x 12 floats) + plan records
-constexpr int kTiledFixedSmem = (64 + kSlots * 64 + 1536 + kSlots * 368 + 127) / 128 * 128;      // 3456
+// barriers (64) + slot info + per-warp row coefficients (32 rows x 12 floats, once for each of the two thread
+// mappings: a warp owns different tile rows in them and warps are not in step) + plan records
+constexpr int kTiledFixedSmem = (64 + kSlots * 64 + 2 * 1536 + kSlots * 368 + 127) / 128 * 128;
 static_assert(kTiledFixedSmem % 128 == 0 && kTableBytes % 128 == 0, "ring alignment");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -477,14 +485,15 @@ struct TensorMaps {
 };
 
 template <int INTERP, typename TIn, typename TOut>
-__global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid_constant__ TiledParams P,
+__global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __grid_constant__ TiledParams P,
                                                                     const __grid_constant__ TensorMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [kSlots]
     uint64_t* empty = full + kSlots;                               // [kSlots]
     SlotInfo* slots = reinterpret_cast<SlotInfo*>(smem + 64);      // [kSlots]
     float* rowc = reinterpret_cast<float*>(smem + 64 + kSlots * 64);             // [32 rows][12], per-warp regions
-    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 64 + kSlots * 64 + 1536);   // [kSlots]
+    float* rowc_col = rowc + kTile * 12;                                         // the same for the lane-per-column mapping
+    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 64 + kSlots * 64 + 2 * 1536);   // [kSlots]
     unsigned char* table = smem + kTiledFixedSmem;
     unsigned char* stage0 = table + (P.use_table ? kTableBytes : 0);
     unsigned char* ring = stage0 + P.out_stage_bytes;
@@ -492,26 +501,28 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
     constexpr bool kFastU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
                              (INTERP == kLinear || INTERP == kCubic);
     constexpr bool kFastU16 = std::is_same<TIn, uint16_t>::value && (INTERP == kLinear || INTERP == kCubic);
+    constexpr int kCW = consumer_warps(kFastU8 && INTERP == kCubic);       // consumer warps of this instantiation
+    constexpr int kRPW = kTile / kCW;                                      // tile rows per warp on the lane-per-column path
     const int tid = threadIdx.x;
     const int n_tiles = P.tiles_x * P.tiles_y;
     const int total = P.n_groups * P.n_views * n_tiles;             // the host keeps this below 2^31
 
     if (tid == 0) {
-        for (int q = 0; q < kSlots; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], kConsumerWarps); }
+        for (int q = 0; q < kSlots; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], kCW); }
         fence_mbar_init();
     }
     if (P.use_table) {
         const int4* src = reinterpret_cast<const int4*>(g_tables.cubic_fixed);
         // Two planes (tap rows 0,1 | rows 2,3) with a 16-byte entry stride: a warp's 32 random entries
         // then spread over all 8 bank groups instead of the 4 a 32-byte stride would reach.
-        for (int q = tid; q < kTableBytes / 16; q += kTiledThreads)
+        for (int q = tid; q < kTableBytes / 16; q += kCW * 32 + 32)
             reinterpret_cast<int4*>(table)[table_entry_index((uint32_t)q >> 6, ((uint32_t)q >> 1) & 31u) + (q & 1) * (kTableBytes / 32)] = __ldg(src + q);
     }
     __syncthreads();
 
-    if (tid >= kConsumerThreads) {
+    if (tid >= kCW * 32) {
         // ================= producer warp: keep it short, it is the serial part of the pipeline ======
-        const int lane = tid - kConsumerThreads;
+        const int lane = tid - kCW * 32;
         PatchRing ringst;                // identical in every lane
         int oldest = 0, k = 0;
         const uint64_t keep = l2_policy_evict_last();
@@ -581,7 +592,11 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
                 si.dst_tile = si.dst_off + (long long)j0 * P.dst.pitch + (long long)i0 * P.channels * (int)sizeof(TOut);
                 si.pad = 0;
                 slots[slot] = si;
+#if R360_WHATIF == 4
+                const uint32_t patch_bytes = (mode == kModeFast || !staged) ? 0u : (uint32_t)(rows * row_bytes);   // what-if: no tensor boxes
+#else
                 const uint32_t patch_bytes = !staged ? 0u : (uint32_t)(mode == kModeFast ? srows * pitch : rows * row_bytes);
+#endif
                 mbar_expect_tx(&full[slot], (uint32_t)sizeof(TilePlan) + patch_bytes);     // arrive + expect
                 bulk_g2s(&planbuf[slot], gp_cur, (uint32_t)sizeof(TilePlan), &full[slot]);
             }
@@ -589,7 +604,7 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             if (mode == kModeFast) {
                 // a few tensor boxes: 32-row boxes first, then 8-row boxes
                 const int n32 = rows / 32, n8 = ((rows % 32) + 7) / 8;
-                if (lane < n32 + n8) {
+                if (lane < n32 + n8 && R360_WHATIF != 4) {
                     const int r0 = lane < n32 ? lane * 32 : n32 * 32 + (lane - n32) * 8;
                     const CUtensorMap* tm = &maps.m[wbox * kNumBoxHeights + (lane < n32 ? 0 : 1)];
                     tensor_g2s_3d(patch + r0 * pitch, tm, xb0 >> 2, py0 + r0, cur_g * P.n_lenses + src_slot, &full[slot], keep);
@@ -652,7 +667,29 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
             continue;
         }
         const TilePlan* plan = &planbuf[slot];
-        if (mode != kModeFill) {
+        // lane-per-column tiles (8-bit RGB bicubic): whole tile inside the image, vector stores possible
+        constexpr bool kHasColumnPath = kFastU8 && (INTERP == kCubic || R360_LINEAR_MAP_B);
+        const bool column_path = kHasColumnPath && mode != kModeFill && mode != kModeFastSeam && P.channels == 3 &&
+                                 si->full_tile && P.bulk_store_ok;
+        if (kCW > kConsumerWarps && !column_path && warp >= kConsumerWarps) {
+            // the 4-rows-per-warp code below is written for eight warps: the others only release the patch
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(empty_s + slot * 8);
+            continue;
+        }
+        if (kRPW != 4 && column_path) {
+            // kRPW rows x 12 residual coefficients of this warp's rows, one task per lane
+            constexpr int kLanesPerRow = 32 / kRPW;
+            const int row = warp * kRPW + lane / kLanesPerRow, c = lane % kLanesPerRow;
+            if (c < 12) {
+                const float* K = (c < 6 ? plan->rx + c : plan->ry + (c - 6));
+                const float tr = (float)(2 * row - (kTile - 1)) * (1.0f / (kTile - 1));
+                float a = K[30];
+#pragma unroll
+                for (int l = 4; l >= 0; --l) a = fmaf(a, tr, K[l * 6]);
+                rowc_col[row * 12 + c] = a;
+            }
+        } else if (mode != kModeFill) {
             // the 12 residual coefficients of this lane's row, spread over the 8 lanes that share the row
             const float* K = plan->rx + koff0;
             float a = K[30];
@@ -669,38 +706,50 @@ __global__ void __launch_bounds__(kTiledThreads) remap_tiled_kernel(const __grid
         }
         __syncwarp();
         if constexpr (kFastU8 && (INTERP == kCubic || R360_LINEAR_MAP_B)) {
-            // ---- bicubic 8-bit RGB: lane = pixel column, 4 rows per lane -------------------------------
+            // ---- bicubic 8-bit RGB: lane = pixel column, kRPW rows per lane ----------------------------
             // Sixteen taps per pixel make this path shared-memory bound; with adjacent lanes on adjacent
             // pixels the tap loads of a warp fall into neighbouring words (few bank conflicts), and the
             // finished row leaves straight from registers: three lanes out of four hold one 32-bit
             // word of the 96-byte row after a shuffle, so the store is contiguous.
-            if (mode != kModeFill && mode != kModeFastSeam && P.channels == 3 && si->full_tile && P.bulk_store_ok) {
+            if (column_path) {
                 const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch, tab = smem_u32(table);
                 const float s = (float)(2 * lane - (kTile - 1)) * (1.0f / (kTile - 1));
                 const double axi = plan->ax[1], ayi = plan->ay[1], axj = plan->ax[2], ayj = plan->ay[2];
-                double ax_r = fma(axi, (double)lane, fma(axj, (double)(warp * 4), plan->ax[0]));
-                double ay_r = fma(ayi, (double)lane, fma(ayj, (double)(warp * 4), plan->ay[0]));
+                double ax_r = fma(axi, (double)lane, fma(axj, (double)(warp * kRPW), plan->ax[0]));
+                double ay_r = fma(ayi, (double)lane, fma(ayj, (double)(warp * kRPW), plan->ay[0]));
                 const int m = lane & 3;
-                unsigned char* out_word = P.dst.data + si->dst_tile + (long long)(warp * 4) * P.dst.pitch +
+                unsigned char* out_word = P.dst.data + si->dst_tile + (long long)(warp * kRPW) * P.dst.pitch +
                                           ((lane >> 2) * 3 + m) * 4;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float* rq = rowc + (warp * 4 + q) * 12;
+                for (int q = 0; q < kRPW; ++q) {
+                    const float* rq = (kRPW != 4 ? rowc_col : rowc) + (warp * kRPW + q) * 12;
                     const float4 c0 = *reinterpret_cast<const float4*>(rq), c1 = *reinterpret_cast<const float4*>(rq + 4),
                                  c2 = *reinterpret_cast<const float4*>(rq + 8);
                     float dx = c1.y, dy = c2.w;
                     dx = fmaf(dx, s, c1.x); dx = fmaf(dx, s, c0.w); dx = fmaf(dx, s, c0.z); dx = fmaf(dx, s, c0.y); dx = fmaf(dx, s, c0.x);
                     dy = fmaf(dy, s, c2.z); dy = fmaf(dy, s, c2.y); dy = fmaf(dy, s, c2.x); dy = fmaf(dy, s, c1.w); dy = fmaf(dy, s, c1.z);
+#if R360_WHATIF == 6
+                    const float sx = (float)ax_r + dx, sy = (float)ay_r + dy;      // what-if: no float64 in the pixel loop
+                    ax_r += 1.0;
+#else
                     const float sx = __double2float_rn(ax_r + (double)dx), sy = __double2float_rn(ay_r + (double)dy);
                     ax_r += axj; ay_r += ayj;
+#endif
                     uint32_t own;
                 if constexpr (INTERP == kCubic) own = bicubic_u8c3(bias, pitch, tab, round_bits(sx), round_bits(sy));
                 else own = bilinear_u8c3(bias, pitch, round_bits(sx), round_bits(sy));
                     const uint32_t nxt = __shfl_down_sync(0xffffffffu, own, 1);
                     const uint32_t word = (own >> (8 * m)) | (nxt << (24 - 8 * m));
-                    if (m < 3) {
-                        asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(out_word + (long long)q * P.dst.pitch), "r"(word) : "memory");
-                    }
+#if R360_WHATIF == 5
+                    if (m < 3 && word == 0x12345678u)                               // what-if: (almost) no global stores
+                        asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(out_word), "r"(word) : "memory");
+#else
+                    // three lanes out of four store: a predicated store (no divergent branch around it); the row
+                    // pointer is carried along instead of being rebuilt from the tile origin for every row
+                    asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %2, 3;\n@p st.global.cs.b32 [%0], %1;\n}"
+                                 ::"l"(out_word), "r"(word), "r"((uint32_t)m) : "memory");
+#endif
+                    out_word += P.dst.pitch;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_s(empty_s + slot * 8);

@@ -625,7 +625,9 @@ struct TiledLauncher {
                 }
                 maps = hit->maps;
             }
-            kernel<<<dim3((unsigned)grid), kTiledThreads, pl->smem_bytes, s>>>(Q, maps);
+            constexpr bool kCubicU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value && INTERP == kCubic;
+            const int threads = consumer_warps(kCubicU8) * 32 + 32;      // must equal the instantiation's kCW
+            kernel<<<dim3((unsigned)grid), threads, pl->smem_bytes, s>>>(Q, maps);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             R360_CUDA(cudaGetLastError());
         }
