@@ -655,6 +655,11 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
     const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty);
     unsigned char* stage = stage0;          // each warp only ever touches its own 4 rows of it
     TOut* stage_row = reinterpret_cast<TOut*>(stage) + (jl * kTile + il0) * P.channels;
+    // per-lane constants of the lane-per-column path (kept in registers across tiles: the int -> double
+    // conversions run on the slow conversion unit)
+    const uint32_t col_tab = smem_u32(table);
+    const float col_s = (float)(2 * lane - (kTile - 1)) * (1.0f / (kTile - 1));
+    const double col_dlane = (double)lane, col_drow = (double)(warp * kRPW);
     int k = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x, ++k) {
         const int slot = k & (kSlots - 1);
@@ -712,11 +717,11 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
             // finished row leaves straight from registers: three lanes out of four hold one 32-bit
             // word of the 96-byte row after a shuffle, so the store is contiguous.
             if (column_path) {
-                const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch, tab = smem_u32(table);
-                const float s = (float)(2 * lane - (kTile - 1)) * (1.0f / (kTile - 1));
+                const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch, tab = col_tab;
+                const float s = col_s;
                 const double axi = plan->ax[1], ayi = plan->ay[1], axj = plan->ax[2], ayj = plan->ay[2];
-                double ax_r = fma(axi, (double)lane, fma(axj, (double)(warp * kRPW), plan->ax[0]));
-                double ay_r = fma(ayi, (double)lane, fma(ayj, (double)(warp * kRPW), plan->ay[0]));
+                double ax_r = fma(axi, col_dlane, fma(axj, col_drow, plan->ax[0]));
+                double ay_r = fma(ayi, col_dlane, fma(ayj, col_drow, plan->ay[0]));
                 const int m = lane & 3;
                 unsigned char* out_word = P.dst.data + si->dst_tile + (long long)(warp * kRPW) * P.dst.pitch +
                                           ((lane >> 2) * 3 + m) * 4;
