@@ -96,6 +96,22 @@ __device__ __forceinline__ uint32_t patch_bias_u8c3(uint32_t patch_saddr, int pi
     return patch_saddr - (uint32_t)xb0 - (uint32_t)(py0 * pitch) - 3u * m - (uint32_t)pitch * m;
 }
 
+// Nearest neighbour (cv2.remap INTER_NEAREST: the float32 map value rounded half to even).  `ux`, `uy` are
+// round_bits() of the coordinate itself (not of 32 x), `bias_px` folds the patch origin and the magic offsets for
+// `px_bytes` bytes per pixel.
+__device__ __forceinline__ uint32_t patch_bias_nearest_u8(uint32_t patch_saddr, int pitch, int xb0, int py0, uint32_t px_bytes) {
+    return patch_saddr - (uint32_t)xb0 - (uint32_t)(py0 * pitch) - px_bytes * kMagicBits - (uint32_t)pitch * kMagicBits;
+}
+__device__ __forceinline__ uint32_t nearest_u8c3(uint32_t bias_px, uint32_t pitch, uint32_t ux, uint32_t uy) {
+    const uint32_t addr = ux * 3u + uy * pitch + bias_px;
+    const uint32_t a4 = addr & ~3u;
+    return __funnelshift_r(lds32(a4), lds32(a4 + 4), (addr & 3u) << 3);      // R | G << 8 | B << 16 | (next byte) << 24
+}
+__device__ __forceinline__ uint32_t nearest_u8c1(uint32_t bias_px, uint32_t pitch, uint32_t ux, uint32_t uy) {
+    const uint32_t addr = ux + uy * pitch + bias_px;
+    return (lds32(addr & ~3u) >> ((addr & 3u) << 3)) & 0xffu;
+}
+
 // One bilinear sample; returns R | G << 8 | B << 16.
 __device__ __forceinline__ uint32_t bilinear_u8c3(uint32_t bias, uint32_t pitch, uint32_t ux, uint32_t uy) {
     const uint32_t fx = ux & 31u, fy = uy & 31u;
