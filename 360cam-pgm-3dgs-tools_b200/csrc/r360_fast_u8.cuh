@@ -203,6 +203,38 @@ __device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, 
 #endif
 }
 
+// One lanczos4 sample (cv2's 8 x 8 kernel, 15-bit table [fy][fx][ky][kx]: 128 bytes per pixel, read through L1 / L2
+// -- it is four times the bicubic table and does not fit beside the patch ring).  `bias` must address tap
+// (ix - 3, iy - 3): the bilinear bias minus (9 + 3 * pitch).  Returns R | G << 8 | B << 16.
+__device__ __forceinline__ uint32_t lanczos4_u8c3(uint32_t bias, uint32_t pitch, const short* wtab, uint32_t ux, uint32_t uy) {
+    const uint32_t fx = ux & 31u, fy = uy & 31u;
+    const uint32_t addr = (ux >> 5) * 3u + (uy >> 5) * pitch + bias;
+    uint32_t a4 = addr & ~3u;
+    const uint32_t sh = (addr & 3u) << 3;
+    const uint4* w = reinterpret_cast<const uint4*>(wtab + ((fy << 5) + fx) * 64u);    // 8 rows x (w0|w1, w2|w3, w4|w5, w6|w7)
+    int r = 16384, g = 16384, b = 16384;
+#pragma unroll 2
+    for (int ky = 0; ky < 8; ++ky) {
+        const uint4 wr = __ldg(w + ky);
+        const uint32_t q0 = lds32(a4), q1 = lds32(a4 + 4), q2 = lds32(a4 + 8), q3 = lds32(a4 + 12), q4 = lds32(a4 + 16),
+                       q5 = lds32(a4 + 20), q6 = lds32(a4 + 24);
+        a4 += pitch;
+        const uint32_t p0 = __funnelshift_r(q0, q1, sh), p1 = __funnelshift_r(q1, q2, sh), p2 = __funnelshift_r(q2, q3, sh),
+                       p3 = __funnelshift_r(q3, q4, sh), p4 = __funnelshift_r(q4, q5, sh), p5 = __funnelshift_r(q5, q6, sh);
+        // (p0 p1 p2) hold pixels 0..3 and (p3 p4 p5) pixels 4..7, both as R G B R | G B R G | B R G B
+        const uint32_t r_lo = __byte_perm(__byte_perm(p0, p1, 0x0630), p2, 0x5210), r_hi = __byte_perm(__byte_perm(p3, p4, 0x0630), p5, 0x5210);
+        const uint32_t g_lo = __byte_perm(__byte_perm(p0, p1, 0x0741), p2, 0x6210), g_hi = __byte_perm(__byte_perm(p3, p4, 0x0741), p5, 0x6210);
+        const uint32_t b_lo = __byte_perm(__byte_perm(p0, p1, 0x0052), p2, 0x7410), b_hi = __byte_perm(__byte_perm(p3, p4, 0x0052), p5, 0x7410);
+        r = dp2a_hi_s16_u8(wr.w, r_hi, dp2a_lo_s16_u8(wr.z, r_hi, dp2a_hi_s16_u8(wr.y, r_lo, dp2a_lo_s16_u8(wr.x, r_lo, r))));
+        g = dp2a_hi_s16_u8(wr.w, g_hi, dp2a_lo_s16_u8(wr.z, g_hi, dp2a_hi_s16_u8(wr.y, g_lo, dp2a_lo_s16_u8(wr.x, g_lo, g))));
+        b = dp2a_hi_s16_u8(wr.w, b_hi, dp2a_lo_s16_u8(wr.z, b_hi, dp2a_hi_s16_u8(wr.y, b_lo, dp2a_lo_s16_u8(wr.x, b_lo, b))));
+    }
+    uint32_t hi, out;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(0), "r"(b >> 15), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(g >> 15), "r"(r >> 15), "r"(hi));
+    return out;
+}
+
 // Four RGB pixels (each R | G<<8 | B<<16) -> three packed words = 12 output bytes.
 __device__ __forceinline__ void pack4_rgb(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3,
                                           uint32_t& w0, uint32_t& w1, uint32_t& w2) {

@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
     constexpr bool kFastU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
                              (INTERP == kLinear || INTERP == kCubic);
     // nearest on 8-bit sources with 3 channels (views) or 1 channel (the dual-fisheye tool's masks, DF:2031-2043)
+    constexpr bool kFastLanczosU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value && INTERP == kLanczos4;
     constexpr bool kFastNearestU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value && INTERP == kNearest;
     constexpr bool kFastU16 = std::is_same<TIn, uint16_t>::value && (INTERP == kLinear || INTERP == kCubic);
     constexpr int kCW = consumer_warps(kFastU8 && INTERP == kCubic);       // consumer warps of this instantiation
@@ -583,6 +584,7 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
                     si.bias = patch_bias_u8c3(si.patch_saddr, pitch, xb0, py0);
                     if (INTERP == kCubic) si.bias -= 3u + (uint32_t)pitch;
                 }
+                if (kFastLanczosU8) si.bias = patch_bias_u8c3(si.patch_saddr, pitch, xb0, py0) - (9u + 3u * (uint32_t)pitch);
                 if (kFastNearestU8) si.bias = patch_bias_nearest_u8(si.patch_saddr, pitch, xb0, py0, (uint32_t)P.channels);
                 if (kFastU16) {
                     si.bias = patch_bias_u16c3(si.patch_saddr, pitch, xb0, py0);
@@ -823,6 +825,20 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
 #pragma unroll
                         for (int q = 0; q < 4; ++q) px[q] = bicubic_u8c3(bias, pitch, tab, round_bits(sxf[q]), round_bits(syf[q]));
                     }
+                    uint32_t w0, w1, w2;
+                    pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
+                    uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
+                    o[0] = w0; o[1] = w1; o[2] = w2;
+                    done = true;
+                }
+            }
+            if constexpr (kFastLanczosU8) {
+                if (P.channels == 3) {
+                    const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch;
+                    uint32_t px[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        px[q] = lanczos4_u8c3(bias, pitch, g_tables.lanczos_fixed, round_bits(sxf[q]), round_bits(syf[q]));
                     uint32_t w0, w1, w2;
                     pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
                     uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
