@@ -4,6 +4,7 @@
 #include <nvjpeg.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -50,8 +51,16 @@ int r360_jpeg_create(r360_jpeg** out) {
     *out = nullptr;
     r360_jpeg* c = new (std::nothrow) r360_jpeg();
     if (!c) return R360_E_INVALID_ARG;
-    // GPU-assisted Huffman decode for large baseline images; falls back inside nvJPEG otherwise
-    nvjpegStatus_t st = nvjpegCreateEx(NVJPEG_BACKEND_GPU_HYBRID, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &c->handle);
+    // GPU-assisted Huffman decode for large baseline images; falls back inside nvJPEG otherwise.
+    // R360_JPEG_BACKEND=hardware asks for the NVJPG engine (baseline, single scan), =hybrid for CPU Huffman.
+    nvjpegBackend_t backend = NVJPEG_BACKEND_GPU_HYBRID;
+    if (const char* env = std::getenv("R360_JPEG_BACKEND")) {
+        if (!std::strcmp(env, "hardware")) backend = NVJPEG_BACKEND_HARDWARE;
+        else if (!std::strcmp(env, "hybrid")) backend = NVJPEG_BACKEND_HYBRID;
+    }
+    nvjpegStatus_t st = nvjpegCreateEx(backend, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &c->handle);
+    if (st != NVJPEG_STATUS_SUCCESS && backend != NVJPEG_BACKEND_GPU_HYBRID)
+        st = nvjpegCreateEx(NVJPEG_BACKEND_GPU_HYBRID, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &c->handle);
     if (st != NVJPEG_STATUS_SUCCESS) st = nvjpegCreateSimple(&c->handle);
     if (st != NVJPEG_STATUS_SUCCESS) { delete c; return fail("nvjpegCreate", (int)st); }
     if ((st = nvjpegJpegStateCreate(c->handle, &c->decoder)) != NVJPEG_STATUS_SUCCESS ||
