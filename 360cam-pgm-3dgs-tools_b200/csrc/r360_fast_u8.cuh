@@ -206,16 +206,22 @@ __device__ __forceinline__ uint32_t bicubic_u8c3(uint32_t bias, uint32_t pitch, 
 // One lanczos4 sample (cv2's 8 x 8 kernel, 15-bit table [fy][fx][ky][kx]: 128 bytes per pixel, read through L1 / L2
 // -- it is four times the bicubic table and does not fit beside the patch ring).  `bias` must address tap
 // (ix - 3, iy - 3): the bilinear bias minus (9 + 3 * pitch).  Returns R | G << 8 | B << 16.
-__device__ __forceinline__ uint32_t lanczos4_u8c3(uint32_t bias, uint32_t pitch, const short* wtab, uint32_t ux, uint32_t uy) {
+template <bool SMEM_TABLE>
+__device__ __forceinline__ uint32_t lanczos4_u8c3(uint32_t bias, uint32_t pitch, const short* wtab, uint32_t table_saddr,
+                                                  uint32_t ux, uint32_t uy) {
     const uint32_t fx = ux & 31u, fy = uy & 31u;
     const uint32_t addr = (ux >> 5) * 3u + (uy >> 5) * pitch + bias;
     uint32_t a4 = addr & ~3u;
     const uint32_t sh = (addr & 3u) << 3;
-    const uint4* w = reinterpret_cast<const uint4*>(wtab + ((fy << 5) + fx) * 64u);    // 8 rows x (w0|w1, w2|w3, w4|w5, w6|w7)
+    const uint32_t entry = (fy << 5) + fx;
+    const uint4* w = reinterpret_cast<const uint4*>(wtab + entry * 64u);               // 8 rows x (w0|w1, w2|w3, w4|w5, w6|w7)
+    const uint32_t wt = table_saddr + entry * 128u;                                     // shared-memory copy: row ky in slot (ky + entry) mod 8
     int r = 16384, g = 16384, b = 16384;
 #pragma unroll 2
     for (int ky = 0; ky < 8; ++ky) {
-        const uint4 wr = __ldg(w + ky);
+        uint4 wr;
+        if constexpr (SMEM_TABLE) wr = lds128(wt + (((uint32_t)ky + entry) & 7u) * 16u);
+        else wr = __ldg(w + ky);
         const uint32_t q0 = lds32(a4), q1 = lds32(a4 + 4), q2 = lds32(a4 + 8), q3 = lds32(a4 + 12), q4 = lds32(a4 + 16),
                        q5 = lds32(a4 + 20), q6 = lds32(a4 + 24);
         a4 += pitch;

@@ -467,7 +467,9 @@ struct SlotInfo {            // per item, written by the producer
 };
 static_assert(sizeof(SlotInfo) == 64, "SlotInfo layout");
 
-constexpr int kTableBytes = 32 * 32 * 16 * 2;
+constexpr int kTableBytes = 32 * 32 * 16 * 2;              // bicubic: cv2's 15-bit 4 x 4 table
+constexpr int kLanczosTableBytes = 32 * 32 * 64 * 2;       // lanczos4: the 8 x 8 one (TiledParams::use_table == 2)
+__host__ __device__ constexpr int table_bytes(int use_table) { return use_table == 2 ? kLanczosTableBytes : use_table ? kTableBytes : 0; }
 // barriers (64) + slot info + per-warp row coefficients (32 rows x 12 floats, once for each of the two thread
 // mappings: a warp owns different tile rows in them and warps are not in step) + plan records
 constexpr int kTiledFixedSmem = (64 + kSlots * 64 + 2 * 1536 + kSlots * 368 + 127) / 128 * 128;
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
     float* rowc_col = rowc + kTile * 12;                                         // the same for the lane-per-column mapping
     TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 64 + kSlots * 64 + 2 * 1536);   // [kSlots]
     unsigned char* table = smem + kTiledFixedSmem;
-    unsigned char* stage0 = table + (P.use_table ? kTableBytes : 0);
+    unsigned char* stage0 = table + table_bytes(P.use_table);
     unsigned char* ring = stage0 + P.out_stage_bytes;
 
     constexpr bool kFastU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
@@ -514,7 +516,15 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
         for (int q = 0; q < kSlots; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], kCW); }
         fence_mbar_init();
     }
-    if (P.use_table) {
+    if (P.use_table == 2) {
+        // lanczos4: 128-byte entries (eight 16-byte tap rows); row ky of entry e sits in slot (ky + e) mod 8 so that
+        // the 32 entries a warp reads for the same ky spread over the eight bank groups
+        const int4* src = reinterpret_cast<const int4*>(g_tables.lanczos_fixed);
+        for (int q = tid; q < kLanczosTableBytes / 16; q += kCW * 32 + 32) {
+            const int e = q >> 3, ky = q & 7;
+            reinterpret_cast<int4*>(table)[e * 8 + ((ky + e) & 7)] = __ldg(src + q);
+        }
+    } else if (P.use_table) {
         const int4* src = reinterpret_cast<const int4*>(g_tables.cubic_fixed);
         // Two planes (tap rows 0,1 | rows 2,3) with a 16-byte entry stride: a warp's 32 random entries
         // then spread over all 8 bank groups instead of the 4 a 32-byte stride would reach.
@@ -838,7 +848,9 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
                     uint32_t px[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        px[q] = lanczos4_u8c3(bias, pitch, g_tables.lanczos_fixed, round_bits(sxf[q]), round_bits(syf[q]));
+                        px[q] = P.use_table == 2
+                                    ? lanczos4_u8c3<true>(bias, pitch, nullptr, smem_u32(table), round_bits(sxf[q]), round_bits(syf[q]))
+                                    : lanczos4_u8c3<false>(bias, pitch, g_tables.lanczos_fixed, 0u, round_bits(sxf[q]), round_bits(syf[q]));
                     uint32_t w0, w1, w2;
                     pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
                     uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);

@@ -494,14 +494,19 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     // table, two output tiles, two patch buffers.  The patch budget follows from how many blocks
     // should be resident per SM; tiles whose patch is larger take the fallback path.
     pl->use_table = (pl->pr.in_dt == R360_U8 && pl->pr.interp == R360_CUBIC && dst->channels == 3) ? 1 : 0;
+    // lanczos4 on 8-bit RGB: the 128 KB table in shared memory, one block per SM (measured: the kernel runs as fast
+    // with 8 warps per SM as with 32 -- it is bound by the table reads, 32 L1 lines per warp load when they go through L1)
+    if (pl->pr.in_dt == R360_U8 && pl->pr.out_dt == R360_U8 && pl->pr.interp == R360_LANCZOS4 && dst->channels == 3 &&
+        std::getenv("R360_LANCZOS_L1") == nullptr)
+        pl->use_table = 2;
     {
         int dev = 0, smem_per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-        int want = pl->use_table ? 2 : 4;
+        int want = pl->use_table == 2 ? 1 : pl->use_table ? 2 : 4;
         if (const char* env = std::getenv("R360_TILED_CTAS_PER_SM")) want = std::atoi(env) > 0 ? std::atoi(env) : want;
-        const int fixed = kTiledFixedSmem + (pl->use_table ? kTableBytes : 0) + pl->out_stage_bytes + 128;
+        const int fixed = kTiledFixedSmem + table_bytes(pl->use_table) + pl->out_stage_bytes + 128;
         for (;; --want) {
             const int per_block = smem_per_sm / want - 1024;       // 1 KB per block is reserved by the driver
             pl->ring_bytes = (per_block - fixed) & ~127;
@@ -509,6 +514,10 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         }
         if (pl->ring_bytes < 8192) pl->ring_bytes = 8192;
         if (pl->ring_bytes > 160 * 1024) pl->ring_bytes = 160 * 1024;
+        if (const char* env = std::getenv("R360_RING_KB")) {                   // experiments: leave more of the SM to L1
+            const int cap = std::atoi(env) * 1024;
+            if (cap >= 8192 && cap < pl->ring_bytes) pl->ring_bytes = cap & ~127;
+        }
         pl->patch_budget = pl->ring_bytes;                          // a patch may use the whole ring
         pl->ctas_per_sm = want;
         pl->smem_bytes = fixed + pl->ring_bytes;
@@ -518,7 +527,7 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
                        ((int64_t)src->width * src->channels * in_es) % 16 == 0;
     pl->bulk_store_ok = dst->pitch_bytes % 16 == 0 && dst->image_stride_bytes % 16 == 0;
     pl->tensor_ok = pl->bulk_load_ok && encode_tiled_fn() != nullptr && std::getenv("R360_NO_TENSOR_TMA") == nullptr;
-    pl->box_family = pl->use_table ? 1 : 0;      // lane-per-column bicubic path: rows on identical banks
+    pl->box_family = pl->use_table == 1 ? 1 : 0;      // lane-per-column bicubic path: rows on identical banks
     if (const char* env = std::getenv("R360_BOX_FAMILY")) pl->box_family = std::atoi(env) == 1 ? 1 : 0;
     pl->ws = static_cast<unsigned char*>(workspace);
     pl->d_header = reinterpret_cast<PlanHeader*>(pl->ws + wl.header);

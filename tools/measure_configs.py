@@ -89,7 +89,7 @@ def main():
                      "Mpix_per_s": 8 * 2 * 3840 * 3840 / ms / 1e3, "pairs_per_s": 8 / ms * 1e3, "interp": interp})
     del pairs, out, out_u
     torch.cuda.empty_cache()
-    erp_case("cfg2 u8 lanczos4 (packed sampler, weights through L1/L2)", "full360coverage", torch.uint8, "lanczos4", 2)
+    erp_case("cfg2 u8 lanczos4 (packed sampler, table in shared memory)", "full360coverage", torch.uint8, "lanczos4", 2)
     # preset fisheyeXY: 2 equidistant fisheye views 3600^2, d_fov 180
     hf, vf = remap360.api.fisheye_fov_from_dfov(180.0, 3600, 3600)
     fviews = [remap360.PerspectiveView(y, 0.0, hf, vf, projection="fisheye") for y in (0.0, 180.0)]
