@@ -22,9 +22,9 @@ CODEC_OUT = HERE / "remap360" / "libr360codec.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-std=c++17",
+    "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off",
-    "-Xptxas", "-v",
+    "-Xptxas", "-v", "-split-compile", "0",
 ]
 
 

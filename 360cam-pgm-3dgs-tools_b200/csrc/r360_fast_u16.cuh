@@ -41,19 +41,31 @@ __device__ __forceinline__ void load_row_u16(uint32_t addr, uint32_t* out) {
 #pragma unroll
     for (int k = 0; k < NW; ++k) {
         const uint32_t lo = odd ? w[k + 1] : w[k], hi = odd ? w[k + 2] : w[k + 1];
-        out[k] = __funnelshift_r(lo, hi, sh);
+        out[k] = shf_r(lo, hi, sh);
     }
 }
 
-// One bicubic sample, three float accumulators (R/G/B in memory order).  `bias` must address tap
-// (ix - 1, iy - 1): the patch bias minus (6 + pitch).  wtab: the 1-D cubic table [32][4] (global, L1-resident).
-__device__ __forceinline__ void bicubic_u16c3(uint32_t bias, uint32_t pitch, const float* wtab,
-                                              uint32_t ux, uint32_t uy, float* acc) {
+// Bicubic, split like the 8-bit samplers: `prep` fetches what depends on the coordinate only (tap address, the two
+// rows of the 1-D cubic table [32][4] -- global, L1-resident), `taps` samples one frame of the item.  `bias` must
+// address tap (ix - 1, iy - 1): the patch bias minus (6 + pitch).
+struct BicubicPrepU16 {
+    uint32_t addr;
+    float wx[4], wy[4];
+};
+__device__ __forceinline__ BicubicPrepU16 bicubic_prep_u16c3(uint32_t bias, uint32_t pitch, const float* wtab,
+                                                             uint32_t ux, uint32_t uy) {
+    BicubicPrepU16 p;
     const uint32_t fx = ux & 31u, fy = uy & 31u;
-    uint32_t addr = (ux >> 5) * 6u + (uy >> 5) * pitch + bias;
+    p.addr = (ux >> 5) * 6u + (uy >> 5) * pitch + bias;
     const float4 wx = __ldg(reinterpret_cast<const float4*>(wtab) + fx);
     const float4 wy = __ldg(reinterpret_cast<const float4*>(wtab) + fy);
-    const float wxs[4] = {wx.x, wx.y, wx.z, wx.w}, wys[4] = {wy.x, wy.y, wy.z, wy.w};
+    p.wx[0] = wx.x; p.wx[1] = wx.y; p.wx[2] = wx.z; p.wx[3] = wx.w;
+    p.wy[0] = wy.x; p.wy[1] = wy.y; p.wy[2] = wy.z; p.wy[3] = wy.w;
+    return p;
+}
+// Three float accumulators (R/G/B in memory order) for the frame whose patch starts `frame_off` bytes further.
+__device__ __forceinline__ void bicubic_taps_u16c3(const BicubicPrepU16& p, uint32_t pitch, uint32_t frame_off, float* acc) {
+    uint32_t addr = p.addr + frame_off;
     acc[0] = acc[1] = acc[2] = 0.0f;
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
@@ -65,7 +77,7 @@ __device__ __forceinline__ void bicubic_u16c3(uint32_t bias, uint32_t pitch, con
         float row[3];
 #pragma unroll
         for (int kx = 0; kx < 4; ++kx) {
-            const float wgt = __fmul_rn(wys[ky], wxs[kx]);
+            const float wgt = __fmul_rn(p.wy[ky], p.wx[kx]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float term = __fmul_rn(t[3 * kx + c], wgt);
@@ -77,12 +89,21 @@ __device__ __forceinline__ void bicubic_u16c3(uint32_t bias, uint32_t pitch, con
     }
 }
 
-// One bilinear sample (cv2: one left-to-right expression over the four taps).
-__device__ __forceinline__ void bilinear_u16c3(uint32_t bias, uint32_t pitch, uint32_t ux, uint32_t uy, float* acc) {
+// Bilinear (cv2: one left-to-right expression over the four taps).
+struct BilinearPrepU16 {
+    uint32_t addr;
+    float tx, ty;
+};
+__device__ __forceinline__ BilinearPrepU16 bilinear_prep_u16c3(uint32_t bias, uint32_t pitch, uint32_t ux, uint32_t uy) {
+    BilinearPrepU16 p;
     const uint32_t fx = ux & 31u, fy = uy & 31u;
-    const uint32_t addr = (ux >> 5) * 6u + (uy >> 5) * pitch + bias;
-    const float tx = (float)fx * (1.0f / 32.0f), ty = (float)fy * (1.0f / 32.0f);
-    const float wxs[2] = {1.0f - tx, tx}, wys[2] = {1.0f - ty, ty};
+    p.addr = (ux >> 5) * 6u + (uy >> 5) * pitch + bias;
+    p.tx = (float)fx * (1.0f / 32.0f); p.ty = (float)fy * (1.0f / 32.0f);
+    return p;
+}
+__device__ __forceinline__ void bilinear_taps_u16c3(const BilinearPrepU16& p, uint32_t pitch, uint32_t frame_off, float* acc) {
+    const uint32_t addr = p.addr + frame_off;
+    const float wxs[2] = {1.0f - p.tx, p.tx}, wys[2] = {1.0f - p.ty, p.ty};
 #pragma unroll
     for (int ky = 0; ky < 2; ++ky) {
         uint32_t v[3];

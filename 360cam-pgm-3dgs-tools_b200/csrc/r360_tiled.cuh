@@ -31,10 +31,6 @@
 #include "r360_fast_u8.cuh"
 #include "r360_fast_u16.cuh"
 
-#ifndef R360_LINEAR_MAP_B
-#define R360_LINEAR_MAP_B 0     // bilinear 8-bit RGB on the lane-per-column mapping of the bicubic path (experiment)
-#endif
-
 namespace r360 {
 
 constexpr int kTile = 32;
@@ -319,47 +315,34 @@ __device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar_saddr, uint32_t par
         "}\n" : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
     return done != 0;
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_s(smem_u32(bar), parity); }
-// Wait on a barrier given by its shared-memory address (cheaper in the per-tile loop).
-#ifndef R360_WAIT_STYLE
-#define R360_WAIT_STYLE 0
-#endif
+// Wait on a barrier given by its shared-memory address.  try_wait suspends the warp for a hardware time slice
+// per call; a copy that never completes is a bug, so trap instead of hanging the device.
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar_saddr, uint32_t parity) {
     if (mbar_try_wait_s(bar_saddr, parity)) return;
-#if R360_WAIT_STYLE == 1
-    // bare poll: try_wait itself suspends the warp for a hardware time slice; a watchdog every 2^20 polls
-    for (unsigned spins = 1; !mbar_try_wait_s(bar_saddr, parity); ++spins)
-        if ((spins & 0xFFFFFu) == 0u && spins > 0x4000000u) __trap();
-#elif R360_WAIT_STYLE == 2
-    for (unsigned spins = 0; !mbar_try_wait_s(bar_saddr, parity); ++spins) {
-        __nanosleep(1024);
+    for (unsigned spins = 0; !mbar_try_wait_s(bar_saddr, parity); ++spins)
+        if (spins > 4000000u) __trap();
+}
+// The producer's wait (a slot to be released): it sleeps between polls so that the polling does not take issue
+// slots from the consumer warps of its scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    if (mbar_try_wait_s(a, parity)) return;
+    for (unsigned spins = 0; !mbar_try_wait_s(a, parity); ++spins) {
+        __nanosleep(128);
         if (spins > 8000000u) __trap();
     }
-#else
-    for (unsigned spins = 0; !mbar_try_wait_s(bar_saddr, parity); ++spins) {
-        __nanosleep(256);
-        if (spins > 8000000u) __trap();
-    }
-#endif
 }
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar_saddr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // try_wait suspends for a hardware time slice per call; a copy that never completes is a
-    // bug, so trap instead of hanging the device
-    if (mbar_try_wait(bar, parity)) return;
-    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        __nanosleep(256);
-        if (spins > 8000000u) __trap();
-    }
-}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { mbar_arrive_s(smem_u32(bar)); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// L2 policies: the source frame is re-read by every view of the frame -> keep it (evict_last);
-// output tiles are written once and never read -> stream them (st.global.cs below).
+// L2 policy of the patch loads: the source frames are re-read by every view that overlaps them (and by the
+// neighbouring tiles' halos) -> evict_last; the outputs are written once and never read -> streamed (st.global.cs).
+// Measured on B200 (16 x 8K frames, 12 views): DRAM reads 2.84 GB with evict_last, 4.84 GB with evict_normal.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -374,27 +357,29 @@ __device__ __forceinline__ void tensor_g2s_3d(void* smem_dst, const void* tmap, 
 __device__ __forceinline__ void st_global_streaming(void* gptr, const int4& v) {
     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Experiment builds (-DR360_TILED_STATS=1) time what the warps wait for: [0] consumer warps' cycles in the slot
+// loop, [1] of which waiting for a slot's data, [2] producer cycles, [3] of which waiting for ring space / a free
+// slot, [4] slots published, [5] of which multi-frame.  Read back with r360_debug_tiled_stats.
+#ifndef R360_TILED_STATS
+#define R360_TILED_STATS 0
+#endif
+__device__ unsigned long long g_tiled_stats[8];
 
 // ---- the remap kernel -------------------------------------------------------------------------------
 //
-// Persistent and warp-specialised.  Each block walks (frame, view, tile) work items:
-//   * one producer warp runs ahead.  Per item it reads the tile's plan record, carves space for the
-//     patch out of a shared-memory ring (variable-size patches, FIFO), issues the tensor-TMA boxes
-//     (or per-row bulk copies) that complete on the item's mbarrier, and meanwhile prepares
-//     everything that is uniform per tile or per row -- the 12 residual-polynomial coefficients,
-//     the float64 affine base and the destination address of each of the 32 rows -- so that the
-//     consumers spend their issue slots on pixels only;
-//   * eight consumer warps each own 4 rows of every tile and never synchronise with one another:
-//     wait for the item's mbarrier, sample 4 pixels per lane, write their rows of the output tile
-//     to a per-warp double-buffered stage and send them off as bulk-async row stores; the last
-//     reader of a patch releases it to the producer through a second mbarrier (8 arrivals).
+// Persistent and warp-specialised.  Each block walks work items (tile, view, block of FR consecutive frames):
+//   * one producer warp runs ahead.  Per item it reads the tile's plan record, carves space for the patches
+//     (the same source rectangle of each of the item's frames) out of a shared-memory ring (variable-size,
+//     FIFO), issues the tensor-TMA boxes (or per-row bulk copies) that complete on the slot's mbarrier, and
+//     publishes a slot record.  Items whose FR patches do not fit the budget, and the frames left over when
+//     the batch is not a multiple of FR, are published as one-frame slots; fallback tiles are skipped;
+//   * consumer warps work in teams of eight (a block has one or two teams, slot k belongs to team k mod
+//     teams).  A team's warps each own 4 rows of the tile and never synchronise with one another: wait for
+//     the slot's mbarrier, generate the coordinates, tap addresses and weights of their pixels ONCE and sample
+//     every frame of the item with them (what a video / batch shares between frames: the map), write their rows;
+//     the last reader of a slot releases it to the producer through a second mbarrier (8 arrivals).
+//   The producer ends the stream with one `kModeExit` slot per team.
 
 // FIFO allocator for variable-size patches in the shared-memory ring.  The bytes in flight form
 // one circular interval [tail, head) of length `used`; allocations are contiguous (an allocation
@@ -426,6 +411,8 @@ struct PatchRing {
     }
 };
 
+constexpr int kMaxFramesPerItem = 4;
+
 struct TiledParams {
     ImageSetDev src, dst;
     int channels;
@@ -433,52 +420,71 @@ struct TiledParams {
     int n_groups;           // source groups (frames) in this launch
     int n_lenses;
     int tiles_x, tiles_y;
-    int out_stage_bytes;    // kTile * kTile * channels * sizeof(TOut), rounded up to 128
+    int out_stage_bytes;    // kTile * kTile * channels * sizeof(TOut), rounded up to 128 (one frame of one team)
     int ring_bytes;         // shared-memory ring for patches (multiple of 128)
     int bulk_store_ok;      // destination layout allows 16-byte aligned row stores
     int use_table;          // copy the fixed-point cubic table into shared memory
+    int frames_per_item;    // FR: must equal the kernel's template argument
+    int multi_budget;       // an item takes FR frames at once when FR * (patch bytes) <= this
     float border_value;
+    long long dst_fstride;  // bytes between the same view of consecutive frames (n_views * image stride)
     const TilePlan* plans;  // whole plan (all views)
 };
 
-constexpr int kSlots = 4;                               // work items in flight per block
-constexpr int kConsumerWarps = 8;                       // warps of the 4-rows-per-warp mapping (256 threads <-> 32 x 8 lanes)
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-// Experiment switch: the 8-bit bicubic kernel with 16 consumer warps (two tile rows each on the lane-per-column
-// tiles; seam / fill / partial tiles stay with the first eight warps, the others only release the patch).
-// Measured on B200: 99.5 vs 103.0 Gpix/s with 8 warps -- the kernel is not short of warps.
-#ifndef R360_CUBIC_WARPS
-#define R360_CUBIC_WARPS 8
+// Build-time shape of a block: consumer teams, and how many blocks per SM the register allocation must allow
+// (0 = the kernel's own default, tiled_min_blocks).  Experiments build variants with other values.
+#ifndef R360_TILED_TEAMS
+#define R360_TILED_TEAMS 1
 #endif
-__host__ __device__ constexpr int consumer_warps(bool cubic_u8) { return cubic_u8 ? R360_CUBIC_WARPS : kConsumerWarps; }
-constexpr int kMaxTiledThreads = (R360_CUBIC_WARPS > kConsumerWarps ? R360_CUBIC_WARPS : kConsumerWarps) * 32 + 32;
+#ifndef R360_TILED_MINB
+#define R360_TILED_MINB 0
+#endif
+constexpr int kConsumerWarps = 8;                       // warps of a team (256 threads <-> 32 rows x 8 lanes)
+constexpr int kTeamThreads = kConsumerWarps * 32;
+constexpr int kTeams = R360_TILED_TEAMS;
+constexpr int kMaxTeams = 4;
+static_assert(kTeams >= 1 && kTeams <= kMaxTeams, "team count");
+constexpr int kSlots = kTeams <= 2 ? 4 : 2 * kTeams;    // slots in flight per block (a multiple of the team count)
+static_assert(kSlots % kTeams == 0, "slot k belongs to team k mod kTeams");
+constexpr int kTiledThreads = kTeams * kTeamThreads + 32;
+// blocks per SM the registers are budgeted for: the 8-bit bicubic kernel shares the SM with its 32 KB weight
+// table (2 blocks), lanczos4 with a 128 KB one (1 block); bilinear, 16-bit and float samplers want the registers
+// (and, with several frames per item, the shared memory) of 2 blocks -- measured: bilinear 8-bit, two frames per
+// item, 266 Gpix/s at 2 blocks per SM against 208 at 4; nearest runs 4 blocks of one team
+__host__ __device__ constexpr int tiled_default_blocks(int elem_bytes, int interp) {
+    return (elem_bytes == 1 && interp == kLanczos4) ? 1 : (interp == kLinear || interp == kCubic || elem_bytes > 1) ? 2 : 4;
+}
+__host__ __device__ constexpr int tiled_min_blocks(int elem_bytes, int interp) {
+    return R360_TILED_MINB > 0 ? R360_TILED_MINB
+                               : (tiled_default_blocks(elem_bytes, interp) + kTeams - 1) / kTeams;
+}
+constexpr int kModeExit = 255;                          // slot record that ends a team's stream
 
-struct SlotInfo {            // per item, written by the producer
-    uint32_t patch_saddr;    // shared-memory address of the patch
-    uint32_t bias;           // 8-bit RGB fast path: tap address bias (r360_fast_u8.cuh)
+struct SlotInfo {            // per slot, written by the producer
+    uint32_t patch_saddr;    // shared-memory address of the first frame's patch
+    uint32_t bias;           // fast samplers: tap address bias (r360_fast_u8.cuh)
     int size;                // ring bytes to give back on release
     int mode;                // TileMode
     int pitch, xb0, py0;     // patch geometry
     int full_tile;           // the tile lies completely inside the destination image
     int i0, j0;
-    long long dst_tile;      // byte offset of the tile's first output pixel inside the destination batch
-    long long dst_off;       // byte offset of the destination image (frame, view)
-    long long pad;
+    long long dst_tile;      // byte offset of the tile's first output pixel inside the destination batch (first frame)
+    long long dst_off;       // byte offset of the destination image (first frame, view)
+    int nf;                  // frames of this slot (1 or FR)
+    uint32_t fstride;        // shared-memory bytes between the patches of consecutive frames
 };
 static_assert(sizeof(SlotInfo) == 64, "SlotInfo layout");
 
 constexpr int kTableBytes = 32 * 32 * 16 * 2;              // bicubic: cv2's 15-bit 4 x 4 table
 constexpr int kLanczosTableBytes = 32 * 32 * 64 * 2;       // lanczos4: the 8 x 8 one (TiledParams::use_table == 2)
 __host__ __device__ constexpr int table_bytes(int use_table) { return use_table == 2 ? kLanczosTableBytes : use_table ? kTableBytes : 0; }
-// barriers (64) + slot info + per-warp row coefficients (32 rows x 12 floats, once for each of the two thread
-// mappings: a warp owns different tile rows in them and warps are not in step) + plan records
-constexpr int kTiledFixedSmem = (64 + kSlots * 64 + 2 * 1536 + kSlots * 368 + 127) / 128 * 128;
-static_assert(kTiledFixedSmem % 128 == 0 && kTableBytes % 128 == 0, "ring alignment");
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// fixed part of the dynamic shared memory: barriers | slot records | per-team row coefficients (32 rows x 12
+// floats) | plan records
+constexpr int kSmemSlots = (2 * kSlots * 8 + 63) / 64 * 64;
+constexpr int kSmemRowc = kSmemSlots + kSlots * 64;
+constexpr int kSmemPlans = kSmemRowc + kTeams * 1536;
+constexpr int kTiledFixedSmem = (kSmemPlans + kSlots * 368 + 127) / 128 * 128;
+static_assert(kTiledFixedSmem % 128 == 0 && kTableBytes % 128 == 0 && kSmemPlans % 16 == 0, "ring alignment");
 
 // One descriptor per box shape, all over the same 3-D view of the source batch:
 // (row bytes / 4 as uint32, rows, images) with strides (pitch, image stride).
@@ -486,41 +492,92 @@ struct TensorMaps {
     CUtensorMap m[kNumBoxWidths * kNumBoxHeights];     // [width index][height index]
 };
 
-template <int INTERP, typename TIn, typename TOut>
-__global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __grid_constant__ TiledParams P,
+// Residual polynomial of one pixel: Horner in s over the row's 12 coefficients (6 for x, 6 for y).
+__device__ __forceinline__ void residual_xy(const float4& c0, const float4& c1, const float4& c2, float s, float& dx, float& dy) {
+    dx = c1.y; dy = c2.w;
+    dx = fmaf(dx, s, c1.x); dx = fmaf(dx, s, c0.w); dx = fmaf(dx, s, c0.z); dx = fmaf(dx, s, c0.y); dx = fmaf(dx, s, c0.x);
+    dy = fmaf(dy, s, c2.z); dy = fmaf(dy, s, c2.y); dy = fmaf(dy, s, c2.x); dy = fmaf(dy, s, c1.w); dy = fmaf(dy, s, c1.z);
+}
+
+// ---- 8-bit RGB, lane = pixel column, 4 rows per lane ---------------------------------------------------
+// With adjacent lanes on adjacent pixels the tap loads of a warp fall into neighbouring words (few bank conflicts),
+// and the finished row leaves straight from registers: three lanes out of four hold one 32-bit word of the 96-byte
+// row after a shuffle, so the store is contiguous.  The weights and the tap address of a pixel serve all NF frames
+// of the slot.  Bilinear and bicubic full tiles both take this path (measured on B200, 16 x 8K frames -> 12 views,
+// two frames per item: bilinear 266 Gpix/s here against 244 with four pixels per lane through the output stage).
+template <int INTERP, int NF>
+__device__ __forceinline__ void column_rows_u8c3(const TilePlan* plan, const float* rowc_warp, uint32_t bias, uint32_t pitch,
+                                                 uint32_t tab, uint32_t fstride, float s, double dlane, double drow,
+                                                 unsigned char* out_word, long long dst_pitch, long long dst_fstride, int m) {
+    const double axi = plan->ax[1], ayi = plan->ay[1], axj = plan->ax[2], ayj = plan->ay[2];
+    double ax_r = fma(axi, dlane, fma(axj, drow, plan->ax[0]));
+    double ay_r = fma(ayi, dlane, fma(ayj, drow, plan->ay[0]));
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float* rq = rowc_warp + q * 12;
+        const float4 c0 = *reinterpret_cast<const float4*>(rq), c1 = *reinterpret_cast<const float4*>(rq + 4),
+                     c2 = *reinterpret_cast<const float4*>(rq + 8);
+        float dx, dy;
+        residual_xy(c0, c1, c2, s, dx, dy);
+        const float sx = __double2float_rn(ax_r + (double)dx), sy = __double2float_rn(ay_r + (double)dy);
+        ax_r += axj; ay_r += ayj;
+        uint32_t own[NF];
+        if constexpr (INTERP == kCubic) {
+            const BicubicPrep pp = bicubic_prep_u8c3(bias, pitch, tab, round_bits(sx), round_bits(sy));
+#pragma unroll
+            for (int f = 0; f < NF; ++f) own[f] = bicubic_taps_u8c3(pp, pitch, (uint32_t)f * fstride);
+        } else {
+            const BilinearPrep pp = bilinear_prep_u8c3(bias, pitch, round_bits(sx), round_bits(sy));
+#pragma unroll
+            for (int f = 0; f < NF; ++f) own[f] = bilinear_taps_u8c3(pp, pitch, (uint32_t)f * fstride);
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const uint32_t nxt = __shfl_down_sync(0xffffffffu, own[f], 1);
+            const uint32_t word = (own[f] >> (8 * m)) | (nxt << (24 - 8 * m));
+            // three lanes out of four store: a predicated store (no divergent branch around it; no "memory"
+            // clobber: the outputs are never read back, and the next row's tap loads may move above it)
+            asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %2, 3;\n@p st.global.cs.b32 [%0], %1;\n}"
+                         ::"l"(out_word + f * dst_fstride), "r"(word), "r"((uint32_t)m));
+        }
+        out_word += dst_pitch;
+    }
+}
+
+template <int INTERP, typename TIn, typename TOut, int FR>
+__global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks((int)sizeof(TIn), INTERP)) remap_tiled_kernel(const __grid_constant__ TiledParams P,
                                                                     const __grid_constant__ TensorMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [kSlots]
     uint64_t* empty = full + kSlots;                               // [kSlots]
-    SlotInfo* slots = reinterpret_cast<SlotInfo*>(smem + 64);      // [kSlots]
-    float* rowc = reinterpret_cast<float*>(smem + 64 + kSlots * 64);             // [32 rows][12], per-warp regions
-    float* rowc_col = rowc + kTile * 12;                                         // the same for the lane-per-column mapping
-    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + 64 + kSlots * 64 + 2 * 1536);   // [kSlots]
+    SlotInfo* slots = reinterpret_cast<SlotInfo*>(smem + kSmemSlots);            // [kSlots]
+    float* rowc_all = reinterpret_cast<float*>(smem + kSmemRowc);                // [team][32 rows][12]
+    TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + kSmemPlans);          // [kSlots]
     unsigned char* table = smem + kTiledFixedSmem;
-    unsigned char* stage0 = table + table_bytes(P.use_table);
-    unsigned char* ring = stage0 + P.out_stage_bytes;
+    unsigned char* stage_all = table + table_bytes(P.use_table);   // [team][FR][out_stage_bytes]
+    constexpr int n_teams = kTeams;
+    unsigned char* ring = stage_all + n_teams * FR * P.out_stage_bytes;
 
     constexpr bool kFastU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
                              (INTERP == kLinear || INTERP == kCubic);
-    // nearest on 8-bit sources with 3 channels (views) or 1 channel (the dual-fisheye tool's masks, DF:2031-2043)
     constexpr bool kFastLanczosU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value && INTERP == kLanczos4;
+    // nearest on 8-bit sources with 3 channels (views) or 1 channel (the dual-fisheye tool's masks, DF:2031-2043)
     constexpr bool kFastNearestU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value && INTERP == kNearest;
     constexpr bool kFastU16 = std::is_same<TIn, uint16_t>::value && (INTERP == kLinear || INTERP == kCubic);
-    constexpr int kCW = consumer_warps(kFastU8 && INTERP == kCubic);       // consumer warps of this instantiation
-    constexpr int kRPW = kTile / kCW;                                      // tile rows per warp on the lane-per-column path
     const int tid = threadIdx.x;
     const int n_tiles = P.tiles_x * P.tiles_y;
-    const int total = P.n_groups * P.n_views * n_tiles;             // the host keeps this below 2^31
+    const int n_fblocks = (P.n_groups + FR - 1) / FR;
+    const int total = n_fblocks * P.n_views * n_tiles;              // the host keeps this below 2^31
 
     if (tid == 0) {
-        for (int q = 0; q < kSlots; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], kCW); }
+        for (int q = 0; q < kSlots; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], kConsumerWarps); }
         fence_mbar_init();
     }
     if (P.use_table == 2) {
         // lanczos4: 128-byte entries (eight 16-byte tap rows); row ky of entry e sits in slot (ky + e) mod 8 so that
         // the 32 entries a warp reads for the same ky spread over the eight bank groups
         const int4* src = reinterpret_cast<const int4*>(g_tables.lanczos_fixed);
-        for (int q = tid; q < kLanczosTableBytes / 16; q += kCW * 32 + 32) {
+        for (int q = tid; q < kLanczosTableBytes / 16; q += blockDim.x) {
             const int e = q >> 3, ky = q & 7;
             reinterpret_cast<int4*>(table)[e * 8 + ((ky + e) & 7)] = __ldg(src + q);
         }
@@ -528,21 +585,25 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
         const int4* src = reinterpret_cast<const int4*>(g_tables.cubic_fixed);
         // Two planes (tap rows 0,1 | rows 2,3) with a 16-byte entry stride: a warp's 32 random entries
         // then spread over all 8 bank groups instead of the 4 a 32-byte stride would reach.
-        for (int q = tid; q < kTableBytes / 16; q += kCW * 32 + 32)
+        for (int q = tid; q < kTableBytes / 16; q += blockDim.x)
             reinterpret_cast<int4*>(table)[table_entry_index((uint32_t)q >> 6, ((uint32_t)q >> 1) & 31u) + (q & 1) * (kTableBytes / 32)] = __ldg(src + q);
     }
     __syncthreads();
 
-    if (tid >= kCW * 32) {
+    if (tid >= n_teams * kTeamThreads) {
         // ================= producer warp: keep it short, it is the serial part of the pipeline ======
-        const int lane = tid - kCW * 32;
+        const int lane = tid - n_teams * kTeamThreads;
         PatchRing ringst;                // identical in every lane
         int oldest = 0, k = 0;
-        const uint64_t keep = l2_policy_evict_last();
-        // (tile, view, group) of the current item, advanced incrementally (no divisions in the loop)
+        const uint64_t policy = l2_policy_evict_last();
+#if R360_TILED_STATS
+        const long long st_t0 = clock64();
+        long long st_wait = 0, st_slots = 0, st_multi = 0;
+#endif
+        // (tile, view, frame block) of the current item, advanced incrementally (no divisions in the loop)
         int item = blockIdx.x;
         int tile = item % n_tiles, unit = item / n_tiles;
-        int v = unit % P.n_views, g = unit / P.n_views;
+        int v = unit % P.n_views, gb = unit / P.n_views;
         int ti = tile % P.tiles_x, tj = tile / P.tiles_x;
         const int step_tile = gridDim.x % n_tiles, step_unit = gridDim.x / n_tiles;
         const int step_ti = step_tile % P.tiles_x, step_tj = step_tile / P.tiles_x;
@@ -551,13 +612,12 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
         int4 geo = make_int4(0, 0, 0, 0);
         const TilePlan* gp = P.plans + (long long)v * n_tiles + tile;
         if (item < total && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
-        for (; item < total; item += gridDim.x, ++k) {
-            const int slot = k & (kSlots - 1);
+        for (; item < total; item += gridDim.x) {
             const int py0 = __shfl_sync(0xffffffffu, geo.x, 0), rows_needed = __shfl_sync(0xffffffffu, geo.y, 0);
             const int xb0 = __shfl_sync(0xffffffffu, geo.z, 0), row_bytes = __shfl_sync(0xffffffffu, geo.w, 0);
             const int pitch = __shfl_sync(0xffffffffu, geo.x, 1), mode_slot = __shfl_sync(0xffffffffu, geo.y, 1);
             const TilePlan* gp_cur = gp;
-            const int cur_g = g, cur_v = v, cur_ti = ti, cur_tj = tj;
+            const int cur_gb = gb, cur_v = v, cur_ti = ti, cur_tj = tj;
             // advance to the next item and start fetching its geometry
             {
                 int du = step_unit;
@@ -566,98 +626,140 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
                 tile += step_tile;
                 if (tile >= n_tiles) { tile -= n_tiles; tj -= P.tiles_y; ++du; }
                 v += du;
-                while (v >= P.n_views) { v -= P.n_views; ++g; }
+                while (v >= P.n_views) { v -= P.n_views; ++gb; }
             }
             gp = P.plans + (long long)v * n_tiles + tile;
             if (item + (int)gridDim.x < total && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
 
             const int mode = mode_slot & 0xff, src_slot = (mode_slot >> 8) & 0xff, wbox = mode_slot >> 16;
+            if (mode == kModeFallback) continue;                     // remap_fallback_kernel owns this tile
             const bool staged = mode == kModeFast || mode == kModeFastRows || mode == kModeFastSeam;
             const int rows = staged ? rows_needed : 0;
             const int srows = mode == kModeFast ? staged_rows(rows) : rows;      // rows written to the ring
-            const int need = (srows * pitch + 127) & ~127;
-            // ---- find room: wait for the oldest items to be released until the patch fits ---------
-            int off = 0, charge = 0;
-            while ((k - oldest) >= kSlots || !ringst.try_alloc(need, P.ring_bytes, off, charge)) {
-                mbar_wait(&empty[oldest & (kSlots - 1)], (oldest / kSlots) & 1);
-                ringst.release(slots[oldest & (kSlots - 1)].size, P.ring_bytes);
-                ++oldest;
-            }
-            unsigned char* patch = ring + off;
-            __syncwarp();                                              // slots[] reads above are done
-            if (lane == 0) {
-                const int i0 = cur_ti * kTile, j0 = cur_tj * kTile;
-                SlotInfo si;
-                si.patch_saddr = smem_u32(patch);
-                si.bias = 0;
-                if (kFastU8) {
-                    si.bias = patch_bias_u8c3(si.patch_saddr, pitch, xb0, py0);
-                    if (INTERP == kCubic) si.bias -= 3u + (uint32_t)pitch;
-                }
-                if (kFastLanczosU8) si.bias = patch_bias_u8c3(si.patch_saddr, pitch, xb0, py0) - (9u + 3u * (uint32_t)pitch);
-                if (kFastNearestU8) si.bias = patch_bias_nearest_u8(si.patch_saddr, pitch, xb0, py0, (uint32_t)P.channels);
-                if (kFastU16) {
-                    si.bias = patch_bias_u16c3(si.patch_saddr, pitch, xb0, py0);
-                    if (INTERP == kCubic) si.bias -= 6u + (uint32_t)pitch;
-                }
-                si.size = charge; si.mode = mode; si.pitch = pitch; si.xb0 = xb0; si.py0 = py0;
-                si.full_tile = (i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height) ? 1 : 0;
-                si.i0 = i0; si.j0 = j0;
-                si.dst_off = ((long long)cur_g * P.n_views + cur_v) * P.dst.image_stride;
-                si.dst_tile = si.dst_off + (long long)j0 * P.dst.pitch + (long long)i0 * P.channels * (int)sizeof(TOut);
-                si.pad = 0;
-                slots[slot] = si;
-#if R360_WHATIF == 4
-                const uint32_t patch_bytes = (mode == kModeFast || !staged) ? 0u : (uint32_t)(rows * row_bytes);   // what-if: no tensor boxes
-#else
-                const uint32_t patch_bytes = !staged ? 0u : (uint32_t)(mode == kModeFast ? srows * pitch : rows * row_bytes);
+            const int need1 = (srows * pitch + 127) & ~127;                       // one frame's patch
+            const uint32_t patch_bytes1 = !staged ? 0u : (uint32_t)(mode == kModeFast ? srows * pitch : rows * row_bytes);
+            // frames of this item: all FR in one slot when they fit, else one slot per frame
+            const int g_first = cur_gb * FR;
+            const int avail = min(FR, P.n_groups - g_first);
+            const bool multi = FR > 1 && avail == FR && FR * need1 <= P.multi_budget;
+            const int nf = multi ? FR : 1, n_sub = multi ? 1 : avail;
+            const int i0 = cur_ti * kTile, j0 = cur_tj * kTile;
+            for (int sub = 0; sub < n_sub; ++sub, ++k) {
+                const int slot = k % kSlots;
+                const int g0 = g_first + sub;                                     // first frame of the slot
+                const int need = need1 * nf;
+                // ---- find room: wait for the oldest slots to be released until the patches fit ---------
+                int off = 0, charge = 0;
+#if R360_TILED_STATS
+                const long long st_w0 = clock64();
 #endif
-                mbar_expect_tx(&full[slot], (uint32_t)sizeof(TilePlan) + patch_bytes);     // arrive + expect
-                bulk_g2s(&planbuf[slot], gp_cur, (uint32_t)sizeof(TilePlan), &full[slot]);
-            }
-            __syncwarp();
-            if (mode == kModeFast) {
-                // a few tensor boxes: 32-row boxes first, then 8-row boxes
-                const int n32 = rows / 32, n8 = ((rows % 32) + 7) / 8;
-                if (lane < n32 + n8 && R360_WHATIF != 4) {
-                    const int r0 = lane < n32 ? lane * 32 : n32 * 32 + (lane - n32) * 8;
-                    const CUtensorMap* tm = &maps.m[wbox * kNumBoxHeights + (lane < n32 ? 0 : 1)];
-                    tensor_g2s_3d(patch + r0 * pitch, tm, xb0 >> 2, py0 + r0, cur_g * P.n_lenses + src_slot, &full[slot], keep);
+                while ((k - oldest) >= kSlots || !ringst.try_alloc(need, P.ring_bytes, off, charge)) {
+                    mbar_wait_relaxed(&empty[oldest % kSlots], (oldest / kSlots) & 1);
+                    ringst.release(slots[oldest % kSlots].size, P.ring_bytes);
+                    ++oldest;
                 }
-            } else if (mode == kModeFastRows) {
-                const unsigned char* img = P.src.data + ((long long)cur_g * P.n_lenses + src_slot) * P.src.image_stride;
-                for (int r = lane; r < rows; r += 32) {
-                    const int sy = min(max(py0 + r, 0), P.src.height - 1);            // pole rows replicate
-                    bulk_g2s(patch + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[slot]);
+#if R360_TILED_STATS
+                st_wait += clock64() - st_w0; ++st_slots; st_multi += nf > 1;
+#endif
+                unsigned char* patch = ring + off;
+                __syncwarp();                                              // slots[] reads above are done
+                if (lane == 0) {
+                    SlotInfo si;
+                    si.patch_saddr = smem_u32(patch);
+                    si.bias = 0;
+                    if (kFastU8) {
+                        si.bias = patch_bias_u8c3(si.patch_saddr, pitch, xb0, py0);
+                        if (INTERP == kCubic) si.bias -= 3u + (uint32_t)pitch;
+                    }
+                    if (kFastLanczosU8) si.bias = patch_bias_u8c3(si.patch_saddr, pitch, xb0, py0) - (9u + 3u * (uint32_t)pitch);
+                    if (kFastNearestU8) si.bias = patch_bias_nearest_u8(si.patch_saddr, pitch, xb0, py0, (uint32_t)P.channels);
+                    if (kFastU16) {
+                        si.bias = patch_bias_u16c3(si.patch_saddr, pitch, xb0, py0);
+                        if (INTERP == kCubic) si.bias -= 6u + (uint32_t)pitch;
+                    }
+                    si.size = charge; si.mode = mode; si.pitch = pitch; si.xb0 = xb0; si.py0 = py0;
+                    si.full_tile = (i0 + kTile <= P.dst.width && j0 + kTile <= P.dst.height) ? 1 : 0;
+                    si.i0 = i0; si.j0 = j0;
+                    si.dst_off = ((long long)g0 * P.n_views + cur_v) * P.dst.image_stride;
+                    si.dst_tile = si.dst_off + (long long)j0 * P.dst.pitch + (long long)i0 * P.channels * (int)sizeof(TOut);
+                    si.nf = nf; si.fstride = (uint32_t)need1;
+                    slots[slot] = si;
+                    mbar_expect_tx(&full[slot], (uint32_t)sizeof(TilePlan) + patch_bytes1 * (uint32_t)nf);     // arrive + expect
+                    bulk_g2s(&planbuf[slot], gp_cur, (uint32_t)sizeof(TilePlan), &full[slot]);
                 }
-            } else if (mode == kModeFastSeam) {
-                // the patch spans the seam: its first bytes come from the end of the image row, the rest
-                // from its beginning (both pieces are multiples of 16 bytes)
-                const unsigned char* img = P.src.data + ((long long)cur_g * P.n_lenses + src_slot) * P.src.image_stride;
-                const int row_total = P.src.width * P.channels * (int)sizeof(TIn);
-                const int start = xb0 < 0 ? xb0 + row_total : xb0;                   // wrapped first byte
-                const int len1 = min(row_bytes, row_total - start);
-                for (int r = lane; r < rows; r += 32) {
-                    const int sy = min(max(py0 + r, 0), P.src.height - 1);
-                    const unsigned char* row = img + (long long)sy * P.src.pitch;
-                    bulk_g2s(patch + r * pitch, row + start, (uint32_t)len1, &full[slot]);
-                    if (len1 < row_bytes)
-                        bulk_g2s(patch + r * pitch + len1, row, (uint32_t)(row_bytes - len1), &full[slot]);
+                __syncwarp();
+                if (mode == kModeFast) {
+                    // a few tensor boxes per frame: 32-row boxes first, then 8-row boxes
+                    const int n32 = rows / 32, nb = n32 + ((rows % 32) + 7) / 8;
+                    for (int t = lane; t < nb * nf; t += 32) {
+                        const int f = t / nb, bx = t - f * nb;
+                        const int r0 = bx < n32 ? bx * 32 : n32 * 32 + (bx - n32) * 8;
+                        const CUtensorMap* tm = &maps.m[wbox * kNumBoxHeights + (bx < n32 ? 0 : 1)];
+                        tensor_g2s_3d(patch + f * need1 + r0 * pitch, tm, xb0 >> 2, py0 + r0, (g0 + f) * P.n_lenses + src_slot,
+                                      &full[slot], policy);
+                    }
+                } else if (mode == kModeFastRows) {
+                    for (int t = lane; t < rows * nf; t += 32) {
+                        const int f = t / rows, r = t - f * rows;
+                        const unsigned char* img = P.src.data + ((long long)(g0 + f) * P.n_lenses + src_slot) * P.src.image_stride;
+                        const int sy = min(max(py0 + r, 0), P.src.height - 1);            // pole rows replicate
+                        bulk_g2s(patch + f * need1 + r * pitch, img + (long long)sy * P.src.pitch + xb0, (uint32_t)row_bytes, &full[slot]);
+                    }
+                } else if (mode == kModeFastSeam) {
+                    // the patch spans the seam: its first bytes come from the end of the image row, the rest
+                    // from its beginning (both pieces are multiples of 16 bytes)
+                    const int row_total = P.src.width * P.channels * (int)sizeof(TIn);
+                    const int start = xb0 < 0 ? xb0 + row_total : xb0;                   // wrapped first byte
+                    const int len1 = min(row_bytes, row_total - start);
+                    for (int t = lane; t < rows * nf; t += 32) {
+                        const int f = t / rows, r = t - f * rows;
+                        const unsigned char* img = P.src.data + ((long long)(g0 + f) * P.n_lenses + src_slot) * P.src.image_stride;
+                        const int sy = min(max(py0 + r, 0), P.src.height - 1);
+                        const unsigned char* row = img + (long long)sy * P.src.pitch;
+                        unsigned char* dst_row = patch + f * need1 + r * pitch;
+                        bulk_g2s(dst_row, row + start, (uint32_t)len1, &full[slot]);
+                        if (len1 < row_bytes) bulk_g2s(dst_row + len1, row, (uint32_t)(row_bytes - len1), &full[slot]);
+                    }
                 }
             }
         }
+        // ---- end of stream: one exit record per team (slots k, k + 1, ... belong to teams k mod n_teams, ...) ----
+        for (int e = 0; e < n_teams; ++e, ++k) {
+            const int slot = k % kSlots;
+            while ((k - oldest) >= kSlots) {
+                mbar_wait_relaxed(&empty[oldest % kSlots], (oldest / kSlots) & 1);
+                ++oldest;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                slots[slot].mode = kModeExit;
+                mbar_arrive(&full[slot]);
+            }
+            __syncwarp();
+        }
+#if R360_TILED_STATS
+        if (lane == 0) {
+            atomicAdd(&g_tiled_stats[2], (unsigned long long)(clock64() - st_t0));
+            atomicAdd(&g_tiled_stats[3], (unsigned long long)st_wait);
+            atomicAdd(&g_tiled_stats[4], (unsigned long long)st_slots);
+            atomicAdd(&g_tiled_stats[5], (unsigned long long)st_multi);
+        }
+#endif
         return;
     }
 
     // ================= consumer warps ================================================================
-    const int warp = tid >> 5, lane = tid & 31;
-    const int jl = tid >> 3;                 // tile row of this thread (4 rows per warp)
-    const int il0 = (tid & 7) * 4;           // first of its 4 pixels
+    const int team = tid / kTeamThreads;
+    const int ttid = tid - team * kTeamThreads;
+    const int warp = ttid >> 5, lane = tid & 31;
+    const int jl = ttid >> 3;                // tile row of this thread (4 rows per warp)
+    const int il0 = (ttid & 7) * 4;          // first of its 4 pixels
     const int row_out_bytes = kTile * P.channels * (int)sizeof(TOut);
     const float s0 = (float)(2 * il0 - (kTile - 1)) * (1.0f / (kTile - 1));
     const float ds = 2.0f / (kTile - 1);
     const float trow = (float)(2 * jl - (kTile - 1)) * (1.0f / (kTile - 1));
     const double dil0 = (double)il0, djl = (double)jl;
+    float* rowc = rowc_all + team * (kTile * 12);
     float* rc = rowc + jl * 12;
     // residual-coefficient tasks of this lane: coefficient c0 = lane & 7 always, c1 = c0 + 8 for c0 < 4
     const int ctask0 = lane & 7, ctask1 = ctask0 + 8;
@@ -668,48 +770,34 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
     const int st_r = lane / chunks_per_row, st_c = lane - st_r * chunks_per_row;
     const int st_dr = 32 / chunks_per_row, st_dc = 32 - st_dr * chunks_per_row;
     const uint32_t full_s = smem_u32(full), empty_s = smem_u32(empty);
-    unsigned char* stage = stage0;          // each warp only ever touches its own 4 rows of it
+    unsigned char* stage = stage_all + team * FR * P.out_stage_bytes;     // [FR][tile]; a warp only touches its own 4 rows
     TOut* stage_row = reinterpret_cast<TOut*>(stage) + (jl * kTile + il0) * P.channels;
+    const int stage_fstride = P.out_stage_bytes / (int)sizeof(TOut);      // elements between the frames of the stage
     // per-lane constants of the lane-per-column path (kept in registers across tiles: the int -> double
     // conversions run on the slow conversion unit)
     const uint32_t col_tab = smem_u32(table);
     const float col_s = (float)(2 * lane - (kTile - 1)) * (1.0f / (kTile - 1));
-    const double col_dlane = (double)lane, col_drow = (double)(warp * kRPW);
-    int k = 0;
-    for (int item = blockIdx.x; item < total; item += gridDim.x, ++k) {
-        const int slot = k & (kSlots - 1);
+    const double col_dlane = (double)lane, col_drow = (double)(warp * 4);
+#if R360_TILED_STATS
+    const long long st_c0 = clock64();
+    long long st_cwait = 0;
+#endif
+    for (int k = team;; k += n_teams) {
+        const int slot = k % kSlots;
+#if R360_TILED_STATS
+        const long long st_w0 = clock64();
+#endif
         mbar_wait_s(full_s + slot * 8, (k / kSlots) & 1);
+#if R360_TILED_STATS
+        st_cwait += clock64() - st_w0;
+#endif
         const SlotInfo* si = &slots[slot];
         const int mode = si->mode;
-        if (mode == kModeFallback) {                       // remap_fallback_kernel owns this tile
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(empty_s + slot * 8);
-            continue;
-        }
+        if (mode == kModeExit) break;
+        const int nf = si->nf;
+        const uint32_t fstride = si->fstride;
         const TilePlan* plan = &planbuf[slot];
-        // lane-per-column tiles (8-bit RGB bicubic): whole tile inside the image, vector stores possible
-        constexpr bool kHasColumnPath = kFastU8 && (INTERP == kCubic || R360_LINEAR_MAP_B);
-        const bool column_path = kHasColumnPath && mode != kModeFill && mode != kModeFastSeam && P.channels == 3 &&
-                                 si->full_tile && P.bulk_store_ok;
-        if (kCW > kConsumerWarps && !column_path && warp >= kConsumerWarps) {
-            // the 4-rows-per-warp code below is written for eight warps: the others only release the patch
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(empty_s + slot * 8);
-            continue;
-        }
-        if (kRPW != 4 && column_path) {
-            // kRPW rows x 12 residual coefficients of this warp's rows, one task per lane
-            constexpr int kLanesPerRow = 32 / kRPW;
-            const int row = warp * kRPW + lane / kLanesPerRow, c = lane % kLanesPerRow;
-            if (c < 12) {
-                const float* K = (c < 6 ? plan->rx + c : plan->ry + (c - 6));
-                const float tr = (float)(2 * row - (kTile - 1)) * (1.0f / (kTile - 1));
-                float a = K[30];
-#pragma unroll
-                for (int l = 4; l >= 0; --l) a = fmaf(a, tr, K[l * 6]);
-                rowc_col[row * 12 + c] = a;
-            }
-        } else if (mode != kModeFill) {
+        if (mode != kModeFill) {
             // the 12 residual coefficients of this lane's row, spread over the 8 lanes that share the row
             const float* K = plan->rx + koff0;
             float a = K[30];
@@ -725,100 +813,53 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
             }
         }
         __syncwarp();
-        if constexpr (kFastU8 && (INTERP == kCubic || R360_LINEAR_MAP_B)) {
-            // ---- bicubic 8-bit RGB: lane = pixel column, kRPW rows per lane ----------------------------
-            // Sixteen taps per pixel make this path shared-memory bound; with adjacent lanes on adjacent
-            // pixels the tap loads of a warp fall into neighbouring words (few bank conflicts), and the
-            // finished row leaves straight from registers: three lanes out of four hold one 32-bit
-            // word of the 96-byte row after a shuffle, so the store is contiguous.
-            if (column_path) {
-                const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch, tab = col_tab;
-                const float s = col_s;
-                const double axi = plan->ax[1], ayi = plan->ay[1], axj = plan->ax[2], ayj = plan->ay[2];
-                double ax_r = fma(axi, col_dlane, fma(axj, col_drow, plan->ax[0]));
-                double ay_r = fma(ayi, col_dlane, fma(ayj, col_drow, plan->ay[0]));
+        if constexpr (kFastU8) {
+            // lane-per-column tiles: whole tile inside the image, vector stores possible
+            if (mode != kModeFill && mode != kModeFastSeam && P.channels == 3 && si->full_tile && P.bulk_store_ok) {
                 const int m = lane & 3;
-                unsigned char* out_word = P.dst.data + si->dst_tile + (long long)(warp * kRPW) * P.dst.pitch +
-                                          ((lane >> 2) * 3 + m) * 4;
-#pragma unroll
-                for (int q = 0; q < kRPW; ++q) {
-                    const float* rq = (kRPW != 4 ? rowc_col : rowc) + (warp * kRPW + q) * 12;
-                    const float4 c0 = *reinterpret_cast<const float4*>(rq), c1 = *reinterpret_cast<const float4*>(rq + 4),
-                                 c2 = *reinterpret_cast<const float4*>(rq + 8);
-                    float dx = c1.y, dy = c2.w;
-                    dx = fmaf(dx, s, c1.x); dx = fmaf(dx, s, c0.w); dx = fmaf(dx, s, c0.z); dx = fmaf(dx, s, c0.y); dx = fmaf(dx, s, c0.x);
-                    dy = fmaf(dy, s, c2.z); dy = fmaf(dy, s, c2.y); dy = fmaf(dy, s, c2.x); dy = fmaf(dy, s, c1.w); dy = fmaf(dy, s, c1.z);
-#if R360_WHATIF == 6
-                    const float sx = (float)ax_r + dx, sy = (float)ay_r + dy;      // what-if: no float64 in the pixel loop
-                    ax_r += 1.0;
-#else
-                    const float sx = __double2float_rn(ax_r + (double)dx), sy = __double2float_rn(ay_r + (double)dy);
-                    ax_r += axj; ay_r += ayj;
-#endif
-                    uint32_t own;
-                if constexpr (INTERP == kCubic) own = bicubic_u8c3(bias, pitch, tab, round_bits(sx), round_bits(sy));
-                else own = bilinear_u8c3(bias, pitch, round_bits(sx), round_bits(sy));
-                    const uint32_t nxt = __shfl_down_sync(0xffffffffu, own, 1);
-                    const uint32_t word = (own >> (8 * m)) | (nxt << (24 - 8 * m));
-#if R360_WHATIF == 5
-                    if (m < 3 && word == 0x12345678u)                               // what-if: (almost) no global stores
-                        asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(out_word), "r"(word) : "memory");
-#else
-                    // three lanes out of four store: a predicated store (no divergent branch around it); the row
-                    // pointer is carried along instead of being rebuilt from the tile origin for every row
-                    asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %2, 3;\n@p st.global.cs.b32 [%0], %1;\n}"
-                                 ::"l"(out_word), "r"(word), "r"((uint32_t)m) : "memory");
-#endif
-                    out_word += P.dst.pitch;
-                }
+                unsigned char* out_word = P.dst.data + si->dst_tile + (long long)(warp * 4) * P.dst.pitch + ((lane >> 2) * 3 + m) * 4;
+                if (FR > 1 && nf == FR)
+                    column_rows_u8c3<INTERP, FR>(plan, rowc + warp * 48, si->bias, (uint32_t)si->pitch, col_tab, fstride, col_s,
+                                                 col_dlane, col_drow, out_word, P.dst.pitch, P.dst_fstride, m);
+                else
+                    column_rows_u8c3<INTERP, 1>(plan, rowc + warp * 48, si->bias, (uint32_t)si->pitch, col_tab, fstride, col_s,
+                                                col_dlane, col_drow, out_word, P.dst.pitch, P.dst_fstride, m);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_s(empty_s + slot * 8);
                 continue;
             }
         }
         if (mode == kModeFill) {
-            for (int q = 0; q < 4 * P.channels; ++q) stage_row[q] = Finish<TIn, TOut>::run(P.border_value);
-        } else if (mode == kModeFastSeam) {
-            // ---- a tile on the +-180 degree seam: same arithmetic, one pixel at a time, the coordinate
-            //      wrapped into (-0.5, W - 0.5] before the float32 cast; the taps of a wrapped pixel sit one
-            //      image width further along the (unwrapped) patch -------------------------------------
-            unsigned char* patch = smem + (si->patch_saddr - smem_u32(smem));
-            const int row_total = P.src.width * P.channels * (int)sizeof(TIn);
-            const double period32 = 32.0 * P.src.width;
-            const double axi = plan->ax[1], ayi = plan->ay[1];
-            const double ax_b = fma(plan->ax[2], djl, plan->ax[0]), ay_b = fma(plan->ay[2], djl, plan->ay[0]);
-#pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                const float s = fmaf((float)q, ds, s0);
-                float dx = rc[5], dy = rc[11];
-#pragma unroll
-                for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
-                double sx = fma(axi, (double)(il0 + q), ax_b) + (double)dx;
-                const double sy = fma(ayi, (double)(il0 + q), ay_b) + (double)dy;
-                int wrapk = 0;
-                if (sx > period32 - 16.0) { sx -= period32; wrapk = 1; }
-                else if (sx <= -16.0) { sx += period32; wrapk = -1; }
-                const PatchTaps<TIn> taps{patch, si->pitch, si->xb0 - wrapk * row_total, si->py0, P.channels};
-                sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
-                                                __double2float_rn(sx) * (1.0f / 32.0f), __double2float_rn(sy) * (1.0f / 32.0f),
-                                                stage_row + q * P.channels);
-            }
+            for (int f = 0; f < nf; ++f)
+                for (int q = 0; q < 4 * P.channels; ++q) stage_row[f * stage_fstride + q] = Finish<TIn, TOut>::run(P.border_value);
         } else {
             // residual polynomial in float32, affine part in float64 (absolute, exact to ~1e-10 px);
-            // the final double -> float conversion IS the float32 cast of the map cv2.remap would get
+            // the final double -> float conversion IS the float32 cast of the map cv2.remap would get.
+            // A tile on the +-180 degree seam (kModeFastSeam) wraps its coordinate into (-0.5, W - 0.5] before
+            // that cast; the taps of a wrapped pixel sit one image width further along the (unwrapped) patch:
+            // woff[q] is that byte offset, zero everywhere else.
             const float4 c0 = *reinterpret_cast<const float4*>(rc), c1 = *reinterpret_cast<const float4*>(rc + 4),
                          c2 = *reinterpret_cast<const float4*>(rc + 8);
             const double axi = plan->ax[1], ayi = plan->ay[1];
             double ax_q = fma(axi, dil0, fma(plan->ax[2], djl, plan->ax[0]));
             double ay_q = fma(ayi, dil0, fma(plan->ay[2], djl, plan->ay[0]));
+            const bool seam = mode == kModeFastSeam;
+            const int row_total = P.src.width * P.channels * (int)sizeof(TIn);
+            const double period32 = 32.0 * P.src.width;
             float sxf[4], syf[4];
+            int woff[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float s = fmaf((float)q, ds, s0);
-                float dx = c1.y, dy = c2.w;
-                dx = fmaf(dx, s, c1.x); dx = fmaf(dx, s, c0.w); dx = fmaf(dx, s, c0.z); dx = fmaf(dx, s, c0.y); dx = fmaf(dx, s, c0.x);
-                dy = fmaf(dy, s, c2.z); dy = fmaf(dy, s, c2.y); dy = fmaf(dy, s, c2.x); dy = fmaf(dy, s, c1.w); dy = fmaf(dy, s, c1.z);
-                sxf[q] = __double2float_rn(ax_q + (double)dx);
+                float dx, dy;
+                residual_xy(c0, c1, c2, s, dx, dy);
+                double sx = ax_q + (double)dx;
+                woff[q] = 0;
+                if (seam) {
+                    if (sx > period32 - 16.0) { sx -= period32; woff[q] = row_total; }
+                    else if (sx <= -16.0) { sx += period32; woff[q] = -row_total; }
+                }
+                sxf[q] = __double2float_rn(sx);
                 syf[q] = __double2float_rn(ay_q + (double)dy);
                 ax_q += axi; ay_q += ayi;
             }
@@ -826,55 +867,85 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
             if constexpr (kFastU8) {
                 if (P.channels == 3) {
                     const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch;
-                    uint32_t px[4];
                     if constexpr (INTERP == kLinear) {
+                        BilinearPrep pp[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) px[q] = bilinear_u8c3(bias, pitch, round_bits(sxf[q]), round_bits(syf[q]));
+                        for (int q = 0; q < 4; ++q) pp[q] = bilinear_prep_u8c3(bias + (uint32_t)woff[q], pitch, round_bits(sxf[q]), round_bits(syf[q]));
+                        auto frames = [&](auto nfc) {
+                            constexpr int NF = decltype(nfc)::value;
+                            uint32_t w[NF][3];          // every frame sampled before the first stage store (which the
+#pragma unroll                                          // compiler must assume to alias the patches)
+                            for (int f = 0; f < NF; ++f) {
+                                uint32_t px[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) px[q] = bilinear_taps_u8c3(pp[q], pitch, (uint32_t)f * fstride);
+                                pack4_rgb(px[0], px[1], px[2], px[3], w[f][0], w[f][1], w[f][2]);
+                            }
+#pragma unroll
+                            for (int f = 0; f < NF; ++f) {
+                                uint32_t* o = reinterpret_cast<uint32_t*>(stage_row + f * stage_fstride);
+                                o[0] = w[f][0]; o[1] = w[f][1]; o[2] = w[f][2];
+                            }
+                        };
+                        if (FR > 1 && nf == FR) frames(std::integral_constant<int, FR>{});
+                        else frames(std::integral_constant<int, 1>{});
                     } else {
+                        // bicubic tiles off the lane-per-column path (partial tiles, unaligned destinations)
                         const uint32_t tab = smem_u32(table);
+                        for (int f = 0; f < nf; ++f) {
+                            uint32_t px[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) px[q] = bicubic_u8c3(bias, pitch, tab, round_bits(sxf[q]), round_bits(syf[q]));
+                            for (int q = 0; q < 4; ++q)
+                                px[q] = bicubic_u8c3(bias + (uint32_t)woff[q] + (uint32_t)f * fstride, pitch, tab, round_bits(sxf[q]), round_bits(syf[q]));
+                            uint32_t w0, w1, w2;
+                            pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
+                            uint32_t* o = reinterpret_cast<uint32_t*>(stage_row + f * stage_fstride);
+                            o[0] = w0; o[1] = w1; o[2] = w2;
+                        }
                     }
-                    uint32_t w0, w1, w2;
-                    pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
-                    uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
-                    o[0] = w0; o[1] = w1; o[2] = w2;
                     done = true;
                 }
             }
             if constexpr (kFastLanczosU8) {
                 if (P.channels == 3) {
-                    const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch;
-                    uint32_t px[4];
+                    const uint32_t pitch = (uint32_t)si->pitch;
+                    for (int f = 0; f < nf; ++f) {
+                        const uint32_t bias = si->bias + (uint32_t)f * fstride;
+                        uint32_t px[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        px[q] = P.use_table == 2
-                                    ? lanczos4_u8c3<true>(bias, pitch, nullptr, smem_u32(table), round_bits(sxf[q]), round_bits(syf[q]))
-                                    : lanczos4_u8c3<false>(bias, pitch, g_tables.lanczos_fixed, 0u, round_bits(sxf[q]), round_bits(syf[q]));
-                    uint32_t w0, w1, w2;
-                    pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
-                    uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
-                    o[0] = w0; o[1] = w1; o[2] = w2;
+                        for (int q = 0; q < 4; ++q)
+                            px[q] = P.use_table == 2
+                                        ? lanczos4_u8c3<true>(bias + (uint32_t)woff[q], pitch, nullptr, smem_u32(table), round_bits(sxf[q]), round_bits(syf[q]))
+                                        : lanczos4_u8c3<false>(bias + (uint32_t)woff[q], pitch, g_tables.lanczos_fixed, 0u, round_bits(sxf[q]), round_bits(syf[q]));
+                        uint32_t w0, w1, w2;
+                        pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
+                        uint32_t* o = reinterpret_cast<uint32_t*>(stage_row + f * stage_fstride);
+                        o[0] = w0; o[1] = w1; o[2] = w2;
+                    }
                     done = true;
                 }
             }
             if constexpr (kFastNearestU8) {
                 if (P.channels == 3 || P.channels == 1) {
-                    const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch;
-                    uint32_t px[4];
-                    if (P.channels == 3) {
+                    const uint32_t pitch = (uint32_t)si->pitch;
+                    uint32_t ux[4], uy[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            px[q] = nearest_u8c3(bias, pitch, round_bits(sxf[q] * (1.0f / 32.0f)), round_bits(syf[q] * (1.0f / 32.0f)));
-                        uint32_t w0, w1, w2;
-                        pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
-                        uint32_t* o = reinterpret_cast<uint32_t*>(stage_row);
-                        o[0] = w0; o[1] = w1; o[2] = w2;
-                    } else {
+                    for (int q = 0; q < 4; ++q) { ux[q] = round_bits(sxf[q] * (1.0f / 32.0f)); uy[q] = round_bits(syf[q] * (1.0f / 32.0f)); }
+                    for (int f = 0; f < nf; ++f) {
+                        const uint32_t bias = si->bias + (uint32_t)f * fstride;
+                        uint32_t px[4];
+                        if (P.channels == 3) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            px[q] = nearest_u8c1(bias, pitch, round_bits(sxf[q] * (1.0f / 32.0f)), round_bits(syf[q] * (1.0f / 32.0f)));
-                        *reinterpret_cast<uint32_t*>(stage_row) = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+                            for (int q = 0; q < 4; ++q) px[q] = nearest_u8c3(bias + (uint32_t)woff[q], pitch, ux[q], uy[q]);
+                            uint32_t w0, w1, w2;
+                            pack4_rgb(px[0], px[1], px[2], px[3], w0, w1, w2);
+                            uint32_t* o = reinterpret_cast<uint32_t*>(stage_row + f * stage_fstride);
+                            o[0] = w0; o[1] = w1; o[2] = w2;
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) px[q] = nearest_u8c1(bias + (uint32_t)woff[q], pitch, ux[q], uy[q]);
+                            *reinterpret_cast<uint32_t*>(stage_row + f * stage_fstride) = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+                        }
                     }
                     done = true;
                 }
@@ -884,54 +955,79 @@ __global__ void __launch_bounds__(kMaxTiledThreads) remap_tiled_kernel(const __g
                     const uint32_t bias = si->bias, pitch = (uint32_t)si->pitch;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float acc[3];
-                        if constexpr (INTERP == kLinear) bilinear_u16c3(bias, pitch, round_bits(sxf[q]), round_bits(syf[q]), acc);
-                        else bicubic_u16c3(bias, pitch, g_tables.cubic_1d, round_bits(sxf[q]), round_bits(syf[q]), acc);
+                        if constexpr (INTERP == kLinear) {
+                            const BilinearPrepU16 pp = bilinear_prep_u16c3(bias + (uint32_t)woff[q], pitch, round_bits(sxf[q]), round_bits(syf[q]));
+                            for (int f = 0; f < nf; ++f) {
+                                float acc[3];
+                                bilinear_taps_u16c3(pp, pitch, (uint32_t)f * fstride, acc);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) stage_row[q * 3 + c] = Finish<TIn, TOut>::run(acc[c]);
+                                for (int c = 0; c < 3; ++c) stage_row[f * stage_fstride + q * 3 + c] = Finish<TIn, TOut>::run(acc[c]);
+                            }
+                        } else {
+                            const BicubicPrepU16 pp = bicubic_prep_u16c3(bias + (uint32_t)woff[q], pitch, g_tables.cubic_1d, round_bits(sxf[q]), round_bits(syf[q]));
+                            for (int f = 0; f < nf; ++f) {
+                                float acc[3];
+                                bicubic_taps_u16c3(pp, pitch, (uint32_t)f * fstride, acc);
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) stage_row[f * stage_fstride + q * 3 + c] = Finish<TIn, TOut>::run(acc[c]);
+                            }
+                        }
                     }
                     done = true;
                 }
             }
             if (!done) {
                 unsigned char* patch = smem + (si->patch_saddr - smem_u32(smem));
-                const PatchTaps<TIn> taps{patch, si->pitch, si->xb0, si->py0, P.channels};
+#pragma unroll 1
+                for (int f = 0; f < nf; ++f) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
-                                                    sxf[q] * (1.0f / 32.0f), syf[q] * (1.0f / 32.0f),
-                                                    stage_row + q * P.channels);
+                    for (int q = 0; q < 4; ++q) {
+                        const PatchTaps<TIn> taps{patch + f * fstride, si->pitch, si->xb0 - woff[q], si->py0, P.channels};
+                        sample_pixel<INTERP, TIn, TOut>(taps, P.channels, P.src.width, P.src.height, P.border_value,
+                                                        sxf[q] * (1.0f / 32.0f), syf[q] * (1.0f / 32.0f),
+                                                        stage_row + f * stage_fstride + q * P.channels);
+                    }
+                }
             }
         }
-        // ---- this warp's 4 rows leave as 16-byte vector stores; the patch is released ----------------
+        // ---- this warp's 4 rows of every frame leave as 16-byte vector stores; the patches are released ----
         const bool vec_store = si->full_tile && P.bulk_store_ok;
-        const long long dst_tile = si->dst_tile;
+        const long long dst_tile = si->dst_tile, dst_off = si->dst_off;
+        const int i0 = si->i0, j0 = si->j0;
         __syncwarp();
         if (lane == 0) mbar_arrive_s(empty_s + slot * 8);  // all 8 warps arrived -> the producer may reuse the bytes
-        if (vec_store) {
-            unsigned char* dst_rows = P.dst.data + dst_tile + (long long)(warp * 4) * P.dst.pitch;
-            const unsigned char* src_rows = stage + warp * 4 * row_out_bytes;
-            // chunk e = lane, lane + 32, ... of the 4 * chunks_per_row chunks; (r, c) advanced without dividing
-            for (int r = st_r, c = st_c; r < 4;) {
-                st_global_streaming(dst_rows + (long long)r * P.dst.pitch + c * 16,
-                                    *reinterpret_cast<const int4*>(src_rows + r * row_out_bytes + c * 16));
-                r += st_dr; c += st_dc;
-                if (c >= chunks_per_row) { c -= chunks_per_row; ++r; }
-            }
-        } else {
-            const int i0 = si->i0, j0 = si->j0;
-            unsigned char* dst_base = P.dst.data + si->dst_off;
-            const int nelem = kTile * P.channels;
-            for (int e = lane; e < 4 * nelem; e += 32) {
-                const int r = warp * 4 + e / nelem, c = e % nelem;
-                const int i = i0 + c / P.channels, j = j0 + r;
-                if (i < P.dst.width && j < P.dst.height)
-                    reinterpret_cast<TOut*>(dst_base + (long long)j * P.dst.pitch)[(long long)i0 * P.channels + c] =
-                        reinterpret_cast<const TOut*>(stage)[r * nelem + c];
+        for (int f = 0; f < nf; ++f) {
+            const unsigned char* stage_f = stage + f * P.out_stage_bytes;
+            if (vec_store) {
+                unsigned char* dst_rows = P.dst.data + dst_tile + f * P.dst_fstride + (long long)(warp * 4) * P.dst.pitch;
+                const unsigned char* src_rows = stage_f + warp * 4 * row_out_bytes;
+                // chunk e = lane, lane + 32, ... of the 4 * chunks_per_row chunks; (r, c) advanced without dividing
+                for (int r = st_r, c = st_c; r < 4;) {
+                    st_global_streaming(dst_rows + (long long)r * P.dst.pitch + c * 16,
+                                        *reinterpret_cast<const int4*>(src_rows + r * row_out_bytes + c * 16));
+                    r += st_dr; c += st_dc;
+                    if (c >= chunks_per_row) { c -= chunks_per_row; ++r; }
+                }
+            } else {
+                unsigned char* dst_base = P.dst.data + dst_off + f * P.dst_fstride;
+                const int nelem = kTile * P.channels;
+                for (int e = lane; e < 4 * nelem; e += 32) {
+                    const int r = warp * 4 + e / nelem, c = e % nelem;
+                    const int i = i0 + c / P.channels, j = j0 + r;
+                    if (i < P.dst.width && j < P.dst.height)
+                        reinterpret_cast<TOut*>(dst_base + (long long)j * P.dst.pitch)[(long long)i0 * P.channels + c] =
+                            reinterpret_cast<const TOut*>(stage_f)[r * nelem + c];
+                }
             }
         }
         __syncwarp();                              // the stage rows are free again
     }
+#if R360_TILED_STATS
+    if (lane == 0) {
+        atomicAdd(&g_tiled_stats[0], (unsigned long long)(clock64() - st_c0));
+        atomicAdd(&g_tiled_stats[1], (unsigned long long)st_cwait);
+    }
+#endif
 }
 
 // Debug twin: what the tiled kernel samples at, written as maps (r360_plan_coords).  One block per

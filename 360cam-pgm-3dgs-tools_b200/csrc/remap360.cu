@@ -389,6 +389,8 @@ int remap_direct(int proj, const r360_images* src, const r360_images* dst, const
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+constexpr int kMaxRingBytes = 200 * 1024;       // shared-memory ring of one block
+
 struct WorkspaceLayout { size_t header, views, plans, fallback, total; };
 
 WorkspaceLayout workspace_layout(int n_views, int out_w, int out_h) {
@@ -410,6 +412,7 @@ struct r360_plan {
     std::vector<ViewDev> views;
     int tiles_x, tiles_y, n_tiles, n_fallback;
     int out_stage_bytes, patch_budget, ring_bytes, smem_bytes, ctas_per_sm, use_table, sm_count;
+    int frames_pref, ctas_multi_pref;     // launch shape for batches (choose_shape)
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
     PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback;
@@ -504,23 +507,30 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-        int want = pl->use_table == 2 ? 1 : pl->use_table ? 2 : 4;
+        // blocks per SM: what the kernel's registers are budgeted for (tiled_min_blocks); 8-bit bicubic without the
+        // packed sampler (1 / 4 channels) has no table in shared memory but is compiled for 2 blocks all the same
+        int want = pl->use_table == 2 ? 1 : tiled_min_blocks(in_es, pl->pr.interp);
         if (const char* env = std::getenv("R360_TILED_CTAS_PER_SM")) want = std::atoi(env) > 0 ? std::atoi(env) : want;
-        const int fixed = kTiledFixedSmem + table_bytes(pl->use_table) + pl->out_stage_bytes + 128;
+        const int fixed = kTiledFixedSmem + table_bytes(pl->use_table) + kTeams * pl->out_stage_bytes + 128;   // one frame per item
         for (;; --want) {
             const int per_block = smem_per_sm / want - 1024;       // 1 KB per block is reserved by the driver
             pl->ring_bytes = (per_block - fixed) & ~127;
             if (pl->ring_bytes >= 24 * 1024 || want == 1) break;
         }
         if (pl->ring_bytes < 8192) pl->ring_bytes = 8192;
-        if (pl->ring_bytes > 160 * 1024) pl->ring_bytes = 160 * 1024;
+        if (pl->ring_bytes > kMaxRingBytes) pl->ring_bytes = kMaxRingBytes;
         if (const char* env = std::getenv("R360_RING_KB")) {                   // experiments: leave more of the SM to L1
             const int cap = std::atoi(env) * 1024;
             if (cap >= 8192 && cap < pl->ring_bytes) pl->ring_bytes = cap & ~127;
         }
-        pl->patch_budget = pl->ring_bytes;                          // a patch may use the whole ring
         pl->ctas_per_sm = want;
         pl->smem_bytes = fixed + pl->ring_bytes;
+        // batches: frames per work item / blocks per SM (choose_shape).  A patch may use the whole ring of the
+        // smallest shape a call can take: the one with kMaxFramesPerItem output stages per team.
+        pl->frames_pref = pl->use_table == 2 ? 1 : 2;
+        pl->ctas_multi_pref = want;
+        pl->patch_budget = pl->ring_bytes - (kMaxFramesPerItem - 1) * kTeams * pl->out_stage_bytes;
+        if (pl->patch_budget < 8192) pl->patch_budget = 8192;
     }
     // the data pointers are not known yet: assume 16-byte aligned bases (checked at remap time)
     pl->bulk_load_ok = src->pitch_bytes % 16 == 0 && src->image_stride_bytes % 16 == 0 &&
@@ -570,23 +580,58 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     return R360_OK;
 }
 
+// Launch shape of the tiled kernel for one call: frames per work item, consumer teams per block, blocks per SM
+// and the shared-memory ring that is left.  Every fast tile of the plan fits the ring of every shape chosen here
+// (ring >= plan->patch_budget); what a shape changes is how many frames share one coordinate / weight set-up.
+struct TiledShape { int fr, teams, ctas, ring, smem, multi_budget; };
+
+int env_int(const char* name, int fallback) {
+    const char* e = std::getenv(name);
+    return e && *e ? std::atoi(e) : fallback;
+}
+
+bool shape_for(const r360_plan* pl, int fr, int teams, int ctas, int smem_per_sm, TiledShape* out) {
+    const int fixed = kTiledFixedSmem + table_bytes(pl->use_table) + teams * fr * pl->out_stage_bytes + 128;
+    const int per_block = smem_per_sm / ctas - 1024;               // 1 KB per block is reserved by the driver
+    int ring = (per_block - fixed) & ~127;
+    if (ring > kMaxRingBytes) ring = kMaxRingBytes;
+    if (ring < pl->patch_budget) return false;
+    out->fr = fr; out->teams = teams; out->ctas = ctas; out->ring = ring; out->smem = fixed + ring;
+    // an item takes all its frames at once when two such items fit the ring (one being sampled, one in flight)
+    const int pct = std::min(100, std::max(10, env_int("R360_MULTI_PCT", 50)));
+    out->multi_budget = (int)((long long)ring * pct / 100);
+    return true;
+}
+
+TiledShape choose_shape(const r360_plan* pl, int n_groups) {
+    int dev = 0, smem_per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    // defaults measured on B200 (profiles/README.md, round 2); the environment overrides are for experiments
+    int fr = n_groups >= 4 ? pl->frames_pref : n_groups >= 2 ? std::min(2, pl->frames_pref) : 1;
+    fr = env_int("R360_FRAMES", fr);
+    if (fr != 1 && fr != 2 && fr != 4) fr = 1;
+    if (fr > n_groups) fr = n_groups >= 2 ? 2 : 1;
+    int teams = kTeams;                      // a build-time constant of the kernels (R360_TILED_TEAMS)
+    int ctas = std::max(1, env_int("R360_TILED_CTAS_PER_SM", fr > 1 ? pl->ctas_multi_pref : pl->ctas_per_sm));
+    TiledShape s;
+    for (;;) {
+        if (shape_for(pl, fr, teams, ctas, smem_per_sm, &s)) return s;
+        if (ctas > 1) --ctas;
+        else if (fr > 1) fr /= 2;
+        else break;
+    }
+    // the plan's own single-frame shape always fits (it defined the patch budget)
+    s.fr = 1; s.teams = kTeams; s.ctas = pl->ctas_per_sm; s.ring = pl->ring_bytes; s.smem = pl->smem_bytes; s.multi_budget = 0;
+    return s;
+}
+
 struct TiledLauncher {
     const r360_plan* pl; const r360_images* src; const r360_images* dst; cudaStream_t s;
 
-    template <int PROJ, int INTERP, typename TIn, typename TOut> int run() {
-        const LaunchParams& lp = pl->pr.lp;
-        const int n_groups = src->count / pl->pr.n_lenses;
-        TiledParams T;
-        std::memset(&T, 0, sizeof(T));
-        T.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
-        T.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
-        T.channels = lp.channels; T.n_views = pl->pr.n_views; T.n_groups = n_groups;
-        T.n_lenses = pl->pr.n_lenses; T.tiles_x = pl->tiles_x; T.tiles_y = pl->tiles_y;
-        T.out_stage_bytes = pl->out_stage_bytes; T.ring_bytes = pl->ring_bytes;
-        T.bulk_store_ok = pl->bulk_store_ok; T.use_table = pl->use_table; T.border_value = lp.border_value;
-        T.plans = pl->d_plans;
-
-        auto kernel = remap_tiled_kernel<INTERP, TIn, TOut>;
+    template <int INTERP, typename TIn, typename TOut, int FR>
+    int launch(const TiledParams& Q, const TensorMaps& maps, const TiledShape& shape, long long grid) {
+        auto kernel = remap_tiled_kernel<INTERP, TIn, TOut, FR>;
         {
             // opt this instantiation in to the device's full shared memory once per device (the attribute is
             // per context; plans of different channel counts need different amounts of the same kernel)
@@ -602,16 +647,39 @@ struct TiledLauncher {
                 configured[dev] = true;
             }
         }
+        kernel<<<dim3((unsigned)grid), shape.teams * kTeamThreads + 32, shape.smem, s>>>(Q, maps);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        R360_CUDA(cudaGetLastError());
+        return R360_OK;
+    }
+
+    template <int PROJ, int INTERP, typename TIn, typename TOut> int run() {
+        const LaunchParams& lp = pl->pr.lp;
+        const int n_groups = src->count / pl->pr.n_lenses;
+        const TiledShape shape = choose_shape(pl, n_groups);
+        TiledParams T;
+        std::memset(&T, 0, sizeof(T));
+        T.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
+        T.dst = {static_cast<unsigned char*>(dst->data), dst->pitch_bytes, dst->image_stride_bytes, dst->width, dst->height};
+        T.channels = lp.channels; T.n_views = pl->pr.n_views; T.n_groups = n_groups;
+        T.n_lenses = pl->pr.n_lenses; T.tiles_x = pl->tiles_x; T.tiles_y = pl->tiles_y;
+        T.out_stage_bytes = pl->out_stage_bytes; T.ring_bytes = shape.ring;
+        T.bulk_store_ok = pl->bulk_store_ok; T.use_table = pl->use_table; T.border_value = lp.border_value;
+        T.frames_per_item = shape.fr; T.multi_budget = shape.multi_budget;
+        T.dst_fstride = (long long)pl->pr.n_views * T.dst.image_stride;
+        T.plans = pl->d_plans;
+
         // work items are indexed with 32-bit ints inside the kernel: chunk the groups if needed
         const long long per_group = (long long)pl->pr.n_views * pl->n_tiles;
-        const int max_groups = (int)std::max<long long>(1, (1LL << 30) / per_group);
+        int max_groups = (int)std::max<long long>(1, (1LL << 30) / per_group);
+        if (max_groups > shape.fr) max_groups -= max_groups % shape.fr;          // chunks hold whole frame blocks
         for (int g0 = 0; g0 < n_groups; g0 += max_groups) {
             TiledParams Q = T;
             Q.n_groups = n_groups - g0 < max_groups ? n_groups - g0 : max_groups;
             Q.src.data += (long long)g0 * pl->pr.n_lenses * Q.src.image_stride;
             Q.dst.data += (long long)g0 * pl->pr.n_views * Q.dst.image_stride;
-            const long long total = Q.n_groups * per_group;
-            long long grid = (long long)pl->sm_count * pl->ctas_per_sm;
+            const long long total = (long long)((Q.n_groups + shape.fr - 1) / shape.fr) * per_group;
+            long long grid = (long long)pl->sm_count * shape.ctas;
             if (grid > total) grid = total;
             TensorMaps maps;
             std::memset(&maps, 0, sizeof(maps));
@@ -634,11 +702,11 @@ struct TiledLauncher {
                 }
                 maps = hit->maps;
             }
-            constexpr bool kCubicU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value && INTERP == kCubic;
-            const int threads = consumer_warps(kCubicU8) * 32 + 32;      // must equal the instantiation's kCW
-            kernel<<<dim3((unsigned)grid), threads, pl->smem_bytes, s>>>(Q, maps);
-            g_launches.fetch_add(1, std::memory_order_relaxed);
-            R360_CUDA(cudaGetLastError());
+            int rc;
+            if (shape.fr == 4) rc = launch<INTERP, TIn, TOut, 4>(Q, maps, shape, grid);
+            else if (shape.fr == 2) rc = launch<INTERP, TIn, TOut, 2>(Q, maps, shape, grid);
+            else rc = launch<INTERP, TIn, TOut, 1>(Q, maps, shape, grid);
+            if (rc != R360_OK) return rc;
         }
 
         if (pl->n_fallback > 0) {
@@ -980,6 +1048,20 @@ int r360_debug_weight_tables_lanczos4(int16_t* fixed_65536, float* one_d_256) {
     build_weight_tables(&t);
     if (fixed_65536) std::memcpy(fixed_65536, t.lanczos_fixed, sizeof(t.lanczos_fixed));
     if (one_d_256) std::memcpy(one_d_256, t.lanczos_1d, sizeof(t.lanczos_1d));
+    return R360_OK;
+}
+
+// Experiment hook: the wait-time counters of builds with -DR360_TILED_STATS=1 (zeros otherwise); `reset` clears them.
+int r360_debug_tiled_stats(uint64_t* out8, int reset) {
+    unsigned long long h[8] = {};
+    if (out8) {
+        R360_CUDA(cudaMemcpyFromSymbol(h, g_tiled_stats, sizeof(h)));
+        for (int q = 0; q < 8; ++q) out8[q] = h[q];
+    }
+    if (reset) {
+        unsigned long long z[8] = {};
+        R360_CUDA(cudaMemcpyToSymbol(g_tiled_stats, z, sizeof(z)));
+    }
     return R360_OK;
 }
 

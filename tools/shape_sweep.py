@@ -1,0 +1,93 @@
+"""Kernel experiments: launch shapes of the tiled kernel on the bench workload (cfg 2: 8K u8 RGB frames ->
+full360coverage, 12 x 1600^2 views).  For the library named by R360_LIBRARY (default: the in-tree one) every
+combination of frames per work item / blocks per SM / multi-frame budget is timed kernel-only (CUDA events) and a
+digest of the first two frames' views is printed, so that shapes and variants can be compared bit for bit.
+
+    R360_LIBRARY=tools/variants/lib_x.so python tools/shape_sweep.py [--frames 16] [--interp cubic linear]
+        [--fr 1 2 4] [--ctas 0 1 2 3 4] [--pct 50 100]          (ctas 0 = the library's default)"""
+import argparse
+import hashlib
+import json
+import os
+import pathlib
+import sys
+
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "360cam-pgm-3dgs-tools_b200"))
+sys.path.insert(0, str(ROOT))
+import remap360  # noqa: E402
+from bench import preset_views  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--interp", nargs="+", default=["cubic", "linear"])
+    ap.add_argument("--fr", nargs="+", type=int, default=[1, 2, 4])
+    ap.add_argument("--ctas", nargs="+", type=int, default=[0])
+    ap.add_argument("--pct", nargs="+", type=int, default=[50])
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--dtype", default="u8")
+    ap.add_argument("--stats", action="store_true", help="wait-time counters of a -DR360_TILED_STATS=1 build")
+    ns = ap.parse_args()
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)
+    if ns.dtype == "u16":
+        src = torch.randint(0, 65536, (ns.frames, 3840, 7680, 3), dtype=torch.int32, device=dev, generator=g).to(torch.uint16)
+    else:
+        src = torch.randint(0, 256, (ns.frames, 3840, 7680, 3), dtype=torch.uint8, device=dev, generator=g)
+    views = [remap360.PerspectiveView(y, p, hf, vf) for _, y, p, hf, vf in preset_views("full360coverage", 1600)]
+    out = torch.empty((ns.frames, len(views), 1600, 1600, 3), dtype=src.dtype, device=dev)
+    lib = os.environ.get("R360_LIBRARY", "shipped")
+    for interp in ns.interp:
+        for fr in ns.fr:
+            for ctas in ns.ctas:
+                for pct in (ns.pct if fr > 1 else ns.pct[:1]):
+                    os.environ["R360_FRAMES"] = str(fr)
+                    os.environ["R360_MULTI_PCT"] = str(pct)
+                    if ctas > 0:
+                        os.environ["R360_TILED_CTAS_PER_SM"] = str(ctas)
+                    else:
+                        os.environ.pop("R360_TILED_CTAS_PER_SM", None)
+
+                    def fn():
+                        remap360.remap_erp(src, views, (1600, 1600), interp=interp, out=out)
+                    try:
+                        for _ in range(3):
+                            fn()
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(ns.iters):
+                            fn()
+                        e1.record()
+                        torch.cuda.synchronize()
+                    except Exception as exc:                      # a shape the library refuses
+                        print(json.dumps({"library": lib, "interp": interp, "fr": fr, "ctas": ctas, "pct": pct, "error": str(exc)}), flush=True)
+                        continue
+                    ms = e0.elapsed_time(e1) / ns.iters
+                    stats = None
+                    if ns.stats:
+                        import ctypes
+                        import numpy as np
+                        from remap360 import _lib
+                        L = _lib.load()
+                        buf = np.zeros(8, dtype=np.uint64)
+                        L.r360_debug_tiled_stats(ctypes.c_void_p(0), 1)
+                        fn()
+                        torch.cuda.synchronize()
+                        L.r360_debug_tiled_stats(ctypes.c_void_p(buf.ctypes.data), 0)
+                        c, cw, p, pw, sl, mu = (int(x) for x in buf[:6])
+                        stats = {"consumer_wait_frac": round(cw / max(c, 1), 4), "producer_wait_frac": round(pw / max(p, 1), 4),
+                                 "slots": sl, "multi_slots": mu}
+                    sha = hashlib.sha256(out[:2].view(torch.uint8).cpu().numpy().tobytes()).hexdigest()[:12]
+                    print(json.dumps({"library": os.path.basename(lib), "interp": interp, "dtype": ns.dtype, "fr": fr, "ctas": ctas,
+                                      "pct": pct, "ms": round(ms, 4), "Gpix_per_s": round(out.numel() / 3 / ms / 1e6, 1),
+                                      "sha": sha, "stats": stats}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
