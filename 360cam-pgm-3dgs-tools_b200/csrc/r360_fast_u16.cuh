@@ -121,4 +121,114 @@ __device__ __forceinline__ void bilinear_taps_u16c3(const BilinearPrepU16& p, ui
     }
 }
 
+// ---- lane-per-column samplers (the tiled kernel's full tiles) ----------------------------------------------
+// Same arithmetic again, organised for the pipes of the SM (tools/pipe_probe.cu): with one pixel per lane, lanes
+// 12 bytes apart at the 2:1 minification of an 8K -> 1600 px view, aligned 32-bit loads are bank-conflict free
+// (stride of three words) where the 64-bit loads above take four wavefronts; a 16-bit sample never straddles a
+// 32-bit word, so the low / high halves are taken with one byte permute against zero and no funnel shift; and
+// uint16 -> float32 costs nothing: the zero-extended sample IS the float32 denormal v * 2^-149, the weights carry
+// 2^126 (wy * wx <= 1.2 stays finite), products and sums are then the reference's scaled by 2^-23 bit for bit
+// (scaling by powers of two commutes with rounding while nothing underflows: the smallest non-zero product is
+// 2^-149 * 2^126 * 2^-15 > 2^-126), and one exact multiplication by 2^23 ends the accumulation.
+
+// The seven aligned words that hold a row of four RGB pixels starting at byte `addr` (even), and the twelve
+// samples in memory order as zero-extended words.  `hi_first` = addr & 2: the first sample sits in a high half.
+__device__ __forceinline__ void load_row_u16_words(uint32_t addr, bool hi_first, uint32_t* s) {
+    const uint32_t a4 = addr & ~3u;
+    uint32_t w[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) w[k] = lds32(a4 + 4 * k);
+    const uint32_t sel_even = hi_first ? 0x4432u : 0x4410u;      // sample 2k: half of word k chosen by the alignment
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        s[2 * k] = __byte_perm(w[k], 0u, sel_even);
+        // sample 2k + 1: high half of word k, or low half of word k + 1
+        s[2 * k + 1] = __byte_perm(hi_first ? w[k + 1] : w[k], 0u, hi_first ? 0x4410u : 0x4432u);
+    }
+}
+
+struct BicubicColPrepU16 {
+    uint32_t addr;
+    float wgt[16];          // wy[ky] * wx[kx] * 2^126, the reference's float32 products scaled
+};
+__device__ __forceinline__ BicubicColPrepU16 bicubic_col_prep_u16c3(uint32_t bias, uint32_t pitch, const float* wtab,
+                                                                   uint32_t ux, uint32_t uy) {
+    BicubicColPrepU16 p;
+    const uint32_t fx = ux & 31u, fy = uy & 31u;
+    p.addr = (ux >> 5) * 6u + (uy >> 5) * pitch + bias;
+    const float4 wx = __ldg(reinterpret_cast<const float4*>(wtab) + fx);
+    const float4 wy = __ldg(reinterpret_cast<const float4*>(wtab) + fy);
+    const float wxs[4] = {wx.x, wx.y, wx.z, wx.w}, wys[4] = {wy.x, wy.y, wy.z, wy.w};
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx)
+            p.wgt[ky * 4 + kx] = __fmul_rn(__fmul_rn(wys[ky], wxs[kx]), 8.507059173023462e37f);      // * 2^126, exact
+    return p;
+}
+__device__ __forceinline__ void bicubic_col_taps_u16c3(const BicubicColPrepU16& p, uint32_t pitch, uint32_t frame_off, float* acc) {
+    uint32_t addr = p.addr + frame_off;
+    const bool hi_first = (p.addr & 2u) != 0;
+    acc[0] = acc[1] = acc[2] = 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+        uint32_t s[12];
+        load_row_u16_words(addr, hi_first, s);
+        addr += pitch;
+        float row[3];
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float term = __fmul_rn(__uint_as_float(s[3 * kx + c]), p.wgt[ky * 4 + kx]);
+                row[c] = kx == 0 ? term : __fadd_rn(row[c], term);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], row[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] = __fmul_rn(acc[c], 8388608.0f);                               // * 2^23, exact
+}
+
+struct BilinearColPrepU16 {
+    uint32_t addr;
+    float wgt[4];
+};
+__device__ __forceinline__ BilinearColPrepU16 bilinear_col_prep_u16c3(uint32_t bias, uint32_t pitch, uint32_t ux, uint32_t uy) {
+    BilinearColPrepU16 p;
+    const uint32_t fx = ux & 31u, fy = uy & 31u;
+    p.addr = (ux >> 5) * 6u + (uy >> 5) * pitch + bias;
+    const float tx = (float)fx * (1.0f / 32.0f), ty = (float)fy * (1.0f / 32.0f);
+    const float wxs[2] = {1.0f - tx, tx}, wys[2] = {1.0f - ty, ty};
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 2; ++kx) p.wgt[ky * 2 + kx] = __fmul_rn(__fmul_rn(wys[ky], wxs[kx]), 8.507059173023462e37f);
+    return p;
+}
+__device__ __forceinline__ void bilinear_col_taps_u16c3(const BilinearColPrepU16& p, uint32_t pitch, uint32_t frame_off, float* acc) {
+    const uint32_t addr = p.addr + frame_off;
+    const bool hi_first = (p.addr & 2u) != 0;
+#pragma unroll
+    for (int ky = 0; ky < 2; ++ky) {
+        const uint32_t a4 = (addr + ky * pitch) & ~3u;
+        const uint32_t w0 = lds32(a4), w1 = lds32(a4 + 4), w2 = lds32(a4 + 8), w3 = lds32(a4 + 12);
+        const uint32_t sel_even = hi_first ? 0x4432u : 0x4410u, sel_odd = hi_first ? 0x4410u : 0x4432u;
+        const uint32_t s[6] = {__byte_perm(w0, 0u, sel_even), __byte_perm(hi_first ? w1 : w0, 0u, sel_odd),
+                               __byte_perm(w1, 0u, sel_even), __byte_perm(hi_first ? w2 : w1, 0u, sel_odd),
+                               __byte_perm(w2, 0u, sel_even), __byte_perm(hi_first ? w3 : w2, 0u, sel_odd)};
+#pragma unroll
+        for (int kx = 0; kx < 2; ++kx) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float term = __fmul_rn(__uint_as_float(s[3 * kx + c]), p.wgt[ky * 2 + kx]);
+                acc[c] = (ky == 0 && kx == 0) ? term : __fadd_rn(acc[c], term);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] = __fmul_rn(acc[c], 8388608.0f);
+}
+
 }  // namespace r360

@@ -294,6 +294,17 @@ __global__ void __launch_bounds__(64) plan_kernel(const __grid_constant__ PlanPa
     else plan_tile<kProjUndistort>(P);
 }
 
+// Sort key of every (view, tile) for the remap kernel's walk: source slot, then the centre row of the patch;
+// fallback tiles (not staged) get INT_MAX and drop off the end of the list.
+__global__ void __launch_bounds__(256) order_key_kernel(const TilePlan* plans, int n, int* keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TilePlan& p = plans[i];
+    const int mode = p.mode_slot & 0xff, slot = (p.mode_slot >> 8) & 0xff;
+    const bool staged = mode == kModeFast || mode == kModeFastRows || mode == kModeFastSeam;
+    keys[i] = mode == kModeFallback ? INT_MAX : (slot << 24) + (staged ? max(0, min(p.py0 + p.rows / 2, (1 << 24) - 1)) : 0);
+}
+
 // ---- bulk-async copy / mbarrier wrappers (PTX) ------------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -346,6 +357,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_by_kind(int kind) {
+    uint64_t pol;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else pol = l2_policy_evict_last();
     return pol;
 }
 __device__ __forceinline__ void tensor_g2s_3d(void* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar,
@@ -429,6 +447,9 @@ struct TiledParams {
     float border_value;
     long long dst_fstride;  // bytes between the same view of consecutive frames (n_views * image stride)
     const TilePlan* plans;  // whole plan (all views)
+    const int2* order;      // (view, tile) of the staged tiles sorted by source row: the order the items are walked in
+    int n_order;            // entries of `order` (tiles that are not on the fallback list)
+    int l2_policy;          // patch loads: 0 evict_last, 1 evict_normal, 2 evict_first (R360_L2_POLICY, experiments)
 };
 
 // Build-time shape of a block: consumer teams, and how many blocks per SM the register allocation must allow
@@ -544,6 +565,61 @@ __device__ __forceinline__ void column_rows_u8c3(const TilePlan* plan, const flo
     }
 }
 
+// ---- 16-bit RGB, lane = pixel column, 4 rows per lane (BASELINE config 4) ------------------------------
+// The samplers of r360_fast_u16.cuh; a finished pixel is three 16-bit values, two lanes (a pixel pair) own three
+// 32-bit words of the row: the even lane stores words 0 and 1 (it fetches the odd lane's first word with a
+// shuffle), the odd lane word 2.
+template <typename TOut>
+__device__ __forceinline__ uint32_t out_bits16(float a);
+template <>
+__device__ __forceinline__ uint32_t out_bits16<uint16_t>(float a) { return (uint32_t)Finish<uint16_t, uint16_t>::run(a); }
+template <>
+__device__ __forceinline__ uint32_t out_bits16<__half>(float a) { return (uint32_t)__half_as_ushort(Finish<uint16_t, __half>::run(a)); }
+
+template <int INTERP, typename TOut, int NF>
+__device__ __forceinline__ void column_rows_u16c3(const TilePlan* plan, const float* rowc_warp, uint32_t bias, uint32_t pitch,
+                                                  uint32_t fstride, float s, double dlane, double drow, unsigned char* out_row,
+                                                  long long dst_pitch, long long dst_fstride, int lane) {
+    const double axi = plan->ax[1], ayi = plan->ay[1], axj = plan->ax[2], ayj = plan->ay[2];
+    double ax_r = fma(axi, dlane, fma(axj, drow, plan->ax[0]));
+    double ay_r = fma(ayi, dlane, fma(ayj, drow, plan->ay[0]));
+    const bool odd = (lane & 1) != 0;
+    // even lane: words 0 and 1 of its pair at byte 12 * (lane / 2); odd lane: word 2
+    unsigned char* out_a = out_row + 12 * (lane >> 1) + (odd ? 8 : 0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float* rq = rowc_warp + q * 12;
+        const float4 c0 = *reinterpret_cast<const float4*>(rq), c1 = *reinterpret_cast<const float4*>(rq + 4),
+                     c2 = *reinterpret_cast<const float4*>(rq + 8);
+        float dx, dy;
+        residual_xy(c0, c1, c2, s, dx, dy);
+        const float sx = __double2float_rn(ax_r + (double)dx), sy = __double2float_rn(ay_r + (double)dy);
+        ax_r += axj; ay_r += ayj;
+        float acc[NF][3];
+        if constexpr (INTERP == kCubic) {
+            const BicubicColPrepU16 pp = bicubic_col_prep_u16c3(bias, pitch, g_tables.cubic_1d, round_bits(sx), round_bits(sy));
+#pragma unroll
+            for (int f = 0; f < NF; ++f) bicubic_col_taps_u16c3(pp, pitch, (uint32_t)f * fstride, acc[f]);
+        } else {
+            const BilinearColPrepU16 pp = bilinear_col_prep_u16c3(bias, pitch, round_bits(sx), round_bits(sy));
+#pragma unroll
+            for (int f = 0; f < NF; ++f) bilinear_col_taps_u16c3(pp, pitch, (uint32_t)f * fstride, acc[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const uint32_t a = out_bits16<TOut>(acc[f][0]) | (out_bits16<TOut>(acc[f][1]) << 16), b = out_bits16<TOut>(acc[f][2]);
+            const uint32_t a_other = __shfl_xor_sync(0xffffffffu, a, 1);
+            const uint32_t first = odd ? ((a >> 16) | (b << 16)) : a;          // word 2 | word 0
+            const uint32_t second = b | (a_other << 16);                        // word 1 (even lanes only)
+            unsigned char* o = out_a + f * dst_fstride;
+            asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(o), "r"(first));
+            asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %2, 0;\n@p st.global.cs.b32 [%0], %1;\n}"
+                         ::"l"(o + 4), "r"(second), "r"((uint32_t)odd));
+        }
+        out_a += dst_pitch;
+    }
+}
+
 template <int INTERP, typename TIn, typename TOut, int FR>
 __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks((int)sizeof(TIn), INTERP)) remap_tiled_kernel(const __grid_constant__ TiledParams P,
                                                                     const __grid_constant__ TensorMaps maps) {
@@ -567,7 +643,7 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks((int)sizeof(TI
     const int tid = threadIdx.x;
     const int n_tiles = P.tiles_x * P.tiles_y;
     const int n_fblocks = (P.n_groups + FR - 1) / FR;
-    const int total = n_fblocks * P.n_views * n_tiles;              // the host keeps this below 2^31
+    const int total = n_fblocks * P.n_order;                        // the host keeps this below 2^31
 
     if (tid == 0) {
         for (int q = 0; q < kSlots; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], kConsumerWarps); }
@@ -595,40 +671,43 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks((int)sizeof(TI
         const int lane = tid - n_teams * kTeamThreads;
         PatchRing ringst;                // identical in every lane
         int oldest = 0, k = 0;
-        const uint64_t policy = l2_policy_evict_last();
+        const uint64_t policy = l2_policy_by_kind(P.l2_policy);
 #if R360_TILED_STATS
         const long long st_t0 = clock64();
         long long st_wait = 0, st_slots = 0, st_multi = 0;
 #endif
-        // (tile, view, frame block) of the current item, advanced incrementally (no divisions in the loop)
+        // Items are walked in the plan's source-row order (all views interleaved): the blocks of the grid then read
+        // from one band of source rows at a time, so a frame's bytes come out of DRAM once and every view that
+        // overlaps the band finds them in L2.  Item = (entry of the order list, frame block); the (view, tile) pair
+        // is prefetched two items ahead, the tile's geometry one item ahead.
         int item = blockIdx.x;
-        int tile = item % n_tiles, unit = item / n_tiles;
-        int v = unit % P.n_views, gb = unit / P.n_views;
-        int ti = tile % P.tiles_x, tj = tile / P.tiles_x;
-        const int step_tile = gridDim.x % n_tiles, step_unit = gridDim.x / n_tiles;
-        const int step_ti = step_tile % P.tiles_x, step_tj = step_tile / P.tiles_x;
+        int idx = item % P.n_order, gb = item / P.n_order;
+        const int step_idx = gridDim.x % P.n_order, step_gb = gridDim.x / P.n_order;
+        int2 vt = make_int2(0, 0), vt_next = make_int2(0, 0);       // (view, tile) of this item / the next one
+        int idx_next = idx + step_idx, gb_next = gb + step_gb;
+        if (idx_next >= P.n_order) { idx_next -= P.n_order; ++gb_next; }
+        if (item < total) vt = __ldg(P.order + idx);
+        if (item + (int)gridDim.x < total) vt_next = __ldg(P.order + idx_next);
         // geometry of the item about to be processed: lanes 0 and 1 hold the record's last two
-        // 16-byte pieces (py0 rows xb0 row_bytes | pitch mode_slot - -), prefetched one item ahead
+        // 16-byte pieces (py0 rows xb0 row_bytes | pitch mode_slot - -)
         int4 geo = make_int4(0, 0, 0, 0);
-        const TilePlan* gp = P.plans + (long long)v * n_tiles + tile;
+        const TilePlan* gp = P.plans + (long long)vt.x * n_tiles + vt.y;
         if (item < total && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
         for (; item < total; item += gridDim.x) {
             const int py0 = __shfl_sync(0xffffffffu, geo.x, 0), rows_needed = __shfl_sync(0xffffffffu, geo.y, 0);
             const int xb0 = __shfl_sync(0xffffffffu, geo.z, 0), row_bytes = __shfl_sync(0xffffffffu, geo.w, 0);
             const int pitch = __shfl_sync(0xffffffffu, geo.x, 1), mode_slot = __shfl_sync(0xffffffffu, geo.y, 1);
             const TilePlan* gp_cur = gp;
-            const int cur_gb = gb, cur_v = v, cur_ti = ti, cur_tj = tj;
-            // advance to the next item and start fetching its geometry
+            const int cur_gb = gb, cur_v = vt.x;
+            const int cur_tj = vt.y / P.tiles_x, cur_ti = vt.y - cur_tj * P.tiles_x;
+            // advance: the next item's geometry and the (view, tile) pair of the one after it
             {
-                int du = step_unit;
-                ti += step_ti; tj += step_tj;
-                if (ti >= P.tiles_x) { ti -= P.tiles_x; ++tj; }
-                tile += step_tile;
-                if (tile >= n_tiles) { tile -= n_tiles; tj -= P.tiles_y; ++du; }
-                v += du;
-                while (v >= P.n_views) { v -= P.n_views; ++gb; }
+                vt = vt_next; gb = gb_next;
+                idx_next += step_idx; gb_next += step_gb;
+                if (idx_next >= P.n_order) { idx_next -= P.n_order; ++gb_next; }
+                if (item + 2 * (int)gridDim.x < total) vt_next = __ldg(P.order + idx_next);
             }
-            gp = P.plans + (long long)v * n_tiles + tile;
+            gp = P.plans + (long long)vt.x * n_tiles + vt.y;
             if (item + (int)gridDim.x < total && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
 
             const int mode = mode_slot & 0xff, src_slot = (mode_slot >> 8) & 0xff, wbox = mode_slot >> 16;
@@ -824,6 +903,22 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks((int)sizeof(TI
                 else
                     column_rows_u8c3<INTERP, 1>(plan, rowc + warp * 48, si->bias, (uint32_t)si->pitch, col_tab, fstride, col_s,
                                                 col_dlane, col_drow, out_word, P.dst.pitch, P.dst_fstride, m);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(empty_s + slot * 8);
+                continue;
+            }
+        }
+        if constexpr (kFastU16) {
+            // lane-per-column tiles of 16-bit RGB sources (4-byte aligned destination rows)
+            if (mode != kModeFill && mode != kModeFastSeam && P.channels == 3 && si->full_tile && (P.dst.pitch & 3) == 0 &&
+                (P.dst.image_stride & 3) == 0) {
+                unsigned char* out_row = P.dst.data + si->dst_tile + (long long)(warp * 4) * P.dst.pitch;
+                if (FR > 1 && nf == FR)
+                    column_rows_u16c3<INTERP, TOut, FR>(plan, rowc + warp * 48, si->bias, (uint32_t)si->pitch, fstride, col_s, col_dlane,
+                                                        col_drow, out_row, P.dst.pitch, P.dst_fstride, lane);
+                else
+                    column_rows_u16c3<INTERP, TOut, 1>(plan, rowc + warp * 48, si->bias, (uint32_t)si->pitch, fstride, col_s, col_dlane,
+                                                       col_drow, out_row, P.dst.pitch, P.dst_fstride, lane);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_s(empty_s + slot * 8);
                 continue;

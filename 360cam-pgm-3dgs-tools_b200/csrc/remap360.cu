@@ -391,7 +391,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kMaxRingBytes = 200 * 1024;       // shared-memory ring of one block
 
-struct WorkspaceLayout { size_t header, views, plans, fallback, total; };
+struct WorkspaceLayout { size_t header, views, plans, fallback, order, total; };
 
 WorkspaceLayout workspace_layout(int n_views, int out_w, int out_h) {
     const size_t tiles = (size_t)((out_w + kTile - 1) / kTile) * ((out_h + kTile - 1) / kTile);
@@ -400,7 +400,8 @@ WorkspaceLayout workspace_layout(int n_views, int out_w, int out_h) {
     w.views = align_up(sizeof(PlanHeader), 256);
     w.plans = w.views + align_up(sizeof(ViewDev) * n_views, 256);
     w.fallback = w.plans + align_up(sizeof(TilePlan) * n_views * tiles, 256);
-    w.total = w.fallback + align_up(sizeof(int2) * n_views * tiles, 256);
+    w.order = w.fallback + align_up(sizeof(int2) * n_views * tiles, 256);      // also scratch for the sort keys
+    w.total = w.order + align_up(sizeof(int2) * n_views * tiles, 256);
     return w;
 }
 
@@ -415,7 +416,8 @@ struct r360_plan {
     int frames_pref, ctas_multi_pref;     // launch shape for batches (choose_shape)
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
-    PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback;
+    PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback; int2* d_order;
+    int n_order;                                    // staged / fill tiles, in the order the remap kernel walks them
     // tensor-TMA descriptors depend on the source base pointer and batch size: small cache
     bool tensor_ok;
     int box_family;
@@ -452,12 +454,19 @@ int encode_tensor_maps(const r360_images& src, int family, TensorMaps* out) {
     const cuuint64_t strides[2] = {(cuuint64_t)src.pitch_bytes,
                                    (cuuint64_t)(src.count > 1 ? src.image_stride_bytes : src.pitch_bytes * src.height)};
     const cuuint32_t estr[3] = {1, 1, 1};
+    // L2 fetch granularity of the boxes (R360_L2_PROMO = 0 / 64 / 128 / 256 for experiments)
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char* env = std::getenv("R360_L2_PROMO")) {
+        const int v = std::atoi(env);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }
     for (int wk = 0; wk < kNumBoxWidths; ++wk)
         for (int hk = 0; hk < kNumBoxHeights; ++hk) {
             const cuuint32_t box[3] = {(cuuint32_t)box_width_bytes(wk, family) / 4, (cuuint32_t)box_height_rows(hk), 1};
             const CUresult r = enc(&out->m[wk * kNumBoxHeights + hk], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.data, dims,
                                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                   promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
                 std::snprintf(tl_cuda_error, sizeof(tl_cuda_error), "cuTensorMapEncodeTiled failed (%d) for box %dx%d",
                               (int)r, box_width_bytes(wk, family), box_height_rows(hk));
@@ -544,6 +553,7 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     pl->d_views = reinterpret_cast<ViewDev*>(pl->ws + wl.views);
     pl->d_plans = reinterpret_cast<TilePlan*>(pl->ws + wl.plans);
     pl->d_fallback = reinterpret_cast<int2*>(pl->ws + wl.fallback);
+    pl->d_order = reinterpret_cast<int2*>(pl->ws + wl.order);
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     auto fail = [&](cudaError_t e, const char* what) { delete pl; return cuda_fail(e, what); };
@@ -576,6 +586,28 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     if ((e = cudaMemcpyAsync(&h, pl->d_header, sizeof(h), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "cudaMemcpyAsync(header)");
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
     pl->n_fallback = h.n_fallback;
+    // ---- walk order of the remap kernel: (view, tile) sorted by source slot and source row ------------------
+    {
+        const int n = n_views * pl->n_tiles;
+        int* d_keys = reinterpret_cast<int*>(pl->d_order);            // the order region doubles as key scratch
+        order_key_kernel<<<(n + 255) / 256, 256, 0, s>>>(pl->d_plans, n, d_keys);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "order_key_kernel launch");
+        std::vector<int> keys(n);
+        if ((e = cudaMemcpyAsync(keys.data(), d_keys, sizeof(int) * n, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "cudaMemcpyAsync(keys)");
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
+        std::vector<int> idx(n);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+        std::vector<int2> order;
+        order.reserve(n);
+        for (int i = 0; i < n && keys[idx[i]] != INT_MAX; ++i) order.push_back(make_int2(idx[i] / pl->n_tiles, idx[i] % pl->n_tiles));
+        pl->n_order = (int)order.size();
+        if (pl->n_order > 0 &&
+            (e = cudaMemcpyAsync(pl->d_order, order.data(), sizeof(int2) * order.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            return fail(e, "cudaMemcpyAsync(order)");
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
+    }
     *plan_out = pl;
     return R360_OK;
 }
@@ -597,8 +629,9 @@ bool shape_for(const r360_plan* pl, int fr, int teams, int ctas, int smem_per_sm
     if (ring > kMaxRingBytes) ring = kMaxRingBytes;
     if (ring < pl->patch_budget) return false;
     out->fr = fr; out->teams = teams; out->ctas = ctas; out->ring = ring; out->smem = fixed + ring;
-    // an item takes all its frames at once when two such items fit the ring (one being sampled, one in flight)
-    const int pct = std::min(100, std::max(10, env_int("R360_MULTI_PCT", 50)));
+    // an item takes all its frames at once when it leaves room for the next one to load behind it (measured on B200,
+    // 8K -> 12 x 1600^2, two frames per item: 50 % of the ring 140.9 / 279.0 Gpix/s bicubic / bilinear, 75 % 143.1 / 280.1)
+    const int pct = std::min(100, std::max(10, env_int("R360_MULTI_PCT", 75)));
     out->multi_budget = (int)((long long)ring * pct / 100);
     return true;
 }
@@ -668,12 +701,14 @@ struct TiledLauncher {
         T.frames_per_item = shape.fr; T.multi_budget = shape.multi_budget;
         T.dst_fstride = (long long)pl->pr.n_views * T.dst.image_stride;
         T.plans = pl->d_plans;
+        T.order = pl->d_order; T.n_order = pl->n_order;
+        T.l2_policy = env_int("R360_L2_POLICY", 0);
 
         // work items are indexed with 32-bit ints inside the kernel: chunk the groups if needed
-        const long long per_group = (long long)pl->pr.n_views * pl->n_tiles;
+        const long long per_group = std::max(1, pl->n_order);
         int max_groups = (int)std::max<long long>(1, (1LL << 30) / per_group);
         if (max_groups > shape.fr) max_groups -= max_groups % shape.fr;          // chunks hold whole frame blocks
-        for (int g0 = 0; g0 < n_groups; g0 += max_groups) {
+        for (int g0 = 0; g0 < n_groups && pl->n_order > 0; g0 += max_groups) {
             TiledParams Q = T;
             Q.n_groups = n_groups - g0 < max_groups ? n_groups - g0 : max_groups;
             Q.src.data += (long long)g0 * pl->pr.n_lenses * Q.src.image_stride;

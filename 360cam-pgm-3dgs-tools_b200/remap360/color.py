@@ -194,3 +194,56 @@ def convert_video_color(images: torch.Tensor, *, keep_rec709: bool = False, filt
                                                   1 if channel_order == "rgb" else 0,
                                                   _stream_handle(stream, images.device)))
     return out
+
+
+# ---- decoder matrix --------------------------------------------------------------------------------------
+# Video decoders hand over R'G'B' computed from Y'CbCr with ONE matrix; OpenCV's FFmpeg reader (swscale without
+# colourspace details) and JPEG decoders (JFIF) use BT.601, whereas the cutter's filter chain declares its input
+# BT.709 (`iall=bt709`, PC:299-309) and ffmpeg's colorspace filter then reads the same Y'CbCr samples with the
+# BT.709 matrix.  R'G'B'(709) = M709 . M601^-1 . R'G'B'(601): a 3 x 3 matrix on the ENCODED values, independent of
+# the range convention because offsets and scales are common to both conversions.
+
+_LUMA = {"bt601": (0.299, 0.114), "bt709": (0.2126, 0.0722)}       # (Kr, Kb)
+
+
+def ycbcr_to_rgb_matrix(standard: str):
+    """Normalised Y'CbCr (Y in [0, 1], Cb / Cr in [-0.5, 0.5]) -> R'G'B' for BT.601 / BT.709 luma coefficients."""
+    import numpy as np
+    kr, kb = _LUMA[standard]
+    kg = 1.0 - kr - kb
+    return np.array([[1.0, 0.0, 2.0 * (1.0 - kr)],
+                     [1.0, -2.0 * kb * (1.0 - kb) / kg, -2.0 * kr * (1.0 - kr) / kg],
+                     [1.0, 2.0 * (1.0 - kb), 0.0]], dtype=np.float64)
+
+
+def decoder_matrix_correction(decoded_with: str = "bt601", declared: str = "bt709"):
+    """R'G'B' as decoded -> R'G'B' the declared matrix gives for the same Y'CbCr samples (float64 3 x 3, RGB order)."""
+    import numpy as np
+    if decoded_with == declared:
+        return np.eye(3)
+    return ycbcr_to_rgb_matrix(declared) @ np.linalg.inv(ycbcr_to_rgb_matrix(decoded_with))
+
+
+def correct_decoder_matrix(images: torch.Tensor, *, decoded_with: str = "bt601", declared: str = "bt709",
+                           channel_order: str = "bgr", out: Optional[torch.Tensor] = None,
+                           stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """Apply ``decoder_matrix_correction`` to [.., H, W, C] CUDA frames (``out`` may alias ``images``): the
+    r360_convert_color kernel with both transfer curves set to linear, i.e. the matrix on the encoded values, clipped
+    to the code range."""
+    if channel_order not in ("bgr", "rgb"):
+        raise ValueError("channel_order must be 'bgr' or 'rgb'")
+    if not images.is_contiguous():
+        raise ValueError("images must be contiguous")
+    flat = images.reshape((-1,) + tuple(images.shape[-3:]))
+    if out is None:
+        out = torch.empty_like(images)
+    elif out.shape != images.shape or out.dtype != images.dtype or not out.is_contiguous():
+        raise ValueError("out must match images")
+    src, dst = _describe(flat, "images"), _describe(out.reshape(flat.shape), "out")
+    m = decoder_matrix_correction(decoded_with, declared)
+    desc = _lib.ColorConvert(_lib.TRC["linear"], _lib.TRC["linear"], (ctypes.c_float * 9)(*[float(v) for v in m.reshape(-1)]), 0)
+    with torch.cuda.device(images.device):
+        _lib.check(_lib.load().r360_convert_color(ctypes.byref(src), ctypes.byref(dst), ctypes.byref(desc),
+                                                  1 if channel_order == "rgb" else 0,
+                                                  _stream_handle(stream, images.device)))
+    return out

@@ -78,9 +78,35 @@ def parse_job_argv(argv: Sequence[str]) -> ParsedJob:
 
 _INTERP = {"cubic": "cubic", "linear": "linear", "nearest": "nearest", "near": "nearest",
            "lanczos": "lanczos4"}          # v360 `lanczos` -> the cv2-compatible 8x8 Lanczos kernel
-_gpu_slots = threading.BoundedSemaphore(4)      # source groups resident on the device at once (memory bound)
+_gpu_slots = threading.BoundedSemaphore(max(4, min(32, os.cpu_count() or 4)))   # source groups resident on the device at once (an 8K group is ~0.2 GB of 180)
 _pool_lock = threading.Lock()
-_idle_workers: list = []          # (stream, codec or None) pairs, reused across run_jobs calls
+_idle_workers: dict = {}          # device index -> [(stream, codec or None)], reused across run_jobs calls
+
+
+# Wall-clock seconds per stage of the still-image runner, summed over host threads (R360_TIMING=1; read by
+# tools/pipeline_probe.py to see what a file-to-file run waits for).
+STAGE_SECONDS: Dict[str, float] = {}
+_stage_lock = threading.Lock()
+
+
+class _stage:
+    def __init__(self, name: str, stream=None):
+        self.name, self.stream, self.on = name, stream, bool(os.environ.get("R360_TIMING"))
+
+    def __enter__(self):
+        if self.on:
+            import time
+            self.t0 = time.perf_counter()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            import time
+            if self.stream is not None:
+                self.stream.synchronize()
+            with _stage_lock:
+                STAGE_SECONDS[self.name] = STAGE_SECONDS.get(self.name, 0.0) + time.perf_counter() - self.t0
+        return False
 
 
 class _DeviceWorker:
@@ -89,8 +115,10 @@ class _DeviceWorker:
 
     def __enter__(self):
         import torch
+        self._dev = torch.cuda.current_device()
         with _pool_lock:
-            item = _idle_workers.pop() if _idle_workers else None
+            idle = _idle_workers.setdefault(self._dev, [])
+            item = idle.pop() if idle else None
         if item is None:
             item = (torch.cuda.Stream(), _gpu_codec())
         self._item = item
@@ -100,8 +128,18 @@ class _DeviceWorker:
 
     def __exit__(self, *exc):
         with _pool_lock:
-            _idle_workers.append(self._item)
+            _idle_workers.setdefault(self._dev, []).append(self._item)
         return False
+
+
+def job_convention() -> str:
+    """Pixel convention of the ERP jobs.  The default, "halfpixel", is the geometry the reference states in its own
+    code (pixel centres, gs360_GUI.py:419-424) and what every parity test pins; R360_JOB_CONVENTION=v360 switches
+    the job runners to FFmpeg's `(W - 1)` scaling (up to half a pixel of difference across the
+    panorama) for outputs that must line up with views an ffmpeg run produced earlier.  Note also that v360's
+    `lanczos` is a 4 x 4 kernel where the CUDA backend (like cv2) uses 8 x 8 taps."""
+    conv = os.environ.get("R360_JOB_CONVENTION", "halfpixel").lower()
+    return conv if conv in ("halfpixel", "v360") else "halfpixel"
 
 
 def _job_view(job: "ParsedJob"):
@@ -124,11 +162,32 @@ def widen_for_pix_fmt(image, pix_fmt: Optional[str]):
     return image
 
 
+def narrow_to_8bit(image):
+    """16-bit samples -> 8 bits for a JPEG view, full range to full range with rounding: round(v * 255 / 65535)
+    = (v * 255 + 32767) // 65535 -- what swscale's rgb48 -> 8-bit conversion amounts to (the reference's
+    `-pix_fmt yuvj444p` after a 16-bit still, PC:317-339).  cv2.imwrite would SATURATE instead (every sample
+    >= 255 becomes 255).  Accepts a NumPy array or a CUDA / CPU tensor; 8-bit input is returned as it is."""
+    import numpy as np
+    try:
+        import torch
+        if isinstance(image, torch.Tensor):
+            if image.dtype != torch.uint16:
+                return image
+            return ((image.to(torch.int32) * 255 + 32767) // 65535).to(torch.uint8)
+    except ImportError:
+        pass
+    if image.dtype != np.uint16:
+        return image
+    return ((image.astype(np.uint32) * 255 + 32767) // 65535).astype(np.uint8)
+
+
 def _write_image(path: pathlib.Path, image, jpeg_quality: int, pix_fmt: Optional[str] = None) -> None:
     import cv2
     path.parent.mkdir(parents=True, exist_ok=True)
     if path.suffix.lower() in (".png", ".tif", ".tiff"):
         image = widen_for_pix_fmt(image, pix_fmt)
+    if path.suffix.lower() in (".jpg", ".jpeg"):
+        image = narrow_to_8bit(image)
     params: List[int] = []
     if path.suffix.lower() in (".jpg", ".jpeg"):
         params = [int(cv2.IMWRITE_JPEG_QUALITY), int(jpeg_quality)]
@@ -176,13 +235,16 @@ def _run_still_group_on(worker, source: pathlib.Path, jobs: List[ParsedJob], sto
     image = dev_image = None
     if jc is not None and _is_jpeg(source):
         try:
-            with torch.cuda.stream(stream):
-                dev_image = jc.decode(source.read_bytes(), stream=stream)   # [H, W, C] uint8, BGR like cv2
+            with _stage("read"):
+                data = source.read_bytes()
+            with _stage("decode", stream), torch.cuda.stream(stream):
+                dev_image = jc.decode(data, stream=stream)   # [H, W, C] uint8, BGR like cv2
             image = np.empty(tuple(dev_image.shape), dtype=np.uint8)   # shape / dtype carrier only
         except Exception:
             dev_image = None                                         # e.g. progressive JPEG: OpenCV reads it
     if dev_image is None:
-        image = cv2.imread(str(source), cv2.IMREAD_UNCHANGED)
+        with _stage("decode"):
+            image = cv2.imread(str(source), cv2.IMREAD_UNCHANGED)
     if image is None:
         return [(1, "failed to read %s" % source)] * len(jobs)
     if image.ndim == 2:
@@ -214,27 +276,33 @@ def _run_still_group_on(worker, source: pathlib.Path, jobs: List[ParsedJob], sto
                     dev = torch.from_numpy(host.view(np.int16)).cuda().view(torch.uint16)
                 else:
                     dev = torch.from_numpy(host).cuda()
-                out = api.remap_erp(dev[None], views, (w, h), interp=interp, stream=stream)[0]
+                with _stage("remap", stream):
+                    out = api.remap_erp(dev[None], views, (w, h), interp=interp, convention=job_convention(), stream=stream)[0]
                 encoded = {}
-                if jc is not None and out.dtype == torch.uint8 and out.shape[-1] in (1, 3):
-                    for n, k in enumerate(idxs):
-                        if _is_jpeg(jobs[k].output):
-                            encoded[n] = jc.encode(out[n], jobs[k].jpeg_quality, stream=stream)
+                if jc is not None and out.dtype in (torch.uint8, torch.uint16) and out.shape[-1] in (1, 3):
+                    with _stage("encode", stream):
+                        for n, k in enumerate(idxs):
+                            if _is_jpeg(jobs[k].output):
+                                # 16-bit views are scaled to 8 bits on the device first (narrow_to_8bit)
+                                encoded[n] = jc.encode(narrow_to_8bit(out[n]).contiguous() if out.dtype == torch.uint16 else out[n],
+                                                       jobs[k].jpeg_quality, stream=stream)
                 out_host = None
                 if len(encoded) < len(idxs):
-                    if out.dtype == torch.uint16:
-                        out_host = out.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
-                    else:
-                        out_host = out.contiguous().cpu().numpy()
+                    with _stage("download", stream):
+                        if out.dtype == torch.uint16:
+                            out_host = out.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+                        else:
+                            out_host = out.contiguous().cpu().numpy()
                 stream.synchronize()
-            for n, k in enumerate(idxs):
-                if n in encoded:
-                    jobs[k].output.parent.mkdir(parents=True, exist_ok=True)
-                    jobs[k].output.write_bytes(encoded[n])
-                else:
-                    img = out_host[n]
-                    _write_image(jobs[k].output, img[..., 0] if img.shape[2] == 1 else img, jobs[k].jpeg_quality)
-                results[k] = (0, "")
+            with _stage("write"):
+                for n, k in enumerate(idxs):
+                    if n in encoded:
+                        jobs[k].output.parent.mkdir(parents=True, exist_ok=True)
+                        jobs[k].output.write_bytes(encoded[n])
+                    else:
+                        img = out_host[n]
+                        _write_image(jobs[k].output, img[..., 0] if img.shape[2] == 1 else img, jobs[k].jpeg_quality)
+                    results[k] = (0, "")
         except Exception as exc:  # report per job, like a failing ffmpeg process would
             text = "%s: %s" % (type(exc).__name__, exc)
             for k in idxs:

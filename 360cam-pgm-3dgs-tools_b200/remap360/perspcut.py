@@ -162,17 +162,38 @@ def extra_suffix(delta_pitch: float, default_deg: float = 30.0) -> str:
     return "%s%g" % (head, mag)
 
 
+def bit_depth_from_pixel_format_tag(tag: int) -> int:
+    """Nominal bit depth from the codec pixel-format tag OpenCV reports (CAP_PROP_CODEC_PIXEL_FORMAT =
+    avcodec_pix_fmt_to_codec_tag): libavcodec's raw tags spell high-bit-depth planar YUV as 'Y' '3' <chroma> <bits>
+    (yuv420p10le = Y3 0x0b 0x0a), semi-planar ones as P010 / P012 / P016 / P210 / P216 / P410 / P416, packed ones as
+    v210 / Y210 / Y410 / Y216 / Y416, 16-bit RGB as 'b48r' / '0RGB'-style 48 / 64 tags.  Anything above 8 bits counts
+    as 10, like the reference (gs360_360PerspCut.py:133-146); unknown tags are 8."""
+    raw = int(tag) & 0xFFFFFFFF
+    b = raw.to_bytes(4, "little")
+    if b[:2] == b"Y3" and b[3] in (9, 10, 12, 14, 16):
+        return 10
+    if b[::-1][:2] == b"Y3" and b[0] in (9, 10, 12, 14, 16):       # big-endian variants are stored reversed
+        return 10
+    text = b.decode("latin-1")
+    if text in ("P010", "P012", "P016", "P210", "P212", "P216", "P410", "P412", "P416", "v210", "Y210", "Y212", "Y216",
+                "Y410", "Y412", "Y416", "b48r", "b64a", "RBA@", "BRA@"):
+        return 10
+    if b[:2] == b"G3" and b[3] in (9, 10, 12, 14, 16):             # planar GBR
+        return 10
+    return 8
+
+
 def detect_input_bit_depth(in_path: pathlib.Path) -> int:
-    """Nominal bit depth of a video (reference: ffprobe, gs360_360PerspCut.py:111-149).  Here the
-    container is opened with OpenCV; anything it reports above 8 bits counts as 10."""
+    """Nominal bit depth of a video (reference: ffprobe's bits_per_raw_sample / pix_fmt, gs360_360PerspCut.py:111-149).
+    There is no ffprobe here; the container is opened with OpenCV and the STREAM's pixel format is read from its
+    metadata (the decoded frames are always 8-bit BGR and say nothing)."""
     try:
         import cv2
         cap = cv2.VideoCapture(str(in_path))
         if cap.isOpened():
-            ok, frame = cap.read()
+            tag = int(cap.get(cv2.CAP_PROP_CODEC_PIXEL_FORMAT))
             cap.release()
-            if ok and frame is not None and frame.dtype.itemsize > 1:
-                return 10
+            return bit_depth_from_pixel_format_tag(tag)
     except Exception:
         pass
     return 8
@@ -670,12 +691,13 @@ def main(argv: Optional[Sequence[str]] = None) -> None:
             if line:
                 print(line)
 
-    from . import executor
+    from . import multigpu
     ok = fail = done = 0
     last_pct = -1
     # Jobs of one source share one decode and one upload: the executor groups them, but results
-    # are still reported per job like the reference's one-process-per-job pool.
-    for (cmd, src, dst), (rc, err) in executor.run_jobs(result.jobs, stop_event, workers):
+    # are still reported per job like the reference's one-process-per-job pool.  With several GPUs visible the
+    # sources (and a video's frame ranges) are dealt out to one worker process per device (remap360/multigpu.py).
+    for (cmd, src, dst), (rc, err) in multigpu.run_jobs(result.jobs, stop_event, workers):
         done += 1
         if rc == 0:
             ok += 1

@@ -1,10 +1,12 @@
 """Frame streaming: decoded frames in pinned host memory -> H2D -> remap kernel -> D2H -> pinned
-host views, on three CUDA streams with a small ring of device buffers, so that the copies of
-frame n+1 / n-1 overlap the kernel of frame n.
+host views, on three CUDA streams with a ring of device buffers, so that the copies of the
+batches before and after overlap the kernel of the current one.
 
 The reference pays one full decode per (source, view) and moves nothing to a device
 (cli_tools/gs360_360PerspCut.py:569-590, one ffmpeg process per job); here a frame is uploaded
-once and all of its views are cut from the copy in HBM."""
+once and all of its views are cut from the copy in HBM.  Frames travel in small batches (default 2):
+consecutive frames of a video share their map, and the tiled kernel samples the frames of a batch with
+one set of coordinates and weights (r360_tiled.cuh)."""
 
 from __future__ import annotations
 
@@ -17,15 +19,16 @@ from .api import PerspectiveView, alloc_views, remap_erp
 
 
 class _Slot:
-    def __init__(self, frame_shape, dtype, n_views, size, out_dtype, device):
+    def __init__(self, batch, frame_shape, dtype, n_views, size, out_dtype, device):
         h, w, c = frame_shape
-        self.host_in = torch.empty((h, w, c), dtype=dtype).pin_memory()
-        self.dev_in = torch.empty((1, h, w, c), dtype=dtype, device=device)
-        self.dev_out = alloc_views(1, n_views, size[1], size[0], c, out_dtype, device)
-        self.host_out = torch.empty((n_views, size[1], size[0], c), dtype=out_dtype).pin_memory()
+        self.host_in = torch.empty((batch, h, w, c), dtype=dtype).pin_memory()
+        self.dev_in = torch.empty((batch, h, w, c), dtype=dtype, device=device)
+        self.dev_out = alloc_views(batch, n_views, size[1], size[0], c, out_dtype, device)
+        self.host_out = torch.empty((batch, n_views, size[1], size[0], c), dtype=out_dtype).pin_memory()
         self.ev_h2d = torch.cuda.Event()
         self.ev_kernel = torch.cuda.Event()
         self.ev_d2h = torch.cuda.Event()
+        self.n = 0                                   # frames in the slot
 
 
 class StreamingRemapper:
@@ -34,27 +37,29 @@ class StreamingRemapper:
         remapper = StreamingRemapper(views, (1600, 1600), (3840, 7680, 3), torch.uint8)
         for views_host in remapper.run(frames):      # frames: iterable of CPU tensors [H, W, C]
             ...                                       # [V, h, w, C] pinned; valid until the next item
+    Frames may also be CUDA tensors that are complete on their producer's stream (frames decoded on the device).
 
-    ``depth`` frames are in flight at once (default 3: one uploading, one in the kernel, one
-    downloading)."""
+    ``depth`` batches of ``batch`` frames are in flight at once (default 4 x 2: one filling / uploading, one in
+    the kernel, one downloading, one being read by the caller)."""
 
     def __init__(self, views: Sequence[PerspectiveView], size: Tuple[int, int], frame_shape: Tuple[int, int, int],
                  dtype: torch.dtype = torch.uint8, *, interp: str = "cubic", convention: str = "halfpixel",
-                 out_dtype: Optional[torch.dtype] = None, device=None, depth: int = 3, path: str = "auto",
+                 out_dtype: Optional[torch.dtype] = None, device=None, depth: int = 4, batch: int = 2, path: str = "auto",
                  frame_filter: Optional[Callable[[torch.Tensor, torch.cuda.Stream], None]] = None):
-        if depth < 1:
-            raise ValueError("depth must be >= 1")
+        if depth < 1 or batch < 1:
+            raise ValueError("depth and batch must be >= 1")
         self.views = list(views)
         self.size = (int(size[0]), int(size[1]))
         self.interp, self.convention, self.path = interp, convention, path
         self.device = torch.device(device if device is not None else "cuda")
         self.out_dtype = out_dtype or dtype
-        # in-place per-frame step on the uploaded frame [1, H, W, C], run on the kernel stream before the
+        self.depth, self.batch = int(depth), int(batch)
+        # in-place per-frame step on the uploaded frames [n, H, W, C], run on the kernel stream before the
         # remap (the cutter's video colour step, PC:299-309)
         self.frame_filter = frame_filter
         with torch.cuda.device(self.device):
-            self._free: List[_Slot] = [_Slot(frame_shape, dtype, len(self.views), self.size, self.out_dtype, self.device)
-                                       for _ in range(depth)]
+            self._free: List[_Slot] = [_Slot(self.batch, frame_shape, dtype, len(self.views), self.size, self.out_dtype, self.device)
+                                       for _ in range(self.depth)]
             self.s_h2d = torch.cuda.Stream(self.device)
             self.s_kernel = torch.cuda.Stream(self.device)
             self.s_d2h = torch.cuda.Stream(self.device)
@@ -62,40 +67,62 @@ class StreamingRemapper:
         self.frames_done = 0
 
     # -- pipeline stages ---------------------------------------------------------------------------
-    def _push(self, frame: torch.Tensor) -> None:
-        slot = self._free.pop()
+    def _upload(self, slot: _Slot, frame: torch.Tensor) -> None:
+        """Frame -> slot.dev_in[slot.n], asynchronously on the upload stream."""
+        b = slot.n
         src = frame
-        if not (isinstance(frame, torch.Tensor) and frame.is_pinned()):
-            slot.host_in.copy_(torch.as_tensor(frame))       # pageable input: stage through the pinned buffer
-            src = slot.host_in
+        if isinstance(frame, torch.Tensor) and frame.is_cuda:
+            pass                                             # decoded on the device (nvJPEG): a device-to-device copy
+        elif not (isinstance(frame, torch.Tensor) and frame.is_pinned()):
+            slot.host_in[b].copy_(torch.as_tensor(frame))    # pageable input: stage through the pinned buffer
+            src = slot.host_in[b]
         with torch.cuda.stream(self.s_h2d):
-            slot.dev_in[0].copy_(src, non_blocking=True)
-            slot.ev_h2d.record(self.s_h2d)
+            slot.dev_in[b].copy_(src, non_blocking=True)
+            if src.is_cuda:
+                src.record_stream(self.s_h2d)
+        slot.n = b + 1
+
+    def _launch(self, slot: _Slot) -> None:
+        n = slot.n
+        slot.ev_h2d.record(self.s_h2d)
         self.s_kernel.wait_event(slot.ev_h2d)
         if self.frame_filter is not None:
-            self.frame_filter(slot.dev_in, self.s_kernel)
-        remap_erp(slot.dev_in, self.views, self.size, interp=self.interp, convention=self.convention,
-                  out=slot.dev_out, out_dtype=self.out_dtype, path=self.path, stream=self.s_kernel)
+            self.frame_filter(slot.dev_in[:n], self.s_kernel)
+        remap_erp(slot.dev_in[:n], self.views, self.size, interp=self.interp, convention=self.convention,
+                  out=slot.dev_out[:n], out_dtype=self.out_dtype, path=self.path, stream=self.s_kernel)
         slot.ev_kernel.record(self.s_kernel)
         self.s_d2h.wait_event(slot.ev_kernel)
         with torch.cuda.stream(self.s_d2h):
-            slot.host_out.copy_(slot.dev_out[0], non_blocking=True)
+            slot.host_out[:n].copy_(slot.dev_out[:n], non_blocking=True)
             slot.ev_d2h.record(self.s_d2h)
         self._inflight.append(slot)
 
-    def _pop(self) -> torch.Tensor:
+    def _drain_one(self) -> Iterator[torch.Tensor]:
         slot = self._inflight.popleft()
         slot.ev_d2h.synchronize()
-        self._free.append(slot)
-        self.frames_done += 1
-        return slot.host_out
+        for b in range(slot.n):
+            self.frames_done += 1
+            yield slot.host_out[b]
+        slot.n = 0
+        self._free.append(slot)          # only after the caller has moved past the slot's last result
 
     def run(self, frames: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
         """Generator over results, in order.  A yielded tensor is a view of a pinned ring buffer: it
         stays valid until the generator is advanced again."""
+        cur: Optional[_Slot] = None
         for frame in frames:
-            if not self._free:
-                yield self._pop()
-            self._push(frame)
+            if cur is None:
+                while not self._free:
+                    yield from self._drain_one()
+                cur = self._free.pop()
+                cur.n = 0
+            self._upload(cur, frame)
+            if cur.n == self.batch:
+                self._launch(cur)
+                cur = None
+        if cur is not None and cur.n:
+            self._launch(cur)
+        elif cur is not None:
+            self._free.append(cur)
         while self._inflight:
-            yield self._pop()
+            yield from self._drain_one()

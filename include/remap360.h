@@ -276,8 +276,8 @@ int r360_coords_undistort(const r360_fisheye_calib* calib, int32_t n_lenses,
  * The reference builds its remap tables once per view set and applies them to every frame
  * (gs360_DualFisheyeDistortionCalibration.py:1857-1907 build, :1996-2014 apply; ffmpeg's v360
  * does the same inside each process).  A plan is this library's equivalent: per 32x32 output
- * tile, polynomial coordinates fitted in float64 plus the source patch to stage -- 376 bytes per
- * tile (368-byte record + list entry) in a caller-provided device workspace, built on the device by r360_plan_create_*.
+ * tile, polynomial coordinates fitted in float64 plus the source patch to stage -- 384 bytes per
+ * tile (368-byte record + fallback-list and walk-order entries) in a caller-provided device workspace, built on the device by r360_plan_create_*.
  * r360_remap_planned then runs the tiled fast kernels (bulk-async staging to shared memory),
  * falling back to the direct path tile by tile where the plan says so.  Results are the same as
  * r360_remap_erp / r360_remap_fisheye up to 1/32-px bin flips from ~1e-5 px coordinate noise.

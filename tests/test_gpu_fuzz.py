@@ -29,11 +29,23 @@ def _host(t):
     return t.view(torch.int16).cpu().numpy().view(np.uint16) if t.dtype == torch.uint16 else t.cpu().numpy()
 
 
-def _close_fraction(a, b):
+# Pixels within 1 LSB / pixels compared, pooled over every random configuration of a kind.  A single random view can
+# be a handful of pixels (1 x 1 outputs are drawn on purpose), so the per-case asserts below only catch gross
+# errors; BASELINE.json's bar -- >= 99.9 % of the pixels within 1 LSB -- is asserted on the pools by
+# test_pooled_pixels_meet_the_bar at the end of this module.
+POOL = {}
+
+
+def _close_fraction(a, b, pool=None):
     if a.dtype in (np.float16, np.float32):
         scale = np.maximum(np.abs(b.astype(np.float64)), 2.0 ** -14) * (2.0 ** -10 if a.dtype == np.float16 else 2.0 ** -22)
-        return float((np.abs(a.astype(np.float64) - b.astype(np.float64)) <= scale).mean())
-    return float((np.abs(a.astype(np.int64) - b.astype(np.int64)) <= 1).mean())
+        ok = np.abs(a.astype(np.float64) - b.astype(np.float64)) <= scale
+    else:
+        ok = np.abs(a.astype(np.int64) - b.astype(np.int64)) <= 1
+    if pool is not None and ok.size:
+        acc = POOL.setdefault(pool, [0, 0])
+        acc[0] += int(ok.sum()); acc[1] += int(ok.size)
+    return float(ok.mean()) if ok.size else 1.0
 
 
 @pytest.mark.parametrize("seed", range(N_ERP))
@@ -63,7 +75,7 @@ def test_random_erp_configurations(seed):
     tiled = _host(r360.remap_erp(dev, views, (ow, oh), interp=interp, convention=convention, path="tiled"))[0]
     assert direct.shape == (len(views), oh, ow, channels)
     # the two device paths: identical up to 1/32-px bin flips
-    assert _close_fraction(tiled, direct) >= 0.995, (seed, interp, dtype, W, H, ow, oh, views)
+    assert _close_fraction(tiled, direct, "erp tiled vs direct") >= 0.995, (seed, interp, dtype, W, H, ow, oh, views)
     for k, v in enumerate(views):
         mx, my = geo.erp_map64(W, H, ow, oh, v.yaw_deg, v.pitch_deg, v.hfov_deg, v.vfov_deg, convention, v.roll_deg,
                                v.projection)
@@ -74,7 +86,8 @@ def test_random_erp_configurations(seed):
         at_pole = (my <= y_lo + 1e-9) | (my >= y_hi - 1e-9)
         assert at_pole.sum() <= 1
         keep = ~at_pole
-        assert _close_fraction(direct[k][keep], want[keep]) >= 0.995, (seed, k, interp, dtype, W, H, ow, oh, v)
+        assert _close_fraction(direct[k][keep], want[keep], "erp direct vs oracle") >= 0.995, (seed, k, interp, dtype, W, H, ow, oh, v)
+        assert _close_fraction(tiled[k][keep], want[keep], "erp tiled vs oracle") >= 0.99, (seed, k, interp, dtype, W, H, ow, oh, v)
 
 
 @pytest.mark.parametrize("seed", range(N_FISHEYE))
@@ -99,13 +112,14 @@ def test_random_fisheye_configurations(seed):
                                   float(rng.uniform(20, 150)), src_slot=int(rng.integers(0, 2))) for _ in range(3)]
     outs = {p: _host(r360.remap_fisheye(_cuda(pair), [calib, calib], views, (ow, oh), interp=interp, border_value=bv,
                                          fill_invalid=fill, path=p))[0] for p in ("direct", "tiled")}
-    assert _close_fraction(outs["tiled"], outs["direct"]) >= 0.995
+    assert _close_fraction(outs["tiled"], outs["direct"], "fisheye tiled vs direct") >= 0.995
     for k, v in enumerate(views):
         mx, my, ok = geo.fisheye_map64(cal, v.yaw_deg, v.pitch_deg, v.hfov_deg, v.vfov_deg, ow, oh, fov)
         want = sampler.sample(pair[0, v.src_slot], mx, my, interp, "constant", bv)
         if fill:
             want = sampler.apply_invalid_fill(want, ok, bv)
-        assert _close_fraction(outs["direct"][k], want) >= 0.99, (seed, k, interp, dtype, v)
+        assert _close_fraction(outs["direct"][k], want, "fisheye direct vs oracle") >= 0.99, (seed, k, interp, dtype, v)
+        assert _close_fraction(outs["tiled"][k], want, "fisheye tiled vs oracle") >= 0.99, (seed, k, interp, dtype, v)
         # undistort with a random zoom through the same calibration
     item = [r360.UndistortItem(float(rng.uniform(0.7, 1.5)), int(rng.integers(0, 2)))]
     und = {p: _host(r360.undistort_fisheye(_cuda(pair), [calib, calib], item, interp=interp, border_value=bv,
@@ -114,4 +128,16 @@ def test_random_fisheye_configurations(seed):
     want = sampler.sample(pair[0, item[0].src_slot], mx, my, interp, "constant", bv)
     if fill:
         want = sampler.apply_invalid_fill(want, ok, bv)
-    assert _close_fraction(und["direct"], want) >= 0.99 and _close_fraction(und["tiled"], und["direct"]) >= 0.995
+    assert _close_fraction(und["direct"], want, "undistort direct vs oracle") >= 0.99
+    assert _close_fraction(und["tiled"], want, "undistort tiled vs oracle") >= 0.99
+    assert _close_fraction(und["tiled"], und["direct"], "undistort tiled vs direct") >= 0.995
+
+
+def test_pooled_pixels_meet_the_bar():
+    """BASELINE.json north_star: output pixels within 1 LSB on >= 99.9 % of the pixels -- over everything the random
+    sweeps above compared (runs last in this module; skipped when the sweeps were deselected)."""
+    if not POOL:
+        pytest.skip("no random configuration ran")
+    report = {k: (ok / n, n) for k, (ok, n) in POOL.items()}
+    for kind, (frac, n) in report.items():
+        assert frac >= 0.999, (kind, frac, n, report)

@@ -2,6 +2,7 @@
 dual-fisheye stage picks the reference's lenses and renders what the oracle renders, the streaming
 remapper returns frames in order.  Run with ``pytest -m gpu``."""
 
+import os
 import pathlib
 
 import numpy as np
@@ -145,13 +146,17 @@ def test_streaming_remapper_keeps_order_and_matches_batched_call(r360):
     assert all(torch.equal(again[k], ref[k]) for k in range(3))
 
 
-@pytest.mark.parametrize("ext,depth,keep", [("png", 8, False), ("png", 10, True), ("jpg", 8, False)])
-def test_video_source_is_decoded_once_colour_converted_and_cut(r360, tmp_path, monkeypatch, ext, depth, keep):
+@pytest.mark.parametrize("ext,depth,keep,decoder", [("png", 8, False, "opencv"), ("png", 10, True, "opencv"), ("jpg", 8, False, "opencv"),
+                                                    ("png", 8, False, "nvjpeg")])
+def test_video_source_is_decoded_once_colour_converted_and_cut(r360, tmp_path, monkeypatch, ext, depth, keep, decoder):
     """A video source (PC's video branch): frames picked with ffmpeg's fps= rule, the job's colorspace filter applied
     on the device before the remap, views written as <stem>_%07d_<id>.<ext> from 0; a >8-bit source asks for
     rgb48le (16-bit PNG holding the widened 8-bit result)."""
     cv2 = pytest.importorskip("cv2")
     from remap360 import color, executor, perspcut as pc, video
+    # "opencv": frames decoded on the host (bit-identical to the frames this test decodes itself); "nvjpeg": the
+    # Motion-JPEG packets decoded on the device (another IDCT: the source frames differ by a level or two)
+    monkeypatch.setenv("R360_VIDEO_DECODER", "opencv" if decoder == "opencv" else "auto")
     path = tmp_path / "clip.avi"
     wr = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"MJPG"), 12.0, (512, 256))
     if not wr.isOpened():
@@ -186,18 +191,74 @@ def test_video_source_is_decoded_once_colour_converted_and_cut(r360, tmp_path, m
             name = spec.output_name % n if "%" in spec.output_name else spec.output_name
             got = cv2.imread(str(tmp_path / "out" / name), cv2.IMREAD_UNCHANGED)
             assert got is not None, name
-            conv = color.convert_video_color(torch.from_numpy(decoded[src_idx]).cuda()[None], keep_rec709=keep,
-                                             channel_order="bgr")[0].cpu().numpy()
+            # the decoder's BT.601 R'G'B' re-matrixed to the BT.709 the filter declares, then the filter itself
+            fixed = color.correct_decoder_matrix(torch.from_numpy(decoded[src_idx]).cuda()[None], channel_order="bgr")
+            conv = color.convert_video_color(fixed, keep_rec709=keep, channel_order="bgr")[0].cpu().numpy()
             mx, my = geo.erp_map64(512, 256, 80, 80, spec.yaw_deg, spec.pitch_deg, spec.hfov_deg, spec.vfov_deg)
             want = sampler.sample(conv, mx, my, "cubic", "erp")
             if ext == "png" and depth > 8:
                 assert got.dtype == np.uint16 and np.array_equal(got % 257, np.zeros_like(got))
                 got = (got // 257).astype(np.uint8)
             assert got.dtype == np.uint8 and got.shape == want.shape
-            tol = 1 if ext == "png" else 12                      # JPEG views: codec error on top
+            tol = (1 if decoder == "opencv" else 6) if ext == "png" else 12      # JPEG views / another decoder: codec error on top
             assert (np.abs(got.astype(int) - want.astype(int)) <= tol).mean() >= 0.99, (name, ext)
     assert not (tmp_path / "out" / (res.view_specs[0].output_name % len(picked))).exists()
     # the colour step can be switched off: frames then stay in the decoder's BGR values
     monkeypatch.setenv("R360_VIDEO_COLOR", "0")
     done = list(executor.run_jobs(res.jobs[:1], pc.stop_event, workers=1))
     assert done[0][1][0] == 0
+
+
+def test_sixteen_bit_still_to_jpeg_view_is_scaled_not_saturated(r360, tmp_path):
+    """A 16-bit TIFF source cut into .jpg views (the default --ext): the views hold the scaled 8-bit picture, on the
+    nvJPEG path and on the OpenCV one (cv2.imwrite alone would saturate every sample >= 255 to 255)."""
+    cv2 = pytest.importorskip("cv2")
+    from remap360 import executor, perspcut as pc
+    src_dir = tmp_path / "in"
+    src_dir.mkdir()
+    yy, xx = np.mgrid[0:256, 0:512].astype(np.float64)
+    img = np.stack([20000 + 15000 * np.sin(xx / 512 * 6.2832 * (k + 1)) * np.cos(yy / 256 * 3.1416) for k in range(3)], axis=-1).astype(np.uint16)
+    assert cv2.imwrite(str(src_dir / "pano.tif"), img)
+    args = pc.create_arg_parser().parse_args(["-i", str(src_dir), "--preset", "2views", "--size", "96"])
+    args.size_explicit, args.hfov_explicit, args.focal_mm_explicit = True, False, False
+    args.input_is_video, args.video_bit_depth = False, 8
+    res = pc.build_view_jobs(args, [src_dir / "pano.tif"], tmp_path / "out")
+    for cpu_codec in ("", "1"):
+        if cpu_codec:
+            os.environ["R360_CPU_CODEC"] = "1"
+        try:
+            done = list(executor.run_jobs(res.jobs, pc.stop_event, workers=1))
+        finally:
+            os.environ.pop("R360_CPU_CODEC", None)
+        assert all(rc == 0 for _j, (rc, _e) in done), done
+        for spec in res.view_specs:
+            got = cv2.imread(str(tmp_path / "out" / spec.output_name), cv2.IMREAD_UNCHANGED)
+            mx, my = geo.erp_map64(512, 256, 96, 96, spec.yaw_deg, spec.pitch_deg, spec.hfov_deg, spec.vfov_deg)
+            want16 = sampler.sample(img, mx, my, "cubic", "erp")
+            want8 = executor.narrow_to_8bit(want16)
+            assert got.dtype == np.uint8 and (np.abs(got.astype(int) - want8.astype(int)) <= 6).mean() >= 0.99, spec.output_name
+            assert 40 < float(got.mean()) < 120                # the saturated picture would sit at ~255
+
+
+def test_two_worker_processes_write_what_one_process_writes(r360, tmp_path):
+    """remap360.multigpu: still sources dealt out to one worker process per device, a video split by frame ranges.
+    On a one-GPU box both workers share the device; the files must be the same as a single-process run's."""
+    cv2 = pytest.importorskip("cv2")
+    from remap360 import multigpu, perspcut as pc
+    src_dir = tmp_path / "in"
+    src_dir.mkdir()
+    rng = np.random.default_rng(3)
+    for k in range(5):
+        assert cv2.imwrite(str(src_dir / ("p%d.png" % k)), rng.integers(0, 256, (256, 512, 3), dtype=np.uint8))
+    args = pc.create_arg_parser().parse_args(["-i", str(src_dir), "--preset", "2views", "--size", "64", "--ext", "png"])
+    args.size_explicit, args.hfov_explicit, args.focal_mm_explicit = True, False, False
+    args.input_is_video, args.video_bit_depth = False, 8
+    files = sorted(src_dir.iterdir())
+    outs = {}
+    for world in (1, 2):
+        out_dir = tmp_path / ("out%d" % world)
+        res = pc.build_view_jobs(args, files, out_dir)
+        done = list(multigpu.run_jobs(res.jobs, None, 1, devices=world))
+        assert len(done) == len(res.jobs) and all(rc == 0 for _j, (rc, _e) in done), done
+        outs[world] = {p.name: p.read_bytes() for p in sorted(out_dir.iterdir())}
+    assert len(outs[1]) == 10 and outs[1] == outs[2]
