@@ -452,32 +452,26 @@ struct TiledParams {
     int l2_policy;          // patch loads: 0 evict_last, 1 evict_normal, 2 evict_first (R360_L2_POLICY, experiments)
 };
 
-// Build-time shape of a block: consumer teams, and how many blocks per SM the register allocation must allow
-// (0 = the kernel's own default, tiled_min_blocks).  Experiments build variants with other values.
-#ifndef R360_TILED_TEAMS
-#define R360_TILED_TEAMS 1
-#endif
+// Shape of a block: one or two consumer teams of eight warps (a template argument of the kernel) and how many blocks
+// per SM the register allocation must allow (R360_TILED_MINB > 0 overrides the kernel's own default, experiments).
 #ifndef R360_TILED_MINB
 #define R360_TILED_MINB 0
 #endif
 constexpr int kConsumerWarps = 8;                       // warps of a team (256 threads <-> 32 rows x 8 lanes)
 constexpr int kTeamThreads = kConsumerWarps * 32;
-constexpr int kTeams = R360_TILED_TEAMS;
-constexpr int kMaxTeams = 4;
-static_assert(kTeams >= 1 && kTeams <= kMaxTeams, "team count");
-constexpr int kSlots = kTeams <= 2 ? 4 : 2 * kTeams;    // slots in flight per block (a multiple of the team count)
-static_assert(kSlots % kTeams == 0, "slot k belongs to team k mod kTeams");
-constexpr int kTiledThreads = kTeams * kTeamThreads + 32;
+constexpr int kMaxTeams = 2;
+constexpr int kSlots = 4;                               // slots in flight per block (a multiple of the team count)
+static_assert(kSlots % kMaxTeams == 0, "slot k belongs to team k mod teams");
+__host__ __device__ constexpr int tiled_threads(int teams) { return teams * kTeamThreads + 32; }
 // blocks per SM the registers are budgeted for: the 8-bit bicubic kernel shares the SM with its 32 KB weight
 // table (2 blocks), lanczos4 with a 128 KB one (1 block); bilinear, 16-bit and float samplers want the registers
 // (and, with several frames per item, the shared memory) of 2 blocks -- measured: bilinear 8-bit, two frames per
-// item, 266 Gpix/s at 2 blocks per SM against 208 at 4; nearest runs 4 blocks of one team
+// item, 266 Gpix/s at 2 blocks per SM against 208 at 4; nearest runs 4 blocks of one team.  Two teams halve it.
 __host__ __device__ constexpr int tiled_default_blocks(int elem_bytes, int interp) {
     return (elem_bytes == 1 && interp == kLanczos4) ? 1 : (interp == kLinear || interp == kCubic || elem_bytes > 1) ? 2 : 4;
 }
-__host__ __device__ constexpr int tiled_min_blocks(int elem_bytes, int interp) {
-    return R360_TILED_MINB > 0 ? R360_TILED_MINB
-                               : (tiled_default_blocks(elem_bytes, interp) + kTeams - 1) / kTeams;
+__host__ __device__ constexpr int tiled_min_blocks(int elem_bytes, int interp, int teams) {
+    return R360_TILED_MINB > 0 ? R360_TILED_MINB : (tiled_default_blocks(elem_bytes, interp) + teams - 1) / teams;
 }
 constexpr int kModeExit = 255;                          // slot record that ends a team's stream
 
@@ -503,7 +497,7 @@ __host__ __device__ constexpr int table_bytes(int use_table) { return use_table 
 // floats) | plan records
 constexpr int kSmemSlots = (2 * kSlots * 8 + 63) / 64 * 64;
 constexpr int kSmemRowc = kSmemSlots + kSlots * 64;
-constexpr int kSmemPlans = kSmemRowc + kTeams * 1536;
+constexpr int kSmemPlans = kSmemRowc + kMaxTeams * 1536;
 constexpr int kTiledFixedSmem = (kSmemPlans + kSlots * 368 + 127) / 128 * 128;
 static_assert(kTiledFixedSmem % 128 == 0 && kTableBytes % 128 == 0 && kSmemPlans % 16 == 0, "ring alignment");
 
@@ -620,8 +614,72 @@ __device__ __forceinline__ void column_rows_u16c3(const TilePlan* plan, const fl
     }
 }
 
-template <int INTERP, typename TIn, typename TOut, int FR>
-__global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks((int)sizeof(TIn), INTERP)) remap_tiled_kernel(const __grid_constant__ TiledParams P,
+// ---- 8-bit RGB, lane = a PAIR of adjacent pixel columns, 16 pairs x 2 rows per warp pass ----------------
+// At the 2:1 minification of an 8K -> 1600 px view neighbouring pixels are 6 source bytes apart: with one pixel per
+// lane a tap load of the warp spreads over 48 words = two shared-memory wavefronts at best (2.4 measured).  With two
+// adjacent pixels per lane the lanes of a row are 12 bytes = three words apart -- an odd word stride, so 16 lanes
+// hit 16 different banks -- and the second half of the warp works on the next tile row, two source rows further
+// down, which with patch pitches that are odd multiples of 32 bytes lands 16 banks away: the two halves
+// interleave (tools/pipe_probe.cu: 1 wavefront for a 12-byte lane stride against 2 for 6 bytes).  Same samplers,
+// same arithmetic; the finished 4-pixel group of two lanes leaves as three 32-bit words.
+// Measured on B200 (16 x 8K frames -> 12 views, two frames per item; shared-memory wavefronts per launch / time):
+// bilinear 363 M / 1.88 ms with one pixel per lane, 352 M / 1.82 ms with pairs: used for bilinear.  Bicubic goes the
+// other way -- 828 M / 3.48 ms with one pixel per lane on 128-byte pitches against 936 M / 3.70 ms with pairs (its four
+// words per tap row make the two half-warps collide more often than the wider stride saves) -- and stays there.
+template <int INTERP, int NF>
+__device__ __forceinline__ void pair_rows_u8c3(const TilePlan* plan, const float* rowc_warp, uint32_t bias, uint32_t pitch,
+                                               uint32_t tab, uint32_t fstride, int lane, int warp, unsigned char* out_rows,
+                                               long long dst_pitch, long long dst_fstride) {
+    const int half = lane >> 4, pair = lane & 15;              // tile row within the pass, pixel pair within the row
+    const bool odd = (pair & 1) != 0;
+    const double axi = plan->ax[1], ayi = plan->ay[1], axj = plan->ax[2], ayj = plan->ay[2];
+    const float s0 = (float)(4 * pair - (kTile - 1)) * (1.0f / (kTile - 1)), s1 = (float)(4 * pair + 2 - (kTile - 1)) * (1.0f / (kTile - 1));
+    const double di0 = (double)(2 * pair);
+    // even pair lane: words 0 and 1 of its 4-pixel group at byte 12 * (pair / 2); odd pair lane: word 2
+    unsigned char* out_a = out_rows + (long long)half * dst_pitch + 12 * (pair >> 1) + (odd ? 8 : 0);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int row = 2 * pass + half;                        // 0..3 within the warp's four rows
+        const float* rq = rowc_warp + row * 12;
+        const float4 c0 = *reinterpret_cast<const float4*>(rq), c1 = *reinterpret_cast<const float4*>(rq + 4),
+                     c2 = *reinterpret_cast<const float4*>(rq + 8);
+        const double djl = (double)(warp * 4 + row);
+        const double ax_b = fma(axj, djl, plan->ax[0]), ay_b = fma(ayj, djl, plan->ay[0]);
+        uint32_t px[2][NF];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            float dx, dy;
+            residual_xy(c0, c1, c2, e ? s1 : s0, dx, dy);
+            const float sx = __double2float_rn(fma(axi, di0 + (double)e, ax_b) + (double)dx);
+            const float sy = __double2float_rn(fma(ayi, di0 + (double)e, ay_b) + (double)dy);
+            if constexpr (INTERP == kCubic) {
+                const BicubicPrep pp = bicubic_prep_u8c3(bias, pitch, tab, round_bits(sx), round_bits(sy));
+#pragma unroll
+                for (int f = 0; f < NF; ++f) px[e][f] = bicubic_taps_u8c3(pp, pitch, (uint32_t)f * fstride);
+            } else {
+                const BilinearPrep pp = bilinear_prep_u8c3(bias, pitch, round_bits(sx), round_bits(sy));
+#pragma unroll
+                for (int f = 0; f < NF; ++f) px[e][f] = bilinear_taps_u8c3(pp, pitch, (uint32_t)f * fstride);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            // group of four pixels A0 A1 (even lane) B0 B1 (odd lane), each R | G << 8 | B << 16:
+            //   word 0 = A0 | A1 << 24, word 1 = A1 >> 8 | B0 << 16, word 2 = B0 >> 16 | B1 << 8
+            const uint32_t b0 = __shfl_down_sync(0xffffffffu, px[0][f], 1);
+            const uint32_t first = odd ? ((px[0][f] >> 16) | (px[1][f] << 8)) : (px[0][f] | (px[1][f] << 24));
+            const uint32_t second = (px[1][f] >> 8) | (b0 << 16);
+            unsigned char* o = out_a + f * dst_fstride;
+            asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(o), "r"(first));
+            asm volatile("{\n.reg .pred p;\nsetp.eq.u32 p, %2, 0;\n@p st.global.cs.b32 [%0], %1;\n}"
+                         ::"l"(o + 4), "r"(second), "r"((uint32_t)odd));
+        }
+        out_a += 2 * dst_pitch;
+    }
+}
+
+template <int INTERP, typename TIn, typename TOut, int FR, int TEAMS>
+__global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)sizeof(TIn), INTERP, TEAMS)) remap_tiled_kernel(const __grid_constant__ TiledParams P,
                                                                     const __grid_constant__ TensorMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);            // [kSlots]
@@ -631,7 +689,7 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks((int)sizeof(TI
     TilePlan* planbuf = reinterpret_cast<TilePlan*>(smem + kSmemPlans);          // [kSlots]
     unsigned char* table = smem + kTiledFixedSmem;
     unsigned char* stage_all = table + table_bytes(P.use_table);   // [team][FR][out_stage_bytes]
-    constexpr int n_teams = kTeams;
+    constexpr int n_teams = TEAMS;
     unsigned char* ring = stage_all + n_teams * FR * P.out_stage_bytes;
 
     constexpr bool kFastU8 = std::is_same<TIn, uint8_t>::value && std::is_same<TOut, uint8_t>::value &&
@@ -897,7 +955,15 @@ __global__ void __launch_bounds__(kTiledThreads, tiled_min_blocks((int)sizeof(TI
             if (mode != kModeFill && mode != kModeFastSeam && P.channels == 3 && si->full_tile && P.bulk_store_ok) {
                 const int m = lane & 3;
                 unsigned char* out_word = P.dst.data + si->dst_tile + (long long)(warp * 4) * P.dst.pitch + ((lane >> 2) * 3 + m) * 4;
-                if (FR > 1 && nf == FR)
+                if constexpr (INTERP == kLinear) {
+                    unsigned char* out_rows = P.dst.data + si->dst_tile + (long long)(warp * 4) * P.dst.pitch;
+                    if (FR > 1 && nf == FR)
+                        pair_rows_u8c3<INTERP, FR>(plan, rowc + warp * 48, si->bias, (uint32_t)si->pitch, col_tab, fstride, lane, warp,
+                                                   out_rows, P.dst.pitch, P.dst_fstride);
+                    else
+                        pair_rows_u8c3<INTERP, 1>(plan, rowc + warp * 48, si->bias, (uint32_t)si->pitch, col_tab, fstride, lane, warp,
+                                                  out_rows, P.dst.pitch, P.dst_fstride);
+                } else if (FR > 1 && nf == FR)
                     column_rows_u8c3<INTERP, FR>(plan, rowc + warp * 48, si->bias, (uint32_t)si->pitch, col_tab, fstride, col_s,
                                                  col_dlane, col_drow, out_word, P.dst.pitch, P.dst_fstride, m);
                 else

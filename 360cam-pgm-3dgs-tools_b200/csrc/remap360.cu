@@ -413,7 +413,7 @@ struct r360_plan {
     std::vector<ViewDev> views;
     int tiles_x, tiles_y, n_tiles, n_fallback;
     int out_stage_bytes, patch_budget, ring_bytes, smem_bytes, ctas_per_sm, use_table, sm_count;
-    int frames_pref, ctas_multi_pref;     // launch shape for batches (choose_shape)
+    int frames_pref, teams_multi_pref, ctas_multi_pref;     // launch shape for batches (choose_shape)
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
     PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback; int2* d_order;
@@ -518,9 +518,9 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
         // blocks per SM: what the kernel's registers are budgeted for (tiled_min_blocks); 8-bit bicubic without the
         // packed sampler (1 / 4 channels) has no table in shared memory but is compiled for 2 blocks all the same
-        int want = pl->use_table == 2 ? 1 : tiled_min_blocks(in_es, pl->pr.interp);
+        int want = pl->use_table == 2 ? 1 : tiled_min_blocks(in_es, pl->pr.interp, 1);
         if (const char* env = std::getenv("R360_TILED_CTAS_PER_SM")) want = std::atoi(env) > 0 ? std::atoi(env) : want;
-        const int fixed = kTiledFixedSmem + table_bytes(pl->use_table) + kTeams * pl->out_stage_bytes + 128;   // one frame per item
+        const int fixed = kTiledFixedSmem + table_bytes(pl->use_table) + pl->out_stage_bytes + 128;   // one team, one frame per item
         for (;; --want) {
             const int per_block = smem_per_sm / want - 1024;       // 1 KB per block is reserved by the driver
             pl->ring_bytes = (per_block - fixed) & ~127;
@@ -534,11 +534,16 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         }
         pl->ctas_per_sm = want;
         pl->smem_bytes = fixed + pl->ring_bytes;
-        // batches: frames per work item / blocks per SM (choose_shape).  A patch may use the whole ring of the
-        // smallest shape a call can take: the one with kMaxFramesPerItem output stages per team.
-        pl->frames_pref = pl->use_table == 2 ? 1 : 2;
-        pl->ctas_multi_pref = want;
-        pl->patch_budget = pl->ring_bytes - (kMaxFramesPerItem - 1) * kTeams * pl->out_stage_bytes;
+        // batches: frames per work item / teams / blocks per SM (choose_shape).  8-bit bicubic: four frames per
+        // item on two teams in one block per SM -- one weight table per SM instead of two leaves the ring room for
+        // four frames' patches, and every table entry read serves four pixels (measured on B200, 16 x 8K frames ->
+        // 12 views: 148-150 Gpix/s against 141 with two frames per item on two blocks per SM).  A patch may use the
+        // whole ring of the smallest shape a call can take: one team with kMaxFramesPerItem output stages.
+        const bool cubic_u8 = pl->use_table == 1;
+        pl->frames_pref = pl->use_table == 2 ? 1 : cubic_u8 ? 4 : 2;
+        pl->teams_multi_pref = cubic_u8 ? 2 : 1;
+        pl->ctas_multi_pref = cubic_u8 ? 1 : want;
+        pl->patch_budget = pl->ring_bytes - (kMaxFramesPerItem - 1) * pl->out_stage_bytes;
         if (pl->patch_budget < 8192) pl->patch_budget = 8192;
     }
     // the data pointers are not known yet: assume 16-byte aligned bases (checked at remap time)
@@ -645,26 +650,28 @@ TiledShape choose_shape(const r360_plan* pl, int n_groups) {
     fr = env_int("R360_FRAMES", fr);
     if (fr != 1 && fr != 2 && fr != 4) fr = 1;
     if (fr > n_groups) fr = n_groups >= 2 ? 2 : 1;
-    int teams = kTeams;                      // a build-time constant of the kernels (R360_TILED_TEAMS)
-    int ctas = std::max(1, env_int("R360_TILED_CTAS_PER_SM", fr > 1 ? pl->ctas_multi_pref : pl->ctas_per_sm));
+    // two teams exist for four-frame items only (the instantiations the library carries)
+    int teams = fr == 4 ? std::min(kMaxTeams, std::max(1, env_int("R360_TEAMS", pl->teams_multi_pref))) : 1;
+    int ctas = std::max(1, env_int("R360_TILED_CTAS_PER_SM", fr == 4 && teams == 2 ? pl->ctas_multi_pref : pl->ctas_per_sm));
     TiledShape s;
     for (;;) {
         if (shape_for(pl, fr, teams, ctas, smem_per_sm, &s)) return s;
         if (ctas > 1) --ctas;
-        else if (fr > 1) fr /= 2;
+        else if (teams > 1) --teams;
+        else if (fr > 1) { fr /= 2; teams = 1; ctas = pl->ctas_per_sm; }
         else break;
     }
     // the plan's own single-frame shape always fits (it defined the patch budget)
-    s.fr = 1; s.teams = kTeams; s.ctas = pl->ctas_per_sm; s.ring = pl->ring_bytes; s.smem = pl->smem_bytes; s.multi_budget = 0;
+    s.fr = 1; s.teams = 1; s.ctas = pl->ctas_per_sm; s.ring = pl->ring_bytes; s.smem = pl->smem_bytes; s.multi_budget = 0;
     return s;
 }
 
 struct TiledLauncher {
     const r360_plan* pl; const r360_images* src; const r360_images* dst; cudaStream_t s;
 
-    template <int INTERP, typename TIn, typename TOut, int FR>
+    template <int INTERP, typename TIn, typename TOut, int FR, int TEAMS>
     int launch(const TiledParams& Q, const TensorMaps& maps, const TiledShape& shape, long long grid) {
-        auto kernel = remap_tiled_kernel<INTERP, TIn, TOut, FR>;
+        auto kernel = remap_tiled_kernel<INTERP, TIn, TOut, FR, TEAMS>;
         {
             // opt this instantiation in to the device's full shared memory once per device (the attribute is
             // per context; plans of different channel counts need different amounts of the same kernel)
@@ -680,7 +687,7 @@ struct TiledLauncher {
                 configured[dev] = true;
             }
         }
-        kernel<<<dim3((unsigned)grid), shape.teams * kTeamThreads + 32, shape.smem, s>>>(Q, maps);
+        kernel<<<dim3((unsigned)grid), tiled_threads(TEAMS), shape.smem, s>>>(Q, maps);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         R360_CUDA(cudaGetLastError());
         return R360_OK;
@@ -738,9 +745,10 @@ struct TiledLauncher {
                 maps = hit->maps;
             }
             int rc;
-            if (shape.fr == 4) rc = launch<INTERP, TIn, TOut, 4>(Q, maps, shape, grid);
-            else if (shape.fr == 2) rc = launch<INTERP, TIn, TOut, 2>(Q, maps, shape, grid);
-            else rc = launch<INTERP, TIn, TOut, 1>(Q, maps, shape, grid);
+            if (shape.fr == 4 && shape.teams == 2) rc = launch<INTERP, TIn, TOut, 4, 2>(Q, maps, shape, grid);
+            else if (shape.fr == 4) rc = launch<INTERP, TIn, TOut, 4, 1>(Q, maps, shape, grid);
+            else if (shape.fr == 2) rc = launch<INTERP, TIn, TOut, 2, 1>(Q, maps, shape, grid);
+            else rc = launch<INTERP, TIn, TOut, 1, 1>(Q, maps, shape, grid);
             if (rc != R360_OK) return rc;
         }
 

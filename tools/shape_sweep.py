@@ -27,7 +27,8 @@ def main():
     ap.add_argument("--interp", nargs="+", default=["cubic", "linear"])
     ap.add_argument("--fr", nargs="+", type=int, default=[1, 2, 4])
     ap.add_argument("--ctas", nargs="+", type=int, default=[0])
-    ap.add_argument("--pct", nargs="+", type=int, default=[50])
+    ap.add_argument("--pct", nargs="+", type=int, default=[75])
+    ap.add_argument("--teams", nargs="+", type=int, default=[0], help="consumer teams for four-frame items (0 = the library's choice)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--dtype", default="u8")
     ap.add_argument("--stats", action="store_true", help="wait-time counters of a -DR360_TILED_STATS=1 build")
@@ -45,8 +46,13 @@ def main():
     for interp in ns.interp:
         for fr in ns.fr:
             for ctas in ns.ctas:
+              for teams in (ns.teams if fr == 4 else ns.teams[:1]):
                 for pct in (ns.pct if fr > 1 else ns.pct[:1]):
                     os.environ["R360_FRAMES"] = str(fr)
+                    if teams > 0:
+                        os.environ["R360_TEAMS"] = str(teams)
+                    else:
+                        os.environ.pop("R360_TEAMS", None)
                     os.environ["R360_MULTI_PCT"] = str(pct)
                     if ctas > 0:
                         os.environ["R360_TILED_CTAS_PER_SM"] = str(ctas)
@@ -84,7 +90,7 @@ def main():
                         stats = {"consumer_wait_frac": round(cw / max(c, 1), 4), "producer_wait_frac": round(pw / max(p, 1), 4),
                                  "slots": sl, "multi_slots": mu}
                     sha = hashlib.sha256(out[:2].view(torch.uint8).cpu().numpy().tobytes()).hexdigest()[:12]
-                    print(json.dumps({"library": os.path.basename(lib), "interp": interp, "dtype": ns.dtype, "fr": fr, "ctas": ctas,
+                    print(json.dumps({"library": os.path.basename(lib), "interp": interp, "dtype": ns.dtype, "fr": fr, "ctas": ctas, "teams": teams,
                                       "pct": pct, "ms": round(ms, 4), "Gpix_per_s": round(out.numel() / 3 / ms / 1e6, 1),
                                       "sha": sha, "stats": stats}), flush=True)
 
