@@ -91,6 +91,13 @@ int ensure_device_ready() {
         built = true;
     }
     R360_CUDA(cudaMemcpyToSymbol(g_tables, &host_tables, sizeof(WeightTables)));
+    // L2 persisting carve-out: the patch loads carry an evict_last policy, which only protects lines while the
+    // device has a persisting region to keep them in (experiments: R360_L2_PERSIST_MB, default = leave the device alone)
+    if (const char* env = std::getenv("R360_L2_PERSIST_MB")) {
+        const size_t want = (size_t)std::max(0, std::atoi(env)) << 20;
+        const size_t cap = (size_t)prop.persistingL2CacheMaxSize;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(want, cap));
+    }
     static FitConstants fit;
     make_fit_constants(&fit);
     R360_CUDA(cudaMemcpyToSymbol(c_fit, &fit, sizeof(FitConstants)));
@@ -387,6 +394,11 @@ int remap_direct(int proj, const r360_images* src, const r360_images* dst, const
 // ---- plans ------------------------------------------------------------------------------------------
 
 
+int env_int(const char* name, int fallback) {
+    const char* e = std::getenv(name);
+    return e && *e ? std::atoi(e) : fallback;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kMaxRingBytes = 200 * 1024;       // shared-memory ring of one block
@@ -540,7 +552,10 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         // 12 views: 148-150 Gpix/s against 141 with two frames per item on two blocks per SM).  A patch may use the
         // whole ring of the smallest shape a call can take: one team with kMaxFramesPerItem output stages.
         const bool cubic_u8 = pl->use_table == 1;
-        pl->frames_pref = pl->use_table == 2 ? 1 : cubic_u8 ? 4 : 2;
+        const bool linear_u8 = pl->pr.in_dt == R360_U8 && pl->pr.interp == R360_LINEAR && dst->channels == 3;
+        // (8-bit bilinear: four frames per item on one team, 264 against 256 Gpix/s with two; 16-bit patches are twice
+        // the size and stay at two frames per item)
+        pl->frames_pref = pl->use_table == 2 ? 1 : (cubic_u8 || linear_u8) ? 4 : 2;
         pl->teams_multi_pref = cubic_u8 ? 2 : 1;
         pl->ctas_multi_pref = cubic_u8 ? 1 : want;
         pl->patch_budget = pl->ring_bytes - (kMaxFramesPerItem - 1) * pl->out_stage_bytes;
@@ -551,7 +566,9 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
                        ((int64_t)src->width * src->channels * in_es) % 16 == 0;
     pl->bulk_store_ok = dst->pitch_bytes % 16 == 0 && dst->image_stride_bytes % 16 == 0;
     pl->tensor_ok = pl->bulk_load_ok && encode_tiled_fn() != nullptr && std::getenv("R360_NO_TENSOR_TMA") == nullptr;
-    pl->box_family = pl->use_table == 1 ? 1 : 0;      // lane-per-column bicubic path: rows on identical banks
+    // lane-per-column bicubic paths (8-bit and 16-bit): rows on identical banks; measured 16-bit bicubic 76.7 against
+    // 73.3 Gpix/s with the odd multiples of 32 bytes, 8-bit bilinear (pixel pairs) 265 against 251 the other way round
+    pl->box_family = (pl->use_table == 1 || (in_es == 2 && pl->pr.interp == R360_CUBIC && dst->channels == 3)) ? 1 : 0;
     if (const char* env = std::getenv("R360_BOX_FAMILY")) pl->box_family = std::atoi(env) == 1 ? 1 : 0;
     pl->ws = static_cast<unsigned char*>(workspace);
     pl->d_header = reinterpret_cast<PlanHeader*>(pl->ws + wl.header);
@@ -603,6 +620,14 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
         std::vector<int> idx(n);
         for (int i = 0; i < n; ++i) idx[i] = i;
+        // rows are grouped in bands of 128: inside a band the tiles keep their (view, tile) order, so the entries the
+        // grid loads at the same moment are horizontal neighbours of one view.  Measured on B200 (16 x 8K frames, 12
+        // views, DRAM reads per launch / Gpix/s): bicubic 2.02 GB / 145.5 sorted by exact row, 1.60 GB / 148.5 in bands
+        // of 128 rows (unique source bytes: 1.27 GB); bilinear 4.71 GB / 272.8 -> 3.71 GB / 281.8 (R360_ORDER_BAND)
+        const int band = std::max(1, env_int("R360_ORDER_BAND", 128));
+        if (band > 1)
+            for (int i = 0; i < n; ++i)
+                if (keys[i] != INT_MAX) keys[i] = (keys[i] & ~0xFFFFFF) | ((keys[i] & 0xFFFFFF) / band);
         std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return keys[a] < keys[b]; });
         std::vector<int2> order;
         order.reserve(n);
@@ -622,10 +647,6 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
 // (ring >= plan->patch_budget); what a shape changes is how many frames share one coordinate / weight set-up.
 struct TiledShape { int fr, teams, ctas, ring, smem, multi_budget; };
 
-int env_int(const char* name, int fallback) {
-    const char* e = std::getenv(name);
-    return e && *e ? std::atoi(e) : fallback;
-}
 
 bool shape_for(const r360_plan* pl, int fr, int teams, int ctas, int smem_per_sm, TiledShape* out) {
     const int fixed = kTiledFixedSmem + table_bytes(pl->use_table) + teams * fr * pl->out_stage_bytes + 128;
