@@ -202,7 +202,9 @@ int r360_jpeg_encode(r360_jpeg* c, const r360_images* src, int32_t index, int32_
     const bool grey = src->channels == 1;
     if (q != c->quality || grey != c->grey) {
         R360_NVJ(nvjpegEncoderParamsSetQuality(c->params, q, s));
-        R360_NVJ(nvjpegEncoderParamsSetOptimizedHuffman(c->params, 1, s));
+        // optimised Huffman tables (a second pass over the coefficients) unless R360_JPEG_HUFFMAN=default
+        static const int optimise = []() { const char* e = std::getenv("R360_JPEG_HUFFMAN"); return (e && !std::strcmp(e, "default")) ? 0 : 1; }();
+        R360_NVJ(nvjpegEncoderParamsSetOptimizedHuffman(c->params, optimise, s));
         R360_NVJ(nvjpegEncoderParamsSetSamplingFactors(c->params, grey ? NVJPEG_CSS_GRAY : NVJPEG_CSS_444, s));
         c->quality = q; c->grey = grey;
     }

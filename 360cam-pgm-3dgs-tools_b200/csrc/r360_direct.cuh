@@ -31,27 +31,38 @@ __device__ __forceinline__ bool project_pixel(const ViewDev& view, const ErpDev&
     return fisheye_xy(lens[view.slot], dx, dy, dz, x, y);
 }
 
+// Sampling half of one output pixel, for NF consecutive frames of the batch starting at frame g: (x, y) is the
+// source coordinate project_pixel returned, already cast to float32 as cv2's map would be.
+template <int PROJ, int INTERP, typename TIn, typename TOut, int NF>
+__device__ __forceinline__ void direct_sample(const LaunchParams& p, const ViewDev& view, int g, int v, int i, int j,
+                                              float x, float y, bool valid) {
+    const long long dst_img = (long long)g * p.n_views_total + p.view_base + v;
+    const long long dst_fstride = (long long)p.n_views_total * p.dst.image_stride / (long long)sizeof(TOut);   // elements
+    TOut* dst = reinterpret_cast<TOut*>(p.dst.data + dst_img * p.dst.image_stride + (long long)j * p.dst.pitch)
+                + (long long)i * p.channels;
+    if (PROJ != kProjErp && p.fill_invalid && !valid) {
+        for (int f = 0; f < NF; ++f)
+            for (int c = 0; c < p.channels; ++c) dst[f * dst_fstride + c] = Finish<TIn, TOut>::run(p.border_value);
+        return;
+    }
+    const unsigned char* img = p.src.data + ((long long)g * p.n_lenses + view.slot) * p.src.image_stride;
+    const long long src_fstride = (long long)p.n_lenses * p.src.image_stride;
+    if (PROJ == kProjErp) {
+        const ErpGlobalTaps<TIn> taps{img, p.src.pitch, p.src.width, p.src.height, p.channels};
+        sample_pixel_frames<INTERP, TIn, TOut, NF>(taps, src_fstride, p.channels, p.src.width, p.src.height, 0.f, x, y, dst, dst_fstride);
+    } else {
+        const ConstBorderGlobalTaps<TIn> taps{img, p.src.pitch, p.src.width, p.src.height, p.channels, p.border_value};
+        sample_pixel_frames<INTERP, TIn, TOut, NF>(taps, src_fstride, p.channels, p.src.width, p.src.height, p.border_value,
+                                                   x, y, dst, dst_fstride);
+    }
+}
+
 // One output pixel, start to finish.
 template <int PROJ, int INTERP, typename TIn, typename TOut>
 __device__ __forceinline__ void direct_pixel(const LaunchParams& p, const ViewDev& view, int g, int v, int i, int j) {
     double x, y;
     const bool valid = project_pixel<PROJ>(view, p.erp, p.lens, (double)i, (double)j, x, y);
-    const long long dst_img = (long long)g * p.n_views_total + p.view_base + v;
-    TOut* dst = reinterpret_cast<TOut*>(p.dst.data + dst_img * p.dst.image_stride + (long long)j * p.dst.pitch)
-                + (long long)i * p.channels;
-    if (PROJ != kProjErp && p.fill_invalid && !valid) {
-        for (int c = 0; c < p.channels; ++c) dst[c] = Finish<TIn, TOut>::run(p.border_value);
-        return;
-    }
-    const unsigned char* img = p.src.data + ((long long)g * p.n_lenses + view.slot) * p.src.image_stride;
-    if (PROJ == kProjErp) {
-        const ErpGlobalTaps<TIn> taps{img, p.src.pitch, p.src.width, p.src.height, p.channels};
-        sample_pixel<INTERP, TIn, TOut>(taps, p.channels, p.src.width, p.src.height, 0.f, (float)x, (float)y, dst);
-    } else {
-        const ConstBorderGlobalTaps<TIn> taps{img, p.src.pitch, p.src.width, p.src.height, p.channels, p.border_value};
-        sample_pixel<INTERP, TIn, TOut>(taps, p.channels, p.src.width, p.src.height, p.border_value,
-                                        (float)x, (float)y, dst);
-    }
+    direct_sample<PROJ, INTERP, TIn, TOut, 1>(p, view, g, v, i, j, (float)x, (float)y, valid);
 }
 
 template <int PROJ, int INTERP, typename TIn, typename TOut>

@@ -25,14 +25,20 @@ struct ErpGlobalTaps {
     const unsigned char* img; long long pitch; int w, h, channels;
     static constexpr bool kConstantBorder = false;
     __device__ __forceinline__ bool exists(int, int) const { return true; }
-    __device__ __forceinline__ void load(int x, int y, float* out) const {
-        x = x % w;
-        if (x < 0) x += w;
+    // the same tap of NF frames `fstride` bytes apart (NF = 1: one frame)
+    template <int NF>
+    __device__ __forceinline__ void loadn(int x, int y, long long fstride, float (*out)[4]) const {
+        if ((unsigned)x >= (unsigned)w) {            // the seam: rare, so the division stays off the common path
+            x = x % w;
+            if (x < 0) x += w;
+        }
         y = min(max(y, 0), h - 1);
-        const TIn* p = reinterpret_cast<const TIn*>(img + (long long)y * pitch) + (long long)x * channels;
+        const unsigned char* p = img + (long long)y * pitch + (long long)x * channels * (int)sizeof(TIn);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < channels) out[c] = Elem<TIn>::to_float(__ldg(p + c));
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < channels) out[f][c] = Elem<TIn>::to_float(__ldg(reinterpret_cast<const TIn*>(p + f * fstride) + c));
     }
 };
 
@@ -44,15 +50,20 @@ struct ConstBorderGlobalTaps {
     __device__ __forceinline__ bool exists(int x, int y) const {
         return (unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h;
     }
-    __device__ __forceinline__ void load(int x, int y, float* out) const {
+    template <int NF>
+    __device__ __forceinline__ void loadn(int x, int y, long long fstride, float (*out)[4]) const {
         if (exists(x, y)) {
-            const TIn* p = reinterpret_cast<const TIn*>(img + (long long)y * pitch) + (long long)x * channels;
+            const unsigned char* p = img + (long long)y * pitch + (long long)x * channels * (int)sizeof(TIn);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c < channels) out[c] = Elem<TIn>::to_float(__ldg(p + c));
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < channels) out[f][c] = Elem<TIn>::to_float(__ldg(reinterpret_cast<const TIn*>(p + f * fstride) + c));
         } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) out[c] = border;
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) out[f][c] = border;
         }
     }
 };
@@ -68,35 +79,47 @@ struct PatchTaps {
     int channels;
     static constexpr bool kConstantBorder = false;
     __device__ __forceinline__ bool exists(int, int) const { return true; }
-    __device__ __forceinline__ void load(int x, int y, float* out) const {
-        const TIn* p = reinterpret_cast<const TIn*>(base + (y - y0) * pitch + (x * channels * (int)sizeof(TIn) - xb0));
+    template <int NF>
+    __device__ __forceinline__ void loadn(int x, int y, long long fstride, float (*out)[4]) const {
+        const unsigned char* p = base + (y - y0) * pitch + (x * channels * (int)sizeof(TIn) - xb0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < channels) out[c] = Elem<TIn>::to_float(p[c]);
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < channels) out[f][c] = Elem<TIn>::to_float(reinterpret_cast<const TIn*>(p + f * fstride)[c]);
     }
 };
 
 // ---- the sampler ---------------------------------------------------------------------------------
 
-template <int INTERP, typename TIn, typename TOut, typename Taps>
-__device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int src_w, int src_h, float border,
-                                             float x32, float y32, TOut* dst) {
+// One output pixel of NF frames that share the map (a batch): the coordinate, the tap positions and the weights are
+// the frames' common part; `src_fstride` (bytes) and `dst_fstride` (elements) separate the frames.  The arithmetic per
+// frame is exactly the single-frame one, and the loads of the NF frames are independent of one another, which is what
+// the latency-bound fallback kernel needs.
+template <int INTERP, typename TIn, typename TOut, int NF, typename Taps>
+__device__ __forceinline__ void sample_pixel_frames(const Taps& taps, long long src_fstride, int channels, int src_w, int src_h,
+                                                    float border, float x32, float y32, TOut* dst, long long dst_fstride) {
+    float t[NF][4];
     if constexpr (INTERP == kNearest) {
-        float v[4];
-        taps.load(sat_short(__float2int_rn(x32)), sat_short(__float2int_rn(y32)), v);
+        taps.template loadn<NF>(sat_short(__float2int_rn(x32)), sat_short(__float2int_rn(y32)), src_fstride, t);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            if (c < channels) dst[c] = Finish<TIn, TOut>::run(v[c]);   // exact: every element fits a float
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < channels) dst[f * dst_fstride + c] = Finish<TIn, TOut>::run(t[f][c]);   // exact: every element fits a float
         return;
     } else {
         const int sx = __float2int_rn(x32 * 32.0f);
         const int sy = __float2int_rn(y32 * 32.0f);
         const int ix = sat_short(sx >> 5), iy = sat_short(sy >> 5);
         const int fx = sx & 31, fy = sy & 31;
-        float t[4];
 
         if constexpr (std::is_same<TIn, uint8_t>::value) {
-            int acc[4] = {0, 0, 0, 0};
+            int acc[NF][4];
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[f][c] = 0;
             if constexpr (INTERP == kLinear) {
                 // (32-fx)(32-fy) ... in units of 1/1024: cv2's 15-bit table divided by 32, exactly
                 const int wx[2] = {32 - fx, fx}, wy[2] = {32 - fy, fy};
@@ -104,14 +127,18 @@ __device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int
                 for (int ky = 0; ky < 2; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 2; ++kx) {
-                        taps.load(ix + kx, iy + ky, t);
+                        taps.template loadn<NF>(ix + kx, iy + ky, src_fstride, t);
                         const int wgt = wx[kx] * wy[ky];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[c] += wgt * (int)t[c];
+                        for (int f = 0; f < NF; ++f)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[f][c] += wgt * (int)t[f][c];
                     }
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < channels) dst[c] = Finish<uint8_t, TOut>::run((float)((acc[c] + 512) >> 10));
+                for (int f = 0; f < NF; ++f)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < channels) dst[f * dst_fstride + c] = Finish<uint8_t, TOut>::run((float)((acc[f][c] + 512) >> 10));
             } else {
                 constexpr int K = INTERP == kCubic ? 4 : 8, OFF = K / 2 - 1;
                 const short* wt = (INTERP == kCubic ? g_tables.cubic_fixed : g_tables.lanczos_fixed) + (fy * 32 + fx) * (K * K);
@@ -119,17 +146,26 @@ __device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int
                 for (int ky = 0; ky < K; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < K; ++kx) {
-                        taps.load(ix - OFF + kx, iy - OFF + ky, t);
+                        taps.template loadn<NF>(ix - OFF + kx, iy - OFF + ky, src_fstride, t);
                         const int wgt = wt[ky * K + kx];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[c] += wgt * (int)t[c];
+                        for (int f = 0; f < NF; ++f)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[f][c] += wgt * (int)t[f][c];
                     }
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < channels) dst[c] = Finish<uint8_t, TOut>::run((float)min(max((acc[c] + 16384) >> 15, 0), 255));
+                for (int f = 0; f < NF; ++f)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < channels)
+                            dst[f * dst_fstride + c] = Finish<uint8_t, TOut>::run((float)min(max((acc[f][c] + 16384) >> 15, 0), 255));
             }
         } else {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc[NF][4];
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[f][c] = 0.f;
             if constexpr (INTERP == kLinear) {
                 const float tx = (float)fx * (1.0f / 32.0f), ty = (float)fy * (1.0f / 32.0f);
                 const float wx[2] = {1.0f - tx, tx}, wy[2] = {1.0f - ty, ty};
@@ -137,13 +173,15 @@ __device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int
                 for (int ky = 0; ky < 2; ++ky)
 #pragma unroll
                     for (int kx = 0; kx < 2; ++kx) {
-                        taps.load(ix + kx, iy + ky, t);
+                        taps.template loadn<NF>(ix + kx, iy + ky, src_fstride, t);
                         const float wgt = __fmul_rn(wy[ky], wx[kx]);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float term = __fmul_rn(t[c], wgt);
-                            acc[c] = (ky == 0 && kx == 0) ? term : __fadd_rn(acc[c], term);
-                        }
+                        for (int f = 0; f < NF; ++f)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float term = __fmul_rn(t[f][c], wgt);
+                                acc[f][c] = (ky == 0 && kx == 0) ? term : __fadd_rn(acc[f][c], term);
+                            }
                     }
             } else {
                 constexpr int K = INTERP == kCubic ? 4 : 8, OFF = K / 2 - 1;
@@ -158,41 +196,57 @@ __device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int
                     // each row summed left to right, rows added to a running sum that starts at zero
 #pragma unroll(K == 4 ? 4 : 1)
                     for (int ky = 0; ky < K; ++ky) {
-                        float row[4] = {0.f, 0.f, 0.f, 0.f};
+                        float row[NF][4];
 #pragma unroll
                         for (int kx = 0; kx < K; ++kx) {
-                            taps.load(x0 + kx, y0 + ky, t);
+                            taps.template loadn<NF>(x0 + kx, y0 + ky, src_fstride, t);
                             const float wgt = __fmul_rn(wy[ky], wx[kx]);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const float term = __fmul_rn(t[c], wgt);
-                                row[c] = kx == 0 ? term : __fadd_rn(row[c], term);
-                            }
+                            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    const float term = __fmul_rn(t[f][c], wgt);
+                                    row[f][c] = kx == 0 ? term : __fadd_rn(row[f][c], term);
+                                }
                         }
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[c] = __fadd_rn(acc[c], row[c]);
+                        for (int f = 0; f < NF; ++f)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[f][c] = __fadd_rn(acc[f][c], row[f][c]);
                     }
                 } else {
                     // near the sensor edge cv2 starts from the border value and adds
                     // (tap - border) * w for the taps that exist
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[c] = border;
+                    for (int f = 0; f < NF; ++f)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[f][c] = border;
                     for (int ky = 0; ky < K; ++ky)
                         for (int kx = 0; kx < K; ++kx) {
                             if (!taps.exists(x0 + kx, y0 + ky)) continue;
-                            taps.load(x0 + kx, y0 + ky, t);
+                            taps.template loadn<NF>(x0 + kx, y0 + ky, src_fstride, t);
                             const float wgt = __fmul_rn(wy[ky], wx[kx]);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                acc[c] = __fadd_rn(acc[c], __fmul_rn(__fsub_rn(t[c], border), wgt));
+                            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    acc[f][c] = __fadd_rn(acc[f][c], __fmul_rn(__fsub_rn(t[f][c], border), wgt));
                         }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c < channels) dst[c] = Finish<TIn, TOut>::run(acc[c]);
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < channels) dst[f * dst_fstride + c] = Finish<TIn, TOut>::run(acc[f][c]);
         }
     }
+}
+
+template <int INTERP, typename TIn, typename TOut, typename Taps>
+__device__ __forceinline__ void sample_pixel(const Taps& taps, int channels, int src_w, int src_h, float border,
+                                             float x32, float y32, TOut* dst) {
+    sample_pixel_frames<INTERP, TIn, TOut, 1>(taps, 0, channels, src_w, src_h, border, x32, y32, dst, 0);
 }
 
 }  // namespace r360

@@ -80,14 +80,23 @@ struct TilePlan {
     int xb0, row_bytes;  // source byte column of patch byte 0 (multiple of 16), bytes needed per row
     int pitch;           // patch row pitch in shared memory
     int mode_slot;       // TileMode | (source slot << 8) | (box width index << 16)
-    int pad[2];
+    int pad[2];          // [0] why the tile is on the fallback list (tools/fallback_reasons.py), -1: staged tile whose patch
+                         // needs the large ring (large-patch pass), [1] 1 + index of the
+                         // tile's per-pixel map in the coordinate pool (0: the polynomial is the map)
 };
 static_assert(sizeof(TilePlan) == 368, "TilePlan layout");
 
 struct PlanHeader {      // first 256 bytes of the plan workspace
     int n_fallback;
-    int pad[63];
+    int n_coords;        // per-pixel maps handed out (may exceed the pool: the surplus tiles are fallback tiles)
+    int pad[62];
 };
+
+// A tile whose map no degree-5 polynomial follows (the neighbourhood of a pole) but whose patch still fits the ring
+// keeps an explicit map instead: 32 x 32 float64 pairs (32 x, 32 y), unwrapped like the polynomial's values, in a
+// pool behind the plan records.  The remap kernel reads it where it would evaluate the polynomial; everything after
+// that -- seam wrap, float32 cast, staging, sampling of all frames of the batch -- is the ordinary tile path.
+constexpr int kCoordTileBytes = kTile * kTile * 16;
 
 struct FitConstants {
     double node[kFitN];              // Chebyshev nodes on [-1, 1]
@@ -101,6 +110,7 @@ struct PlanParams {
     int out_w, out_h, tiles_x, tiles_y, n_views;
     int src_w, src_h, px_bytes;      // px_bytes = channels * sizeof(source element)
     int patch_budget;                // bytes of shared memory the remap kernel can give to a patch
+    int patch_budget_large;          // ... in its one-block-per-SM, one-frame shape: the pass for tiles with large patches
     int bulk_load_ok;                // source layout allows 16-byte aligned row copies
     int tensor_ok;                   // tensor-TMA descriptors can be built for the source layout
     int fill_invalid;
@@ -112,6 +122,8 @@ struct PlanParams {
     TilePlan* plans;                 // n_views * tiles, device
     PlanHeader* header;
     int2* fallback;                  // (view, tile) list, device
+    double2* coords;                 // pool of per-pixel maps (kTile * kTile entries each), nullptr: none
+    int coords_capacity;             // maps in the pool
 };
 
 __device__ __forceinline__ double poly2d(const double* K, double s, double t) {
@@ -130,6 +142,7 @@ template <int PROJ>
 __device__ __forceinline__ void plan_tile(const PlanParams& P) {
     __shared__ double fx[64], fy[64], gx[36], gy[36], kx[36], ky[36], resid[16];
     __shared__ int valid_count, invalid_count, bmin_x, bmax_x, bmin_y, bmax_y;
+    __shared__ int s_poly_ok, s_coords_idx;
     const int tid = threadIdx.x;
     const int tile = blockIdx.x, v = blockIdx.y;
     const int i0 = (tile % P.tiles_x) * kTile, j0 = (tile / P.tiles_x) * kTile;
@@ -238,8 +251,33 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
         // size of the last Chebyshev terms, i.e. of the truncation error (calibrated offline:
         // tiles passing both tests have fit error < 1e-5 px).  Every
         // comparison is written so that a NaN fails it.
-        bool fit_ok = top_x * (1.0 / 16.0) < 2e-4 && top_y * (1.0 / 16.0) < 2e-4;
-        for (int q = 0; q < kFitChecks; ++q) fit_ok = fit_ok && resid[q] < 4e-6;
+        bool ok_fit = top_x * (1.0 / 16.0) < 2e-4 && top_y * (1.0 / 16.0) < 2e-4;
+        for (int q = 0; q < kFitChecks; ++q) ok_fit = ok_fit && resid[q] < 4e-6;
+        s_poly_ok = ok_fit ? 1 : 0;
+        s_coords_idx = -1;
+    }
+    __syncthreads();
+    // -- no polynomial (panorama tiles next to a pole): the exact map of all 1024 pixels, first its bounding box ----
+    const bool exact = PROJ == kProjErp && P.coords != nullptr && !s_poly_ok;
+    if (exact) {
+        if (tid == 0) { bmin_x = INT_MAX; bmax_x = INT_MIN; bmin_y = INT_MAX; bmax_y = INT_MIN; }
+        __syncthreads();
+        const double ref = fx[0], period = P.erp.su, lim = 268435456.0;
+        for (int px = tid; px < kTile * kTile; px += 64) {
+            double ex, ey;
+            project_pixel<PROJ>(view, P.erp, P.lens, (double)(i0 + (px & (kTile - 1))), (double)(j0 + px / kTile), ex, ey);
+            double d = ex - ref;
+            d -= period * rint(d / period);
+            const int fxv = (int)floor(fmin(fmax(ref + d, -lim), lim));
+            const int fyv = (int)floor(fmin(fmax(ey, -lim), lim));
+            atomicMin(&bmin_x, fxv); atomicMax(&bmax_x, fxv);
+            atomicMin(&bmin_y, fyv); atomicMax(&bmax_y, fyv);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const bool poly_ok = s_poly_ok != 0;
+        bool fit_ok = poly_ok || exact;
         fit_ok = fit_ok && (long long)bmax_x - bmin_x < 2048 && (long long)bmax_y - bmin_y < 2048;
 
         // patch geometry
@@ -248,6 +286,11 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
         const int ys0 = bmin_y - lo, ys1 = bmax_y + hi;
         int mode = kModeFallback, wbox = 0;
         int xb0 = 0, row_bytes = 0, pitch = 0, rows = 0;
+        // why a tile is left to the direct path (pad[0] of its record; tools/fallback_reasons.py reads it):
+        // 1 the polynomial does not fit, 2 the patch does not fit the ring, 3 columns outside one period / the
+        // sensor (and no seam handling for this geometry), 4 rows outside the sensor or invalid pixels, 5 the
+        // map is fine but the tile spans 2048 source pixels or more, 6 the coordinate pool is full
+        int reason = fit_ok ? 3 : (poly_ok || exact) ? 5 : 1;
         if (fit_ok) {
             xb0 = (xs0 * P.px_bytes) & ~15;
             const int xb1 = ((xs1 + 1) * P.px_bytes + 15) & ~15;
@@ -256,7 +299,7 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
             // columns must lie inside one period of the panorama / inside the sensor
             const int row_total = P.src_w * P.px_bytes;
             bool fast = P.bulk_load_ok && xs0 >= 0 && xb1 <= row_total;
-            if (PROJ != kProjErp) fast = fast && ys0 >= 0 && ys1 < P.src_h && invalid_count == 0;
+            if (PROJ != kProjErp && fast && !(ys0 >= 0 && ys1 < P.src_h && invalid_count == 0)) { fast = false; reason = 4; }
             // seam: only when the coordinate period equals the image width (halfpixel convention)
             const bool seam = PROJ == kProjErp && P.bulk_load_ok && !fast && P.erp.su == (double)P.src_w &&
                               row_bytes <= row_total && xb0 > -row_total && xb1 < 2 * row_total;
@@ -264,26 +307,49 @@ __device__ __forceinline__ void plan_tile(const PlanParams& P) {
                 while (wbox < kNumBoxWidths && box_width_bytes(wbox, P.box_family) < row_bytes) ++wbox;
                 const bool rows_inside = ys0 >= 0 && ys1 < P.src_h;
                 if (P.tensor_ok && wbox < kNumBoxWidths && rows_inside &&
-                    staged_rows(rows) * box_width_bytes(wbox, P.box_family) <= P.patch_budget) {
+                    staged_rows(rows) * box_width_bytes(wbox, P.box_family) <= P.patch_budget_large) {
                     mode = kModeFast;                                    // tensor boxes: pitch = box width
                     pitch = box_width_bytes(wbox, P.box_family);
                 } else {
                     wbox = 0;
                     pitch = row_bytes + ((row_bytes & 127) == 0 ? 16 : 0);   // keep rows off the same banks
-                    if (rows * pitch <= P.patch_budget) mode = kModeFastRows;
+                    if (rows * pitch <= P.patch_budget_large) mode = kModeFastRows;
+                    else reason = 2;
                 }
             } else if (seam) {
                 pitch = row_bytes + ((row_bytes & 127) == 0 ? 16 : 0);
-                if (rows * pitch <= P.patch_budget) mode = kModeFastSeam;
+                if (rows * pitch <= P.patch_budget_large) mode = kModeFastSeam;
+                else reason = 2;
             }
         }
         if (PROJ != kProjErp && P.fill_invalid && valid_count == 0) mode = kModeFill;
+        // a patch that only the large ring holds: the tile leaves the main walk for the large-patch pass (pad[0] = -1)
+        const bool large = (mode == kModeFast || mode == kModeFastRows || mode == kModeFastSeam) &&
+                           (mode == kModeFast ? staged_rows(rows) : rows) * pitch > P.patch_budget;
+        if (exact && mode != kModeFallback) {
+            const int idx = atomicAdd(&P.header->n_coords, 1);
+            if (idx < P.coords_capacity) s_coords_idx = idx;
+            else { mode = kModeFallback; reason = 6; }
+        }
         out->py0 = ys0; out->rows = rows; out->xb0 = xb0; out->row_bytes = row_bytes; out->pitch = pitch;
         out->mode_slot = mode | (view.slot << 8) | (wbox << 16);
-        out->pad[0] = 0; out->pad[1] = 0;
+        out->pad[0] = mode == kModeFallback ? reason : large ? -1 : 0; out->pad[1] = s_coords_idx + 1;
         if (mode == kModeFallback) {
             const int idx = atomicAdd(&P.header->n_fallback, 1);
             P.fallback[idx] = make_int2(v, tile);
+        }
+    }
+    __syncthreads();
+    if (exact && s_coords_idx >= 0) {
+        // the map itself, in the units and the unwrapping of the polynomial's values (1/32 px, continuous across the seam)
+        double2* cm = P.coords + (long long)s_coords_idx * (kTile * kTile);
+        const double ref = fx[0], period = P.erp.su;
+        for (int px = tid; px < kTile * kTile; px += 64) {
+            double ex, ey;
+            project_pixel<PROJ>(view, P.erp, P.lens, (double)(i0 + (px & (kTile - 1))), (double)(j0 + px / kTile), ex, ey);
+            double d = ex - ref;
+            d -= period * rint(d / period);
+            cm[px] = make_double2((ref + d) * 32.0, ey * 32.0);
         }
     }
 }
@@ -295,14 +361,15 @@ __global__ void __launch_bounds__(64) plan_kernel(const __grid_constant__ PlanPa
 }
 
 // Sort key of every (view, tile) for the remap kernel's walk: source slot, then the centre row of the patch;
-// fallback tiles (not staged) get INT_MAX and drop off the end of the list.
+// fallback tiles (not staged) get INT_MAX and drop off the end of the list, tiles of the large-patch pass INT_MAX - 1.
 __global__ void __launch_bounds__(256) order_key_kernel(const TilePlan* plans, int n, int* keys) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const TilePlan& p = plans[i];
     const int mode = p.mode_slot & 0xff, slot = (p.mode_slot >> 8) & 0xff;
     const bool staged = mode == kModeFast || mode == kModeFastRows || mode == kModeFastSeam;
-    keys[i] = mode == kModeFallback ? INT_MAX : (slot << 24) + (staged ? max(0, min(p.py0 + p.rows / 2, (1 << 24) - 1)) : 0);
+    keys[i] = mode == kModeFallback ? INT_MAX : p.pad[0] == -1 ? INT_MAX - 1
+            : (slot << 24) + (staged ? max(0, min(p.py0 + p.rows / 2, (1 << 24) - 1)) : 0);
 }
 
 // ---- bulk-async copy / mbarrier wrappers (PTX) ------------------------------------------------
@@ -449,6 +516,7 @@ struct TiledParams {
     const TilePlan* plans;  // whole plan (all views)
     const int2* order;      // (view, tile) of the staged tiles sorted by source row: the order the items are walked in
     int n_order;            // entries of `order` (tiles that are not on the fallback list)
+    const double2* coords;  // pool of per-pixel maps (tiles with TilePlan::pad[1] > 0)
     int l2_policy;          // patch loads: 0 evict_last, 1 evict_normal, 2 evict_first (R360_L2_POLICY, experiments)
 };
 
@@ -939,7 +1007,8 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
         const int nf = si->nf;
         const uint32_t fstride = si->fstride;
         const TilePlan* plan = &planbuf[slot];
-        if (mode != kModeFill) {
+        const int cmap = plan->pad[1];           // > 0: the tile has a per-pixel map instead of a polynomial
+        if (mode != kModeFill && cmap == 0) {
             // the 12 residual coefficients of this lane's row, spread over the 8 lanes that share the row
             const float* K = plan->rx + koff0;
             float a = K[30];
@@ -957,7 +1026,7 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
         __syncwarp();
         if constexpr (kFastU8) {
             // lane-per-column tiles: whole tile inside the image, vector stores possible
-            if (mode != kModeFill && mode != kModeFastSeam && P.channels == 3 && si->full_tile && P.bulk_store_ok) {
+            if (mode != kModeFill && mode != kModeFastSeam && cmap == 0 && P.channels == 3 && si->full_tile && P.bulk_store_ok) {
                 const int m = lane & 3;
                 unsigned char* out_word = P.dst.data + si->dst_tile + (long long)(warp * 4) * P.dst.pitch + ((lane >> 2) * 3 + m) * 4;
                 if constexpr (INTERP == kLinear) {
@@ -981,7 +1050,7 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
         }
         if constexpr (kFastU16) {
             // lane-per-column tiles of 16-bit RGB sources (4-byte aligned destination rows)
-            if (mode != kModeFill && mode != kModeFastSeam && P.channels == 3 && si->full_tile && (P.dst.pitch & 3) == 0 &&
+            if (mode != kModeFill && mode != kModeFastSeam && cmap == 0 && P.channels == 3 && si->full_tile && (P.dst.pitch & 3) == 0 &&
                 (P.dst.image_stride & 3) == 0) {
                 unsigned char* out_row = P.dst.data + si->dst_tile + (long long)(warp * 4) * P.dst.pitch;
                 if (FR > 1 && nf == FR)
@@ -1014,20 +1083,29 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
             const double period32 = 32.0 * P.src.width;
             float sxf[4], syf[4];
             int woff[4];
+            // a tile without a polynomial reads its four (32 x, 32 y) pairs from the coordinate pool instead
+            const double2* cm = cmap > 0 ? P.coords + ((long long)(cmap - 1) * (kTile * kTile) + jl * kTile + il0) : nullptr;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float s = fmaf((float)q, ds, s0);
-                float dx, dy;
-                residual_xy(c0, c1, c2, s, dx, dy);
-                double sx = ax_q + (double)dx;
+                double sx, sy;
+                if (cm != nullptr) {
+                    const double2 c = __ldg(cm + q);
+                    sx = c.x; sy = c.y;
+                } else {
+                    const float s = fmaf((float)q, ds, s0);
+                    float dx, dy;
+                    residual_xy(c0, c1, c2, s, dx, dy);
+                    sx = ax_q + (double)dx;
+                    sy = ay_q + (double)dy;
+                    ax_q += axi; ay_q += ayi;
+                }
                 woff[q] = 0;
                 if (seam) {
                     if (sx > period32 - 16.0) { sx -= period32; woff[q] = row_total; }
                     else if (sx <= -16.0) { sx += period32; woff[q] = -row_total; }
                 }
                 sxf[q] = __double2float_rn(sx);
-                syf[q] = __double2float_rn(ay_q + (double)dy);
-                ax_q += axi; ay_q += ayi;
+                syf[q] = __double2float_rn(sy);
             }
             bool done = false;
             if constexpr (kFastU8) {
@@ -1202,6 +1280,7 @@ struct TiledCoordParams {
     int out_w, out_h, tiles_x, tiles_y;
     double period32;        // 32 * source width (seam tiles wrap their x coordinate)
     const TilePlan* plans;
+    const double2* coords;
     float* x32; float* y32; double* x64; double* y64; unsigned char* valid;
 };
 
@@ -1215,6 +1294,7 @@ __global__ void __launch_bounds__(256) coords_tiled_kernel(const __grid_constant
     __syncthreads();
     const int mode = plan.mode_slot & 0xff;
     if (mode != kModeFast && mode != kModeFastRows && mode != kModeFastSeam) return;
+    const double2* cm = plan.pad[1] > 0 ? P.coords + (long long)(plan.pad[1] - 1) * (kTile * kTile) : nullptr;
     for (int task = tid; task < kTile * 12; task += 256) {
         const int row = task / 12, c = task % 12;
         const float* K = (c < 6 ? plan.rx : plan.ry) + (c < 6 ? c : c - 6);
@@ -1236,7 +1316,8 @@ __global__ void __launch_bounds__(256) coords_tiled_kernel(const __grid_constant
 #pragma unroll
         for (int kk = 4; kk >= 0; --kk) { dx = fmaf(dx, s, rc[kk]); dy = fmaf(dy, s, rc[6 + kk]); }
         double sx = fma(plan.ax[1], (double)(il0 + q), bx) + (double)dx;
-        const double sy = fma(plan.ay[1], (double)(il0 + q), by) + (double)dy;
+        double sy = fma(plan.ay[1], (double)(il0 + q), by) + (double)dy;
+        if (cm != nullptr) { const double2 c = cm[jl * kTile + il0 + q]; sx = c.x; sy = c.y; }
         if (mode == kModeFastSeam) {
             if (sx > P.period32 - 16.0) sx -= P.period32;
             else if (sx <= -16.0) sx += P.period32;
@@ -1249,37 +1330,53 @@ __global__ void __launch_bounds__(256) coords_tiled_kernel(const __grid_constant
     }
 }
 
-// ---- fallback tiles: direct float64 path, one block per listed (view, tile) and frame -------------
+// ---- fallback tiles: direct float64 path ---------------------------------------------------------
+//
+// One block per four rows of a listed (view, tile) and per run of `frames_per_block` frames; a warp owns one
+// tile row at a time (lane = column), so the gathers of neighbouring lanes share lines and the 32 results of a row
+// leave as one contiguous piece.  The kernel is latency-bound -- a float64 projection (~6k cycles of dependent
+// arithmetic) and then taps gathered from L2 -- so a thread projects its pixel ONCE and samples it from four frames
+// of the batch at a time: the loads of the four frames are independent and overlap.  Measured on B200, 8K bicubic,
+// 508 fallback tiles x 8 frames: 340 us with one frame per thread and a projection per frame, see profiles/README.md.
 
 struct FallbackParams {
     LaunchParams lp;               // lp.views is unused: views come from the device array
     const ViewDev* views;          // all views of the plan
     const int2* list;              // (view, tile)
     int tiles_x;
-    float* dbg_x32; float* dbg_y32; double* dbg_x64; double* dbg_y64; unsigned char* dbg_valid;
+    int n_groups, frames_per_block;
 };
 
+constexpr int kFallbackThreads = 128;
+constexpr int kFallbackRows = 4;                       // tile rows per block: one per warp
+constexpr int kFallbackFrames = 4;                     // frames sampled together
+
 template <int PROJ, int INTERP, typename TIn, typename TOut>
-__global__ void __launch_bounds__(256) remap_fallback_kernel(const __grid_constant__ FallbackParams F) {
+__global__ void __launch_bounds__(kFallbackThreads) remap_fallback_kernel(const __grid_constant__ FallbackParams F) {
     const LaunchParams& p = F.lp;
-    const int2 entry = F.list[blockIdx.x];
-    const int v = entry.x, tile = entry.y, g = blockIdx.y;
-    const int i0 = (tile % F.tiles_x) * kTile, j0 = (tile / F.tiles_x) * kTile;
+    constexpr int kParts = kTile / kFallbackRows;
+    const int2 entry = F.list[blockIdx.x / kParts];
+    const int part = blockIdx.x % kParts;
+    const int v = entry.x, tile = entry.y;
+    const int g_first = blockIdx.y * F.frames_per_block, g_end = min(g_first + F.frames_per_block, F.n_groups);
+    const int i0 = (tile % F.tiles_x) * kTile, j0 = (tile / F.tiles_x) * kTile + part * kFallbackRows;
     const ViewDev view = F.views[v];
-    const int jl = threadIdx.x >> 3, il0 = (threadIdx.x & 7) * 4;
+    const int i = i0 + (threadIdx.x & 31);
+    if (i >= p.dst.width) return;
 #pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-        const int i = i0 + il0 + q, j = j0 + jl;
-        if (i >= p.dst.width || j >= p.dst.height) continue;
-        if (F.dbg_x32) {
-            double x, y;
-            const bool ok = project_pixel<PROJ>(view, p.erp, p.lens, (double)i, (double)j, x, y);
-            const long long o = ((long long)v * p.dst.height + j) * p.dst.width + i;
-            F.dbg_x32[o] = (float)x; F.dbg_y32[o] = (float)y; F.dbg_x64[o] = x; F.dbg_y64[o] = y;
-            if (F.dbg_valid) F.dbg_valid[o] = ok;
-        } else {
-            direct_pixel<PROJ, INTERP, TIn, TOut>(p, view, g, v, i, j);   // lp.view_base is 0 here
-        }
+    for (int jl = threadIdx.x >> 5; jl < kFallbackRows; jl += kFallbackThreads / 32) {
+        const int j = j0 + jl;
+        if (j >= p.dst.height) break;
+        double x, y;
+        const bool ok = project_pixel<PROJ>(view, p.erp, p.lens, (double)i, (double)j, x, y);
+        const float xf = (float)x, yf = (float)y;
+        int g = g_first;
+#pragma unroll 1
+        for (; g + kFallbackFrames <= g_end; g += kFallbackFrames)
+            direct_sample<PROJ, INTERP, TIn, TOut, kFallbackFrames>(p, view, g, v, i, j, xf, yf, ok);   // lp.view_base is 0 here
+#pragma unroll 1
+        for (; g < g_end; ++g)
+            direct_sample<PROJ, INTERP, TIn, TOut, 1>(p, view, g, v, i, j, xf, yf, ok);
     }
 }
 

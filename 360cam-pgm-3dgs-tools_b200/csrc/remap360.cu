@@ -403,7 +403,12 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kMaxRingBytes = 200 * 1024;       // shared-memory ring of one block
 
-struct WorkspaceLayout { size_t header, views, plans, fallback, order, total; };
+struct WorkspaceLayout { size_t header, views, plans, fallback, order, coords, total; int coords_capacity; };
+
+// Per-pixel maps for the tiles no polynomial follows (pole neighbourhoods): room for one tile in sixteen, which covers
+// a view set made of pole views only (4.6 % of a pitch-90 view's tiles at 8K); tiles beyond the pool stay on the
+// fallback list.
+int coords_pool_tiles(size_t tiles_total) { return (int)std::min<size_t>(tiles_total / 16 + 32, 1u << 20); }
 
 WorkspaceLayout workspace_layout(int n_views, int out_w, int out_h) {
     const size_t tiles = (size_t)((out_w + kTile - 1) / kTile) * ((out_h + kTile - 1) / kTile);
@@ -413,7 +418,9 @@ WorkspaceLayout workspace_layout(int n_views, int out_w, int out_h) {
     w.plans = w.views + align_up(sizeof(ViewDev) * n_views, 256);
     w.fallback = w.plans + align_up(sizeof(TilePlan) * n_views * tiles, 256);
     w.order = w.fallback + align_up(sizeof(int2) * n_views * tiles, 256);      // also scratch for the sort keys
-    w.total = w.order + align_up(sizeof(int2) * n_views * tiles, 256);
+    w.coords = w.order + align_up(sizeof(int2) * n_views * tiles, 256);
+    w.coords_capacity = coords_pool_tiles((size_t)n_views * tiles);
+    w.total = w.coords + (size_t)w.coords_capacity * kCoordTileBytes;
     return w;
 }
 
@@ -428,14 +435,19 @@ struct r360_plan {
     int frames_pref, teams_multi_pref, ctas_multi_pref;     // launch shape for batches (choose_shape)
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
-    PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback; int2* d_order;
+    PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback; int2* d_order; double2* d_coords;
+    int coords_capacity, n_coords;                  // per-pixel map pool: size, maps in use
     int n_order;                                    // staged / fill tiles, in the order the remap kernel walks them
+    int n_large, patch_budget_large;                // tiles of the large-patch pass (they follow in d_order), its budget
     // tensor-TMA descriptors depend on the source base pointer and batch size: small cache
     bool tensor_ok;
     int box_family;
     mutable std::mutex tm_mutex;
     struct TmEntry { const void* data; int count; int64_t stride; TensorMaps maps; };
     mutable std::vector<TmEntry> tm_cache;
+    // The fallback tiles run beside the tiled kernel on this stream (created with the plan, non-blocking).
+    cudaStream_t side_stream = nullptr;
+    ~r360_plan() { if (side_stream) cudaStreamDestroy(side_stream); }
 };
 
 namespace {
@@ -560,6 +572,11 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         pl->ctas_multi_pref = cubic_u8 ? 1 : want;
         pl->patch_budget = pl->ring_bytes - (kMaxFramesPerItem - 1) * pl->out_stage_bytes;
         if (pl->patch_budget < 8192) pl->patch_budget = 8192;
+        // Tiles whose patch is larger than that (panorama tiles a few degrees from a pole span hundreds of columns)
+        // are walked in a second, short launch of the one-frame kernel with one block per SM, whose ring is the
+        // largest the SM can give; only what exceeds even that goes to the fallback kernel.
+        pl->patch_budget_large = std::min((smem_per_sm - 1024 - fixed) & ~127, kMaxRingBytes);
+        if (pl->patch_budget_large < pl->patch_budget || env_int("R360_LARGE_PATCH_PASS", 1) == 0) pl->patch_budget_large = pl->patch_budget;
     }
     // the data pointers are not known yet: assume 16-byte aligned bases (checked at remap time)
     pl->bulk_load_ok = src->pitch_bytes % 16 == 0 && src->image_stride_bytes % 16 == 0 &&
@@ -576,6 +593,8 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     pl->d_plans = reinterpret_cast<TilePlan*>(pl->ws + wl.plans);
     pl->d_fallback = reinterpret_cast<int2*>(pl->ws + wl.fallback);
     pl->d_order = reinterpret_cast<int2*>(pl->ws + wl.order);
+    pl->d_coords = reinterpret_cast<double2*>(pl->ws + wl.coords);
+    pl->coords_capacity = env_int("R360_COORD_TILES", 1) != 0 ? wl.coords_capacity : 0;   // 0: experiments without the pool
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     auto fail = [&](cudaError_t e, const char* what) { delete pl; return cuda_fail(e, what); };
@@ -587,13 +606,14 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     std::memset(&P, 0, sizeof(P));
     P.proj = proj; P.out_w = dst->width; P.out_h = dst->height; P.tiles_x = pl->tiles_x; P.tiles_y = pl->tiles_y;
     P.n_views = n_views; P.src_w = src->width; P.src_h = src->height; P.px_bytes = src->channels * in_es;
-    P.patch_budget = pl->patch_budget; P.bulk_load_ok = pl->bulk_load_ok; P.tensor_ok = pl->tensor_ok;
+    P.patch_budget = pl->patch_budget; P.patch_budget_large = pl->patch_budget_large; P.bulk_load_ok = pl->bulk_load_ok; P.tensor_ok = pl->tensor_ok;
     P.fill_invalid = pl->pr.lp.fill_invalid;
     P.interp = pl->pr.interp;
     P.box_family = pl->box_family;
     P.erp = pl->pr.lp.erp;
     std::memcpy(P.lens, pl->pr.lp.lens, sizeof(P.lens));
     P.views = pl->d_views; P.plans = pl->d_plans; P.header = pl->d_header; P.fallback = pl->d_fallback;
+    P.coords = pl->coords_capacity > 0 ? pl->d_coords : nullptr; P.coords_capacity = pl->coords_capacity;
     for (int v0 = 0; v0 < n_views; v0 += 65535) {
         PlanParams Q = P;
         const int nv = n_views - v0 < 65535 ? n_views - v0 : 65535;
@@ -608,6 +628,11 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     if ((e = cudaMemcpyAsync(&h, pl->d_header, sizeof(h), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "cudaMemcpyAsync(header)");
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
     pl->n_fallback = h.n_fallback;
+    pl->n_coords = std::min(h.n_coords, pl->coords_capacity);
+    if (pl->n_fallback > 0 && cudaStreamCreateWithFlags(&pl->side_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        pl->side_stream = nullptr;                                     // the fallback kernel then follows in `s`
+        (void)cudaGetLastError();
+    }
     // ---- walk order of the remap kernel: (view, tile) sorted by source slot and source row ------------------
     {
         const int n = n_views * pl->n_tiles;
@@ -627,13 +652,17 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         const int band = std::max(1, env_int("R360_ORDER_BAND", 128));
         if (band > 1)
             for (int i = 0; i < n; ++i)
-                if (keys[i] != INT_MAX) keys[i] = (keys[i] & ~0xFFFFFF) | ((keys[i] & 0xFFFFFF) / band);
+                if (keys[i] < INT_MAX - 1) keys[i] = (keys[i] & ~0xFFFFFF) | ((keys[i] & 0xFFFFFF) / band);
         std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return keys[a] < keys[b]; });
         std::vector<int2> order;
         order.reserve(n);
-        for (int i = 0; i < n && keys[idx[i]] != INT_MAX; ++i) order.push_back(make_int2(idx[i] / pl->n_tiles, idx[i] % pl->n_tiles));
-        pl->n_order = (int)order.size();
-        if (pl->n_order > 0 &&
+        pl->n_order = 0;
+        for (int i = 0; i < n && keys[idx[i]] != INT_MAX; ++i) {
+            order.push_back(make_int2(idx[i] / pl->n_tiles, idx[i] % pl->n_tiles));
+            if (keys[idx[i]] < INT_MAX - 1) ++pl->n_order;
+        }
+        pl->n_large = (int)order.size() - pl->n_order;               // they sort behind the main walk
+        if (!order.empty() &&
             (e = cudaMemcpyAsync(pl->d_order, order.data(), sizeof(int2) * order.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess)
             return fail(e, "cudaMemcpyAsync(order)");
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
@@ -717,7 +746,8 @@ struct TiledLauncher {
     template <int PROJ, int INTERP, typename TIn, typename TOut> int run() {
         const LaunchParams& lp = pl->pr.lp;
         const int n_groups = src->count / pl->pr.n_lenses;
-        const TiledShape shape = choose_shape(pl, n_groups);
+        const TiledShape main_shape = choose_shape(pl, n_groups);
+        const TiledShape& shape = main_shape;
         TiledParams T;
         std::memset(&T, 0, sizeof(T));
         T.src = {static_cast<unsigned char*>(src->data), src->pitch_bytes, src->image_stride_bytes, src->width, src->height};
@@ -730,13 +760,48 @@ struct TiledLauncher {
         T.dst_fstride = (long long)pl->pr.n_views * T.dst.image_stride;
         T.plans = pl->d_plans;
         T.order = pl->d_order; T.n_order = pl->n_order;
+        T.coords = pl->d_coords;
         T.l2_policy = env_int("R360_L2_POLICY", 0);
 
+        // Experiment (R360_FALLBACK_OVERLAP=1): the fallback tiles beside the tiled kernel instead of after it -- a side
+        // stream forked off `s` here and joined after both launches (capturable; the events are made per call because
+        // one plan may be launched from several host threads at once).  Off by default: next to the persistent blocks
+        // only one 128-thread fallback block fits per SM, and the latency-bound fallback kernel then takes longer than
+        // the tiled kernel it was meant to hide behind (B200, 19 views incl. poles: 121 Gpix/s serial, 72 overlapped).
+        struct EventPair {
+            cudaEvent_t fork = nullptr, join = nullptr;
+            ~EventPair() { if (fork) cudaEventDestroy(fork); if (join) cudaEventDestroy(join); }   // deferred by the runtime
+        } ev;
+        cudaStream_t fb_stream = s;
+        bool forked = false;
+        if (pl->n_fallback > 0 && pl->n_order + pl->n_large > 0 && pl->side_stream && env_int("R360_FALLBACK_OVERLAP", 0) != 0 &&
+            cudaEventCreateWithFlags(&ev.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ev.join, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventRecord(ev.fork, s) == cudaSuccess && cudaStreamWaitEvent(pl->side_stream, ev.fork, 0) == cudaSuccess) {
+            fb_stream = pl->side_stream;
+            forked = true;
+        }
+
+        // two passes over the same kernel: the main walk in the shape chosen above, then the tiles with large
+        // patches, one frame per item, one block per SM with the largest ring (their list follows the main one)
+        TiledShape large_shape = shape;
+        if (pl->n_large > 0) {
+            int dev = 0, smem_per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+            if (!shape_for(pl, 1, 1, 1, smem_per_sm, &large_shape) || large_shape.ring < pl->patch_budget_large) return R360_E_UNSUPPORTED;
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+        const TiledShape& shape = pass == 0 ? main_shape : large_shape;
+        const int n_items = pass == 0 ? pl->n_order : pl->n_large;
+        if (n_items == 0) continue;
+        T.order = pl->d_order + (pass == 0 ? 0 : pl->n_order); T.n_order = n_items;
+        T.ring_bytes = shape.ring; T.frames_per_item = shape.fr; T.multi_budget = shape.multi_budget;
         // work items are indexed with 32-bit ints inside the kernel: chunk the groups if needed
-        const long long per_group = std::max(1, pl->n_order);
+        const long long per_group = n_items;
         int max_groups = (int)std::max<long long>(1, (1LL << 30) / per_group);
         if (max_groups > shape.fr) max_groups -= max_groups % shape.fr;          // chunks hold whole frame blocks
-        for (int g0 = 0; g0 < n_groups && pl->n_order > 0; g0 += max_groups) {
+        for (int g0 = 0; g0 < n_groups; g0 += max_groups) {
             TiledParams Q = T;
             Q.n_groups = n_groups - g0 < max_groups ? n_groups - g0 : max_groups;
             Q.src.data += (long long)g0 * pl->pr.n_lenses * Q.src.image_stride;
@@ -772,6 +837,7 @@ struct TiledLauncher {
             else rc = launch<INTERP, TIn, TOut, 1, 1>(Q, maps, shape, grid);
             if (rc != R360_OK) return rc;
         }
+        }
 
         if (pl->n_fallback > 0) {
             FallbackParams F;
@@ -779,14 +845,22 @@ struct TiledLauncher {
             F.lp = lp;
             F.lp.src = T.src; F.lp.dst = T.dst; F.lp.view_base = 0; F.lp.n_views = pl->pr.n_views;
             F.views = pl->d_views; F.list = pl->d_fallback; F.tiles_x = pl->tiles_x;
-            for (int g0 = 0; g0 < n_groups; g0 += 65535) {
-                FallbackParams G = F;
-                const int ng = n_groups - g0 < 65535 ? n_groups - g0 : 65535;
-                G.lp.src.data += (long long)g0 * pl->pr.n_lenses * G.lp.src.image_stride;
-                G.lp.dst.data += (long long)g0 * pl->pr.n_views * G.lp.dst.image_stride;
-                remap_fallback_kernel<PROJ, INTERP, TIn, TOut><<<dim3(pl->n_fallback, ng), 256, 0, s>>>(G);
-                g_launches.fetch_add(1, std::memory_order_relaxed);
-                R360_CUDA(cudaGetLastError());
+            // frames per block: the projection is shared by the frames of a block and four frames are sampled
+            // together, so whole multiples of four while the grid keeps a few waves of blocks
+            constexpr int kParts = kTile / kFallbackRows;
+            const long long blocks_wanted = 16LL * pl->sm_count;
+            long long fpb = (long long)pl->n_fallback * kParts * n_groups / blocks_wanted;
+            fpb = std::max<long long>(kFallbackFrames, fpb / kFallbackFrames * kFallbackFrames);
+            fpb = std::min<long long>(fpb, n_groups);
+            fpb = std::max<long long>(fpb, (n_groups + 65534) / 65535);
+            F.n_groups = n_groups; F.frames_per_block = (int)fpb;
+            remap_fallback_kernel<PROJ, INTERP, TIn, TOut><<<dim3(pl->n_fallback * kParts, (unsigned)((n_groups + fpb - 1) / fpb)),
+                                                             kFallbackThreads, 0, fb_stream>>>(F);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            R360_CUDA(cudaGetLastError());
+            if (forked) {
+                R360_CUDA(cudaEventRecord(ev.join, fb_stream));
+                R360_CUDA(cudaStreamWaitEvent(s, ev.join, 0));
             }
         }
         return R360_OK;
@@ -1048,6 +1122,13 @@ int r360_plan_info(const r360_plan* plan, int32_t* tiles_per_view, int32_t* n_fa
     return R360_OK;
 }
 
+int r360_plan_info_maps(const r360_plan* plan, int32_t* n_map_tiles, int32_t* map_pool_tiles) {
+    if (!plan) return R360_E_INVALID_ARG;
+    if (n_map_tiles) *n_map_tiles = plan->n_coords;
+    if (map_pool_tiles) *map_pool_tiles = plan->coords_capacity;
+    return R360_OK;
+}
+
 int r360_remap_planned(const r360_plan* plan, const r360_images* src, const r360_images* dst, void* stream) {
     if (!plan) return R360_E_INVALID_ARG;
     int rc;
@@ -1086,6 +1167,7 @@ int r360_plan_coords(const r360_plan* plan, float* map_x32, float* map_y32, doub
     T.out_w = p.out_w; T.out_h = p.out_h; T.tiles_x = plan->tiles_x; T.tiles_y = plan->tiles_y;
     T.period32 = 32.0 * plan->src_layout.width;
     T.plans = plan->d_plans;
+    T.coords = plan->d_coords;
     T.x32 = map_x32; T.y32 = map_y32; T.x64 = map_x64; T.y64 = map_y64; T.valid = valid;
     coords_tiled_kernel<<<dim3(plan->n_tiles, n_views), 256, 0, s>>>(T);
     g_launches.fetch_add(1, std::memory_order_relaxed);

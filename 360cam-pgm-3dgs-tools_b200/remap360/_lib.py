@@ -70,7 +70,7 @@ _lib = None
 EXPORTS = ("r360_abi_version", "r360_error_string", "r360_last_cuda_error", "r360_default_options",
            "r360_device_info", "r360_remap_erp", "r360_remap_fisheye", "r360_coords", "r360_launch_count",
            "r360_plan_workspace_bytes", "r360_plan_create_erp", "r360_plan_create_fisheye", "r360_plan_info",
-           "r360_remap_planned", "r360_plan_coords", "r360_plan_destroy",
+           "r360_plan_info_maps", "r360_remap_planned", "r360_plan_coords", "r360_plan_destroy",
            "r360_remap_undistort", "r360_coords_undistort", "r360_plan_create_undistort", "r360_apply_lut",
            "r360_convert_color")
 
@@ -117,6 +117,7 @@ def load() -> ctypes.CDLL:
     lib.r360_apply_lut.argtypes = [POINTER(Images), POINTER(Images), POINTER(Lut3D), c_int32, c_int32, c_void_p]
     lib.r360_convert_color.argtypes = [POINTER(Images), POINTER(Images), POINTER(ColorConvert), c_int32, c_void_p]
     lib.r360_plan_info.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32)]
+    lib.r360_plan_info_maps.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32)]
     lib.r360_remap_planned.argtypes = [c_void_p, POINTER(Images), POINTER(Images), c_void_p]
     lib.r360_plan_coords.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.r360_plan_destroy.argtypes = [c_void_p]

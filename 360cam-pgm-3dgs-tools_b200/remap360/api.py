@@ -191,9 +191,11 @@ def _as_image_batch(t: torch.Tensor) -> torch.Tensor:
 class Plan:
     """A built tile plan (r360_plan) plus the device workspace it lives in."""
 
-    def __init__(self, handle: int, workspace: torch.Tensor, tiles_per_view: int, n_fallback: int, n_views: int):
+    def __init__(self, handle: int, workspace: torch.Tensor, tiles_per_view: int, n_fallback: int, n_views: int,
+                 n_map_tiles: int = 0):
         self.handle, self.workspace = handle, workspace
         self.tiles_per_view, self.n_fallback, self.n_views = tiles_per_view, n_fallback, n_views
+        self.n_map_tiles = n_map_tiles         # tiles that carry a per-pixel map (pole neighbourhoods)
 
     @property
     def fallback_fraction(self) -> float:
@@ -257,7 +259,9 @@ def get_plan(src: Images, dst: Images, views: Sequence[PerspectiveView], opt: Op
     _lib.check(rc)
     tiles, nfb = ctypes.c_int32(), ctypes.c_int32()
     _lib.check(lib.r360_plan_info(handle, ctypes.byref(tiles), ctypes.byref(nfb)))
-    plan = Plan(handle.value, workspace, tiles.value, nfb.value, len(views))
+    nmap = ctypes.c_int32()
+    _lib.check(lib.r360_plan_info_maps(handle, ctypes.byref(nmap), None))
+    plan = Plan(handle.value, workspace, tiles.value, nfb.value, len(views), nmap.value)
     with _PLAN_LOCK:
         # two threads may have built the same plan at once: both are valid, the later one stays cached
         _PLAN_CACHE[key] = plan

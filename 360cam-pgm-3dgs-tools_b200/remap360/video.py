@@ -278,9 +278,14 @@ def _run_bucket(source, jobs, n_in, in_fps, stop_event, shard, device, pool, mjp
                                      device=device)
         source_frames = (_MjpegGpuFrames(source, wanted, device) if mjpeg_gpu else _OpenCvFrames(source, wanted))
 
+        from .executor import _stage
+
         def frames() -> Iterator:
-            for fr in source_frames:
-                if stop_event is not None and stop_event.is_set():
+            it = iter(source_frames)
+            while True:
+                with _stage("video_decode_wait"):
+                    fr = next(it, None)
+                if fr is None or (stop_event is not None and stop_event.is_set()):
                     return
                 yield fr
 
@@ -295,18 +300,21 @@ def _run_bucket(source, jobs, n_in, in_fps, stop_event, shard, device, pool, mjp
                 local = pinned_view.copy()
             finally:
                 copied.release()
-            _write_image(path, local, quality, pix_fmt)
+            with _stage("video_write"):
+                _write_image(path, local, quality, pix_fmt)
 
         for n, out in enumerate(remapper.run(frames())):
             views_host = out.numpy()
             for col, job in enumerate(jobs):
                 path = str(job.output) % (lo + n) if "%" in str(job.output) else str(job.output)
                 futures.append(pool.submit(write_view, pathlib.Path(path), views_host[col], job.jpeg_quality, job.pix_fmt))
-            for _ in jobs:
-                copied.acquire()
+            with _stage("video_copy_wait"):
+                for _ in jobs:
+                    copied.acquire()
             produced += 1
-            while len(futures) > 96:                        # bound the views waiting for a writer
-                futures.popleft().result()
+            with _stage("video_writer_backpressure"):
+                while len(futures) > 96:                    # bound the views waiting for a writer
+                    futures.popleft().result()
         for f in futures:
             f.result()
     if stop_event is not None and stop_event.is_set():

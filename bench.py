@@ -49,12 +49,22 @@ FOOTPRINT_PX = {
     ("dualfisheye_sfm10", 3840, "linear"): 20_721_452, ("dualfisheye_sfm10", 3840, "cubic"): 20_750_796,
 }
 
-# DRAM traffic of ONE launch of the tiled kernel (dram__bytes_read.sum + dram__bytes_write.sum of an `ncu --set
-# full` capture summarised in profiles/), valid only for the kernel sources it was measured with: the entry carries
-# the digest of csrc/ at capture time and is reported as null (with the reason) when the sources have changed since.
-NCU_TRAFFIC = {
-    # (workload, interp, frames): (bytes, csrc digest, profile)
-}
+# DRAM traffic of ONE launch of the tiled kernel (dram__bytes_read.sum + dram__bytes_write.sum, ncu, per workload of
+# workload_table at the default batch), valid only for the kernel sources it was measured with:
+# tools/traffic_capture.py writes profiles/r02_dram_traffic.json with the digest of csrc/ at capture time, and an
+# entry is reported as null (with the reason) when the sources have changed since.
+TRAFFIC_FILE = ROOT / "profiles" / "r02_dram_traffic.json"
+
+
+def ncu_traffic():
+    """{(workload, interp, frames): (bytes, csrc digest, profile)} from TRAFFIC_FILE; {} when it is absent."""
+    try:
+        rec = json.loads(TRAFFIC_FILE.read_text())
+    except (OSError, ValueError):
+        return {}
+    return {(name, e["interp"], int(e["frames"])): (int(e["dram_bytes_read"]) + int(e["dram_bytes_write"]), rec["csrc_digest"],
+                                                     "profiles/" + TRAFFIC_FILE.name)
+            for name, e in rec.get("workloads", {}).items() if "error" not in e}
 
 
 def csrc_digest():
@@ -410,6 +420,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-compressed", action="store_true", help="skip the JPEG-in / JPEG-out end-to-end leg")
     ap.add_argument("--no-variants", action="store_true", help="time the headline workload only")
     ap.add_argument("--workload", default="cfg2", help="headline workload (see workload_table)")
     ns = ap.parse_args()
@@ -563,7 +574,7 @@ def main():
             bytes_per_launch = per_frame * w["frames"]
             kernel_ms = statistics.median(per_step_ms)
             achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-            entry = NCU_TRAFFIC.get((name, w["interp"], w["frames"]))
+            entry = ncu_traffic().get((name, w["interp"], w["frames"]))
             traffic, traffic_note = None, "no ncu capture recorded for this workload"
             if entry is not None:
                 traffic, traffic_note = (entry[0], entry[2]) if entry[1] == digest else (None, "stale: %s was captured with csrc digest %s, the sources are now %s" % (entry[2], entry[1], digest))
@@ -663,6 +674,17 @@ def main():
                "api": "remap360.stream.StreamingRemapper (pinned ring of %d slots x %d frames, H2D / kernel / D2H on three streams)" % (
                    remapper.depth, remapper.batch)}
 
+    # ------------------------------------------------------------------ end to end with compressed frames
+    # JPEG bytes in host memory -> nvJPEG decode on the device -> the same remap -> nvJPEG encode of every view ->
+    # JPEG bytes in host memory (what the still-image runner does per panorama, minus the file system).  Fewer bytes
+    # cross the host link, but the codec (library code, lossy) now bounds the rate; reported beside the raw leg.
+    e2e_compressed = None
+    if e2e is not None and head["dtype"] == "u8" and not ns.no_compressed:
+        try:
+            e2e_compressed = compressed_leg(torch, remap360, dev, runner, head, world, barrier, dist)
+        except Exception as exc:
+            e2e_compressed = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not ns.no_cpu_baseline:
         cpu_baseline = cpu_baseline_block(head, views, ns.cpu_seconds)
@@ -680,7 +702,7 @@ def main():
                 "warmup": ns.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic", "config": config,
                 "views_per_s": value * 1e6 / (head["size"] * head["size"]), "frames_per_s": value * 1e6 / (n_views * head["size"] * head["size"]),
-                "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks.summary(), "e2e": e2e, "e2e_compressed": e2e_compressed, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "variants": variants, "csrc_digest": digest}
         if saved_stdout_fd is not None:
             sys.stdout.flush()
@@ -688,6 +710,63 @@ def main():
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def compressed_leg(torch, remap360, dev, runner, head, world, barrier, dist, panoramas=16, quality=95):
+    """JPEG panoramas -> JPEG views through remap360.codec (nvJPEG) and the remap, one host thread per codec."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    from remap360 import codec
+    W, H = head["src"]
+    size = head["size"]
+    # band-limited content plus a little noise: what a camera frame compresses like (noise alone does not compress)
+    lon = torch.linspace(0.0, 2.0 * torch.pi, W + 1, device=dev)[:-1]
+    lat = torch.linspace(-0.5 * torch.pi, 0.5 * torch.pi, H, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(977)
+    enc0 = codec.JpegCodec(dev)
+    blobs = []
+    for k in range(4):
+        img = torch.zeros((H, W, CHANNELS), dtype=torch.float32, device=dev)
+        for _ in range(6):
+            kx = torch.randint(1, 24, (CHANNELS,), device=dev, generator=gen).float()
+            ky = torch.randint(1, 24, (CHANNELS,), device=dev, generator=gen).float()
+            ph = torch.rand((2, CHANNELS), device=dev, generator=gen) * 2.0 * torch.pi
+            img += torch.sin(lon[None, :, None] * kx + ph[0]) * torch.cos(lat[:, None, None] * ky + ph[1])
+        img = (img / 12.0 + 0.5) * 255.0 + torch.randn((H, W, CHANNELS), device=dev, generator=gen) * 3.0
+        blobs.append(enc0.encode(img.clamp_(0.0, 255.0).round_().to(torch.uint8), 92))
+        del img
+    del enc0
+    threads = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+    tls = threading.local()
+
+    def one(n):
+        if getattr(tls, "codec", None) is None:
+            tls.codec, tls.stream = codec.JpegCodec(dev), torch.cuda.Stream(dev)
+        with torch.cuda.stream(tls.stream):
+            frame = tls.codec.decode(blobs[n % len(blobs)], stream=tls.stream)
+            views = remap360.remap_erp(frame[None], runner.pviews, (size, size), interp=head["interp"], stream=tls.stream)[0]
+            out = [tls.codec.encode(views[v], quality, stream=tls.stream) for v in range(views.shape[0])]
+        return sum(len(b) for b in out)
+
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(one, range(2 * threads)))                    # codecs, streams, plans
+        barrier()
+        t0 = time.perf_counter()
+        down = sum(pool.map(one, range(panoramas)))
+        torch.cuda.synchronize(dev)
+        barrier()
+        dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    up = sum(len(blobs[n % len(blobs)]) for n in range(panoramas))
+    pix = panoramas * len(runner.pviews) * size * size
+    return {"value": pix * world / dt / 1e6, "unit": "Mpix/s", "panoramas_per_s": panoramas * world / dt, "panoramas": panoramas,
+            "host_threads": threads, "h2d_bytes_per_step": up, "d2h_bytes_per_step": down, "ms_per_step": dt * 1e3,
+            "jpeg": "nvJPEG (library): decode of quality-92 4:4:4 frames, encode of every view at quality %d 4:4:4" % quality,
+            "note": "lossy leg: results are JPEG views, not the bit-checked product; the codec, not the remap or the link, bounds it"}
 
 
 def link_probe(torch, dev, barrier, mb=256, reps=4):

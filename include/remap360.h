@@ -278,8 +278,11 @@ int r360_coords_undistort(const r360_fisheye_calib* calib, int32_t n_lenses,
  * does the same inside each process).  A plan is this library's equivalent: per 32x32 output
  * tile, polynomial coordinates fitted in float64 plus the source patch to stage -- 384 bytes per
  * tile (368-byte record + fallback-list and walk-order entries) in a caller-provided device workspace, built on the device by r360_plan_create_*.
+ * Panorama tiles next to a pole, whose map no polynomial follows, carry an explicit 16 KB per-pixel map instead (a pool
+ * for one tile in sixteen follows the records: 1 KB per tile of workspace on average).
  * r360_remap_planned then runs the tiled fast kernels (bulk-async staging to shared memory),
- * falling back to the direct path tile by tile where the plan says so.  Results are the same as
+ * falling back to the direct path tile by tile where the plan says so (tiles that contain a pole, patches larger
+ * than shared memory).  Results are the same as
  * r360_remap_erp / r360_remap_fisheye up to 1/32-px bin flips from ~1e-5 px coordinate noise.
  *
  * A plan is tied to the source/destination LAYOUT (size, channels, dtype, pitches, 16-byte
@@ -309,6 +312,10 @@ int r360_plan_create_undistort(const r360_images* src_layout, const r360_images*
 
 /* Tiles per view and how many (view, tile) pairs take the direct path. */
 int r360_plan_info(const r360_plan* plan, int32_t* tiles_per_view, int32_t* n_fallback_tiles);
+
+/* How many tiles carry an explicit per-pixel map (panorama tiles next to a pole, where no polynomial follows the
+ * projection) and how many such maps the workspace has room for. */
+int r360_plan_info_maps(const r360_plan* plan, int32_t* n_map_tiles, int32_t* map_pool_tiles);
 
 /* Same contract as r360_remap_erp / r360_remap_fisheye for the layout the plan was made for;
  * R360_E_INVALID_ARG if src/dst do not match that layout. */

@@ -22,7 +22,10 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     n_video = int(sys.argv[2]) if len(sys.argv) > 2 else 24
     os.environ["R360_TIMING"] = "1"
-    with tempfile.TemporaryDirectory() as tmp:
+    # files in memory-backed storage when the box has it: the probe times the pipeline, not the container's overlay disk
+    # (R360_PROBE_DIR overrides)
+    scratch = os.environ.get("R360_PROBE_DIR") or ("/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None)
+    with tempfile.TemporaryDirectory(dir=scratch) as tmp:
         tmp = pathlib.Path(tmp)
         (tmp / "in").mkdir()
         yy, xx = np.mgrid[0:3840, 0:7680].astype(np.float32)
@@ -34,7 +37,8 @@ def main():
         sys.path.insert(0, str(ROOT / "360cam-pgm-3dgs-tools_b200"))
         from remap360 import executor, perspcut as pc
         files = sorted((tmp / "in").glob("*.jpg"))
-        for mode in ("gpu", "cpu"):
+        gpu_workers = tuple(int(t) for t in os.environ.get("R360_PROBE_WORKERS", "1,4,8,12,16").split(","))
+        for mode in (("gpu",) if os.environ.get("R360_PROBE_SKIP_CPU") else ("gpu", "cpu")):
             os.environ.pop("R360_CPU_CODEC", None)
             if mode == "cpu":
                 os.environ["R360_CPU_CODEC"] = "1"
@@ -45,14 +49,15 @@ def main():
             warm = pc.build_view_jobs(args, files[:1], out)
             list(executor.run_jobs(warm.jobs, pc.stop_event, workers=1))           # plan, codec, CUDA context
             res = pc.build_view_jobs(args, files[1:], out)
-            for workers in ((1, 4, 8, 12, 16) if mode == "gpu" else (4, 16)):
+            for workers in (gpu_workers if mode == "gpu" else (4, 16)):
                 list(executor.run_jobs(res.jobs, pc.stop_event, workers=workers))   # new threads build their codecs here
                 executor.STAGE_SECONDS.clear()
                 t0 = time.time()
                 done = list(executor.run_jobs(res.jobs, pc.stop_event, workers=workers))
                 dt = time.time() - t0
                 ok = sum(1 for _j, (rc, _e) in done if rc == 0)
-                print(json.dumps({"codec": mode, "jpeg_backend": os.environ.get("R360_JPEG_BACKEND", "gpu_hybrid"), "workers": workers,
+                print(json.dumps({"codec": mode, "scratch": scratch or "tmp", "jpeg_backend": os.environ.get("R360_JPEG_BACKEND", "gpu_hybrid"),
+                                  "huffman": os.environ.get("R360_JPEG_HUFFMAN", "optimised"), "workers": workers,
                                   "panoramas": len(files) - 1, "views_ok": ok,
                                   "seconds": round(dt, 3), "panoramas_per_s": round((len(files) - 1) / dt, 2),
                                   "views_per_s": round(ok / dt, 1),
@@ -60,7 +65,7 @@ def main():
         # ---- video branch: an 8K Motion-JPEG clip, 2 views per frame as PNG-free JPEG views
         clip = tmp / "clip.avi"
         wr = cv2.VideoWriter(str(clip), cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (7680, 3840))
-        if wr.isOpened():
+        if wr.isOpened() and n_video > 0:
             base = cv2.imread(str(files[0]))
             for k in range(n_video):
                 wr.write(np.roll(base, 64 * k, axis=1))
@@ -73,6 +78,7 @@ def main():
                 args.input_is_video, args.video_bit_depth = True, 8
                 res = pc.build_view_jobs(args, [clip], out)
                 for attempt in range(2):                       # the first pass pays for plans and codecs
+                    executor.STAGE_SECONDS.clear()
                     t0 = time.time()
                     done = list(executor.run_jobs(res.jobs, pc.stop_event, workers=1))
                     dt = time.time() - t0
@@ -80,7 +86,8 @@ def main():
                 n_files = len(list(out.glob("*.jpg")))
                 print(json.dumps({"video": "8K MJPG clip, %d frames -> 12 views" % n_video, "decoder": decoder, "jobs_ok": ok,
                                   "files": n_files, "seconds": round(dt, 3), "frames_per_s": round(n_video / dt, 2),
-                                  "views_per_s": round(n_files / dt, 1), "errors": sorted({e for _j, (rc, e) in done if rc})[:2]}), flush=True)
+                                  "views_per_s": round(n_files / dt, 1),
+                                  "stage_seconds": {k: round(v, 3) for k, v in executor.STAGE_SECONDS.items()}, "errors": sorted({e for _j, (rc, e) in done if rc})[:2]}), flush=True)
 
 
 if __name__ == "__main__":
