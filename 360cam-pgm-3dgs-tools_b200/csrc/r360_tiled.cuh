@@ -528,7 +528,8 @@ struct TiledParams {
 constexpr int kConsumerWarps = 8;                       // warps of a team (256 threads <-> 32 rows x 8 lanes)
 constexpr int kTeamThreads = kConsumerWarps * 32;
 constexpr int kMaxTeams = 2;
-constexpr int kSlots = 4;                               // slots in flight per block (a multiple of the team count)
+constexpr int kSlots = 4;                               // slots in flight per block (a multiple of the team count); eight
+                                                        // measured 1-7 % slower on every kernel (profiles/README.md)
 static_assert(kSlots % kMaxTeams == 0, "slot k belongs to team k mod teams");
 __host__ __device__ constexpr int tiled_threads(int teams) { return teams * kTeamThreads + 32; }
 // blocks per SM the registers are budgeted for: the 8-bit bicubic kernel shares the SM with its 32 KB weight

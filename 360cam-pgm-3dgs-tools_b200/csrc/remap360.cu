@@ -433,6 +433,7 @@ struct r360_plan {
     int tiles_x, tiles_y, n_tiles, n_fallback;
     int out_stage_bytes, patch_budget, ring_bytes, smem_bytes, ctas_per_sm, use_table, sm_count;
     int frames_pref, teams_multi_pref, ctas_multi_pref;     // launch shape for batches (choose_shape)
+    int multi_pct_pref;                                     // share of the ring one multi-frame item may take
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
     PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback; int2* d_order; double2* d_coords;
@@ -567,9 +568,12 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         const bool linear_u8 = pl->pr.in_dt == R360_U8 && pl->pr.interp == R360_LINEAR && dst->channels == 3;
         // (8-bit bilinear: four frames per item on one team, 264 against 256 Gpix/s with two; 16-bit patches are twice
         // the size and stay at two frames per item)
+        // (16-bit bicubic: two frames per item on two teams in one block per SM, 82.1 against 76.8 Gpix/s on two blocks)
+        const bool cubic_u16 = in_es == 2 && pl->pr.interp == R360_CUBIC && dst->channels == 3;
         pl->frames_pref = pl->use_table == 2 ? 1 : (cubic_u8 || linear_u8) ? 4 : 2;
-        pl->teams_multi_pref = cubic_u8 ? 2 : 1;
-        pl->ctas_multi_pref = cubic_u8 ? 1 : want;
+        pl->teams_multi_pref = (cubic_u8 || cubic_u16) ? 2 : 1;
+        pl->multi_pct_pref = linear_u8 ? 100 : 75;
+        pl->ctas_multi_pref = (cubic_u8 || cubic_u16) ? 1 : want;
         pl->patch_budget = pl->ring_bytes - (kMaxFramesPerItem - 1) * pl->out_stage_bytes;
         if (pl->patch_budget < 8192) pl->patch_budget = 8192;
         // Tiles whose patch is larger than that (panorama tiles a few degrees from a pole span hundreds of columns)
@@ -686,7 +690,8 @@ bool shape_for(const r360_plan* pl, int fr, int teams, int ctas, int smem_per_sm
     out->fr = fr; out->teams = teams; out->ctas = ctas; out->ring = ring; out->smem = fixed + ring;
     // an item takes all its frames at once when it leaves room for the next one to load behind it (measured on B200,
     // 8K -> 12 x 1600^2, two frames per item: 50 % of the ring 140.9 / 279.0 Gpix/s bicubic / bilinear, 75 % 143.1 / 280.1)
-    const int pct = std::min(100, std::max(10, env_int("R360_MULTI_PCT", 75)));
+    // (four-frame bilinear items: 285.9 Gpix/s at 75 %, 289.2 at 100 %)
+    const int pct = std::min(100, std::max(10, env_int("R360_MULTI_PCT", pl->multi_pct_pref)));
     out->multi_budget = (int)((long long)ring * pct / 100);
     return true;
 }
@@ -700,9 +705,10 @@ TiledShape choose_shape(const r360_plan* pl, int n_groups) {
     fr = env_int("R360_FRAMES", fr);
     if (fr != 1 && fr != 2 && fr != 4) fr = 1;
     if (fr > n_groups) fr = n_groups >= 2 ? 2 : 1;
-    // two teams exist for four-frame items only (the instantiations the library carries)
-    int teams = fr == 4 ? std::min(kMaxTeams, std::max(1, env_int("R360_TEAMS", pl->teams_multi_pref))) : 1;
-    int ctas = std::max(1, env_int("R360_TILED_CTAS_PER_SM", fr == 4 && teams == 2 ? pl->ctas_multi_pref : pl->ctas_per_sm));
+    // two teams exist for two- and four-frame items (the instantiations the library carries); the plan's preference
+    // applies to its preferred frame count
+    int teams = fr >= 2 ? std::min(kMaxTeams, std::max(1, env_int("R360_TEAMS", fr == pl->frames_pref ? pl->teams_multi_pref : 1))) : 1;
+    int ctas = std::max(1, env_int("R360_TILED_CTAS_PER_SM", teams == 2 ? (fr == pl->frames_pref ? pl->ctas_multi_pref : 1) : pl->ctas_per_sm));
     TiledShape s;
     for (;;) {
         if (shape_for(pl, fr, teams, ctas, smem_per_sm, &s)) return s;
@@ -833,6 +839,7 @@ struct TiledLauncher {
             int rc;
             if (shape.fr == 4 && shape.teams == 2) rc = launch<INTERP, TIn, TOut, 4, 2>(Q, maps, shape, grid);
             else if (shape.fr == 4) rc = launch<INTERP, TIn, TOut, 4, 1>(Q, maps, shape, grid);
+            else if (shape.fr == 2 && shape.teams == 2) rc = launch<INTERP, TIn, TOut, 2, 2>(Q, maps, shape, grid);
             else if (shape.fr == 2) rc = launch<INTERP, TIn, TOut, 2, 1>(Q, maps, shape, grid);
             else rc = launch<INTERP, TIn, TOut, 1, 1>(Q, maps, shape, grid);
             if (rc != R360_OK) return rc;

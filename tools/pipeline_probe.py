@@ -62,6 +62,7 @@ def main():
                                   "seconds": round(dt, 3), "panoramas_per_s": round((len(files) - 1) / dt, 2),
                                   "views_per_s": round(ok / dt, 1),
                                   "stage_seconds": {k: round(v, 3) for k, v in executor.STAGE_SECONDS.items()}}), flush=True)
+        os.environ.pop("R360_CPU_CODEC", None)
         # ---- video branch: an 8K Motion-JPEG clip, 2 views per frame as PNG-free JPEG views
         clip = tmp / "clip.avi"
         wr = cv2.VideoWriter(str(clip), cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (7680, 3840))

@@ -25,9 +25,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--interp", nargs="+", default=["cubic", "linear"])
-    ap.add_argument("--fr", nargs="+", type=int, default=[1, 2, 4])
+    ap.add_argument("--fr", nargs="+", type=int, default=[1, 2, 4], help="frames per item (0 = the library's choice)")
     ap.add_argument("--ctas", nargs="+", type=int, default=[0])
-    ap.add_argument("--pct", nargs="+", type=int, default=[75])
+    ap.add_argument("--pct", nargs="+", type=int, default=[0], help="share of the ring a multi-frame item may take (0 = the library's choice)")
     ap.add_argument("--teams", nargs="+", type=int, default=[0], help="consumer teams for four-frame items (0 = the library's choice)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--dtype", default="u8")
@@ -46,14 +46,20 @@ def main():
     for interp in ns.interp:
         for fr in ns.fr:
             for ctas in ns.ctas:
-              for teams in (ns.teams if fr == 4 else ns.teams[:1]):
+              for teams in (ns.teams if fr >= 2 else ns.teams[:1]):
                 for pct in (ns.pct if fr > 1 else ns.pct[:1]):
-                    os.environ["R360_FRAMES"] = str(fr)
+                    if fr > 0:
+                        os.environ["R360_FRAMES"] = str(fr)
+                    else:
+                        os.environ.pop("R360_FRAMES", None)
                     if teams > 0:
                         os.environ["R360_TEAMS"] = str(teams)
                     else:
                         os.environ.pop("R360_TEAMS", None)
-                    os.environ["R360_MULTI_PCT"] = str(pct)
+                    if pct > 0:
+                        os.environ["R360_MULTI_PCT"] = str(pct)
+                    else:
+                        os.environ.pop("R360_MULTI_PCT", None)
                     if ctas > 0:
                         os.environ["R360_TILED_CTAS_PER_SM"] = str(ctas)
                     else:
