@@ -514,6 +514,7 @@ struct TiledParams {
     float border_value;
     long long dst_fstride;  // bytes between the same view of consecutive frames (n_views * image stride)
     const TilePlan* plans;  // whole plan (all views)
+    unsigned int* work_counter;   // zeroed before the launch: the next item of the walk (claimed by the producers)
     const int2* order;      // (view, tile) of the staged tiles sorted by source row: the order the items are walked in
     int n_order;            // entries of `order` (tiles that are not on the fallback list)
     const double2* coords;  // pool of per-pixel maps (tiles with TilePlan::pad[1] > 0)
@@ -807,25 +808,30 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
         // from one band of source rows at a time, so a frame's bytes come out of DRAM once and every view that
         // overlaps the band finds them in L2.  Item = (entry of the order list, frame block); the (view, tile) pair
         // is prefetched two items ahead, the tile's geometry one item ahead.
-        // (Grid-stride on purpose: neighbouring tiles are loaded by different SMs at the same moment and share their
-        // lines through L2.  Giving every block one contiguous run of the list instead was measured at 9.1 GB of DRAM
-        // reads per 16-frame launch against 2.1 GB, and 98 against 145 Gpix/s.)
-        const int stride = (int)gridDim.x;
-        int item = (int)blockIdx.x;
+        // Items are CLAIMED from a counter in global memory, three ahead, not assigned by a grid stride: whatever the
+        // blocks' speeds, the items in flight are always one contiguous stretch of the list, so neighbouring tiles are
+        // loaded by different SMs at the same moment and share their lines through L2.  Measured on B200 (16 x 8K
+        // frames, 12 views, DRAM reads per launch): with a static grid stride the blocks drift apart over their ~400
+        // items each and the stretch in flight grows to many bands -- bilinear (296 blocks) 3.6 GB, a single
+        // four-frame group alone 0.41 GB; claimed items: see profiles/README.md.  (One contiguous run of the list per
+        // block was 9.1 GB and 98 against 145 Gpix/s.)
         const int item_end = total;
-        int idx = item % P.n_order, gb = item / P.n_order;
-        const int step_idx = stride % P.n_order, step_gb = stride / P.n_order;
+        auto claim = [&]() -> int {
+            int v = 0;
+            if (lane == 0) v = (int)atomicAdd(P.work_counter, 1u);
+            return __shfl_sync(0xffffffffu, v, 0);
+        };
+        int item = claim(), item_n1 = claim(), item_n2 = claim();
         int2 vt = make_int2(0, 0), vt_next = make_int2(0, 0);       // (view, tile) of this item / the next one
-        int idx_next = idx + step_idx, gb_next = gb + step_gb;
-        if (idx_next >= P.n_order) { idx_next -= P.n_order; ++gb_next; }
-        if (item < item_end) vt = __ldg(P.order + idx);
-        if (item + stride < item_end) vt_next = __ldg(P.order + idx_next);
+        int gb = item / P.n_order, gb_next = item_n1 / P.n_order;
+        if (item < item_end) vt = __ldg(P.order + (item - gb * P.n_order));
+        if (item_n1 < item_end) vt_next = __ldg(P.order + (item_n1 - gb_next * P.n_order));
         // geometry of the item about to be processed: lanes 0 and 1 hold the record's last two
         // 16-byte pieces (py0 rows xb0 row_bytes | pitch mode_slot - -)
         int4 geo = make_int4(0, 0, 0, 0);
         const TilePlan* gp = P.plans + (long long)vt.x * n_tiles + vt.y;
         if (item < item_end && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
-        for (; item < item_end; item += stride) {
+        for (; item < item_end;) {
             const int py0 = __shfl_sync(0xffffffffu, geo.x, 0), rows_needed = __shfl_sync(0xffffffffu, geo.y, 0);
             const int xb0 = __shfl_sync(0xffffffffu, geo.z, 0), row_bytes = __shfl_sync(0xffffffffu, geo.w, 0);
             const int pitch = __shfl_sync(0xffffffffu, geo.x, 1), mode_slot = __shfl_sync(0xffffffffu, geo.y, 1);
@@ -834,13 +840,14 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
             const int cur_tj = vt.y / P.tiles_x, cur_ti = vt.y - cur_tj * P.tiles_x;
             // advance: the next item's geometry and the (view, tile) pair of the one after it
             {
+                item = item_n1; item_n1 = item_n2;
                 vt = vt_next; gb = gb_next;
-                idx_next += step_idx; gb_next += step_gb;
-                if (idx_next >= P.n_order) { idx_next -= P.n_order; ++gb_next; }
-                if (item + 2 * stride < item_end) vt_next = __ldg(P.order + idx_next);
+                gb_next = item_n1 / P.n_order;
+                if (item_n1 < item_end) vt_next = __ldg(P.order + (item_n1 - gb_next * P.n_order));
+                item_n2 = item_n1 < item_end ? claim() : item_end;
             }
             gp = P.plans + (long long)vt.x * n_tiles + vt.y;
-            if (item + stride < item_end && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
+            if (item < item_end && lane < 2) geo = __ldg(reinterpret_cast<const int4*>(gp) + 21 + lane);
 
             const int mode = mode_slot & 0xff, src_slot = (mode_slot >> 8) & 0xff, wbox = mode_slot >> 16;
             if (mode == kModeFallback) continue;                     // remap_fallback_kernel owns this tile

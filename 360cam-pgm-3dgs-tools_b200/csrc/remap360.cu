@@ -675,6 +675,28 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     return R360_OK;
 }
 
+// Work counters of the tiled kernel's item queue: every launch takes the next one of a pool (zeroed in the launch's
+// stream right before the kernel), so launches of one plan from several host threads / streams do not share a counter.
+constexpr int kWorkCounters = 4096;
+__device__ unsigned int g_work_counters[kWorkCounters];
+std::atomic<unsigned> g_next_work_counter{0};
+
+unsigned int* next_work_counter() {
+    static std::mutex mu;
+    static unsigned int* base[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!base[dev]) {
+            void* p = nullptr;
+            if (cudaGetSymbolAddress(&p, g_work_counters) != cudaSuccess) return nullptr;
+            base[dev] = static_cast<unsigned int*>(p);
+        }
+    }
+    return base[dev] + g_next_work_counter.fetch_add(1, std::memory_order_relaxed) % kWorkCounters;
+}
+
 // Launch shape of the tiled kernel for one call: frames per work item, consumer teams per block, blocks per SM
 // and the shared-memory ring that is left.  Every fast tile of the plan fits the ring of every shape chosen here
 // (ring >= plan->patch_budget); what a shape changes is how many frames share one coordinate / weight set-up.
@@ -836,6 +858,9 @@ struct TiledLauncher {
                 }
                 maps = hit->maps;
             }
+            Q.work_counter = next_work_counter();
+            if (!Q.work_counter) return R360_E_CUDA;
+            R360_CUDA(cudaMemsetAsync(Q.work_counter, 0, sizeof(unsigned int), s));
             int rc;
             if (shape.fr == 4 && shape.teams == 2) rc = launch<INTERP, TIn, TOut, 4, 2>(Q, maps, shape, grid);
             else if (shape.fr == 4) rc = launch<INTERP, TIn, TOut, 4, 1>(Q, maps, shape, grid);
