@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(64) plan_kernel(const __grid_constant__ PlanPa
 
 // Sort key of every (view, tile) for the remap kernel's walk: source slot, then the centre row of the patch;
 // fallback tiles (not staged) get INT_MAX and drop off the end of the list, tiles of the large-patch pass INT_MAX - 1.
-__global__ void __launch_bounds__(256) order_key_kernel(const TilePlan* plans, int n, int* keys) {
+__global__ void __launch_bounds__(256) order_key_kernel(const TilePlan* plans, int n, int* keys, int* patch_bytes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const TilePlan& p = plans[i];
@@ -370,6 +370,8 @@ __global__ void __launch_bounds__(256) order_key_kernel(const TilePlan* plans, i
     const bool staged = mode == kModeFast || mode == kModeFastRows || mode == kModeFastSeam;
     keys[i] = mode == kModeFallback ? INT_MAX : p.pad[0] == -1 ? INT_MAX - 1
             : (slot << 24) + (staged ? max(0, min(p.py0 + p.rows / 2, (1 << 24) - 1)) : 0);
+    // bytes the tile's patch takes in the ring (one frame): the host sizes the batch shape by their mean
+    patch_bytes[i] = staged ? (mode == kModeFast ? staged_rows(p.rows) : p.rows) * p.pitch : 0;
 }
 
 // ---- bulk-async copy / mbarrier wrappers (PTX) ------------------------------------------------

@@ -434,6 +434,7 @@ struct r360_plan {
     int out_stage_bytes, patch_budget, ring_bytes, smem_bytes, ctas_per_sm, use_table, sm_count;
     int frames_pref, teams_multi_pref, ctas_multi_pref;     // launch shape for batches (choose_shape)
     int multi_pct_pref;                                     // share of the ring one multi-frame item may take
+    int mean_patch_bytes;                                   // mean ring bytes of a staged tile's patch (one frame)
     bool bulk_load_ok, bulk_store_ok;
     unsigned char* ws;
     PlanHeader* d_header; ViewDev* d_views; TilePlan* d_plans; int2* d_fallback; int2* d_order; double2* d_coords;
@@ -505,6 +506,9 @@ bool aligned16(const void* p, int64_t pitch, int64_t stride) {
     return reinterpret_cast<uintptr_t>(p) % 16 == 0 && pitch % 16 == 0 && stride % 16 == 0;
 }
 
+struct TiledShape { int fr, teams, ctas, ring, smem, multi_budget; };
+bool shape_for(const r360_plan* pl, int fr, int teams, int ctas, int smem_per_sm, TiledShape* out);
+
 int plan_create(int proj, const r360_images* src, const r360_images* dst, const r360_fisheye_calib* calib,
                 int n_lenses, const std::vector<ViewDev>& views, const r360_options* opt_in,
                 void* workspace, size_t workspace_bytes, void* stream, r360_plan** plan_out) {
@@ -560,10 +564,12 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         pl->ctas_per_sm = want;
         pl->smem_bytes = fixed + pl->ring_bytes;
         // batches: frames per work item / teams / blocks per SM (choose_shape).  8-bit bicubic: four frames per
-        // item on two teams in one block per SM -- one weight table per SM instead of two leaves the ring room for
-        // four frames' patches, and every table entry read serves four pixels (measured on B200, 16 x 8K frames ->
-        // 12 views: 148-150 Gpix/s against 141 with two frames per item on two blocks per SM).  A patch may use the
-        // whole ring of the smallest shape a call can take: one team with kMaxFramesPerItem output stages.
+        // item in ONE block per SM -- one weight table per SM instead of two, and a ring (~187 KB) that holds the
+        // four-frame item being sampled AND the next one, so the L2 -> shared-memory latency of an item is hidden
+        // behind the previous one.  Measured on B200 (16 x 8K frames -> 12 views, profiles/r02_shape_sweep.jsonl):
+        // one team of eight consumer warps 159.4 Gpix/s, two teams (whose second stage set leaves the ring room for
+        // the two items in flight only) 156.7, two blocks per SM with two frames per item 151.5.  A patch may use
+        // the whole ring of the smallest shape a call can take: one team with kMaxFramesPerItem output stages.
         const bool cubic_u8 = pl->use_table == 1;
         const bool linear_u8 = pl->pr.in_dt == R360_U8 && pl->pr.interp == R360_LINEAR && dst->channels == 3;
         // (8-bit bilinear: four frames per item on one team, 264 against 256 Gpix/s with two; 16-bit patches are twice
@@ -571,7 +577,7 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
         // (16-bit bicubic: two frames per item on two teams in one block per SM, 82.1 against 76.8 Gpix/s on two blocks)
         const bool cubic_u16 = in_es == 2 && pl->pr.interp == R360_CUBIC && dst->channels == 3;
         pl->frames_pref = pl->use_table == 2 ? 1 : (cubic_u8 || linear_u8) ? 4 : 2;
-        pl->teams_multi_pref = (cubic_u8 || cubic_u16) ? 2 : 1;
+        pl->teams_multi_pref = cubic_u16 ? 2 : 1;
         pl->multi_pct_pref = linear_u8 ? 100 : 75;
         pl->ctas_multi_pref = (cubic_u8 || cubic_u16) ? 1 : want;
         pl->patch_budget = pl->ring_bytes - (kMaxFramesPerItem - 1) * pl->out_stage_bytes;
@@ -641,12 +647,31 @@ int plan_create(int proj, const r360_images* src, const r360_images* dst, const 
     {
         const int n = n_views * pl->n_tiles;
         int* d_keys = reinterpret_cast<int*>(pl->d_order);            // the order region doubles as key scratch
-        order_key_kernel<<<(n + 255) / 256, 256, 0, s>>>(pl->d_plans, n, d_keys);
+        order_key_kernel<<<(n + 255) / 256, 256, 0, s>>>(pl->d_plans, n, d_keys, d_keys + n);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if ((e = cudaGetLastError()) != cudaSuccess) return fail(e, "order_key_kernel launch");
-        std::vector<int> keys(n);
-        if ((e = cudaMemcpyAsync(keys.data(), d_keys, sizeof(int) * n, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "cudaMemcpyAsync(keys)");
+        std::vector<int> keys(2 * (size_t)n);                          // keys, then the patch bytes of every tile
+        if ((e = cudaMemcpyAsync(keys.data(), d_keys, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "cudaMemcpyAsync(keys)");
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
+        {
+            // 8-bit bicubic batches: two consumer teams when the ring they leave (one block per SM, two sets of output
+            // stages) still holds the two four-frame items being sampled AND a third being loaded; else one team
+            // with the whole ring.  Measured on B200: 8K -> 1600 px preset views (patches 15 KB a frame) 156.7 with
+            // two teams, 159.4 with one; 3840x1920 -> 1600 px (5 KB) 196.7 against 182.7; dual fisheye (12 KB) 166.1
+            // against 157.7.
+            long long sum = 0, cnt = 0;
+            for (int i = 0; i < n; ++i)
+                if (keys[n + i] > 0 && keys[i] < INT_MAX - 1) { sum += keys[n + i]; ++cnt; }
+            pl->mean_patch_bytes = cnt ? (int)(sum / cnt) : 0;
+            if (pl->use_table == 1) {
+                int dev = 0, smem_per_sm = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+                TiledShape two;
+                const bool fits = shape_for(pl, 4, 2, 1, smem_per_sm, &two) && 3LL * 4 * pl->mean_patch_bytes <= two.ring;
+                pl->teams_multi_pref = fits ? 2 : 1;
+            }
+        }
         std::vector<int> idx(n);
         for (int i = 0; i < n; ++i) idx[i] = i;
         // rows are grouped in bands of 128: inside a band the tiles keep their (view, tile) order, so the entries the
@@ -700,7 +725,6 @@ unsigned int* next_work_counter() {
 // Launch shape of the tiled kernel for one call: frames per work item, consumer teams per block, blocks per SM
 // and the shared-memory ring that is left.  Every fast tile of the plan fits the ring of every shape chosen here
 // (ring >= plan->patch_budget); what a shape changes is how many frames share one coordinate / weight set-up.
-struct TiledShape { int fr, teams, ctas, ring, smem, multi_budget; };
 
 
 bool shape_for(const r360_plan* pl, int fr, int teams, int ctas, int smem_per_sm, TiledShape* out) {
@@ -730,7 +754,7 @@ TiledShape choose_shape(const r360_plan* pl, int n_groups) {
     // two teams exist for two- and four-frame items (the instantiations the library carries); the plan's preference
     // applies to its preferred frame count
     int teams = fr >= 2 ? std::min(kMaxTeams, std::max(1, env_int("R360_TEAMS", fr == pl->frames_pref ? pl->teams_multi_pref : 1))) : 1;
-    int ctas = std::max(1, env_int("R360_TILED_CTAS_PER_SM", teams == 2 ? (fr == pl->frames_pref ? pl->ctas_multi_pref : 1) : pl->ctas_per_sm));
+    int ctas = std::max(1, env_int("R360_TILED_CTAS_PER_SM", fr == pl->frames_pref ? pl->ctas_multi_pref : teams == 2 ? 1 : pl->ctas_per_sm));
     TiledShape s;
     for (;;) {
         if (shape_for(pl, fr, teams, ctas, smem_per_sm, &s)) return s;

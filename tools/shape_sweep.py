@@ -65,6 +65,9 @@ def main():
                     else:
                         os.environ.pop("R360_TILED_CTAS_PER_SM", None)
 
+                    from remap360 import api
+                    api.clear_plan_cache()            # the blocks-per-SM variable also shapes the plan (ring, patch budget)
+
                     def fn():
                         remap360.remap_erp(src, views, (1600, 1600), interp=interp, out=out)
                     try:
