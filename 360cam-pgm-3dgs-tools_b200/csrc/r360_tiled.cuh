@@ -445,14 +445,6 @@ __device__ __forceinline__ void st_global_streaming(void* gptr, const int4& v) {
     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// Experiment builds (-DR360_TILED_STATS=1) time what the warps wait for: [0] consumer warps' cycles in the slot
-// loop, [1] of which waiting for a slot's data, [2] producer cycles, [3] of which waiting for ring space / a free
-// slot, [4] slots published, [5] of which multi-frame.  Read back with r360_debug_tiled_stats.
-#ifndef R360_TILED_STATS
-#define R360_TILED_STATS 0
-#endif
-__device__ unsigned long long g_tiled_stats[8];
-
 // ---- the remap kernel -------------------------------------------------------------------------------
 //
 // Persistent and warp-specialised.  Each block walks work items (tile, view, block of FR consecutive frames):
@@ -524,10 +516,7 @@ struct TiledParams {
 };
 
 // Shape of a block: one or two consumer teams of eight warps (a template argument of the kernel) and how many blocks
-// per SM the register allocation must allow (R360_TILED_MINB > 0 overrides the kernel's own default, experiments).
-#ifndef R360_TILED_MINB
-#define R360_TILED_MINB 0
-#endif
+// per SM the register allocation must allow.
 constexpr int kConsumerWarps = 8;                       // warps of a team (256 threads <-> 32 rows x 8 lanes)
 constexpr int kTeamThreads = kConsumerWarps * 32;
 constexpr int kMaxTeams = 2;
@@ -543,7 +532,7 @@ __host__ __device__ constexpr int tiled_default_blocks(int elem_bytes, int inter
     return (elem_bytes == 1 && interp == kLanczos4) ? 1 : (interp == kLinear || interp == kCubic || elem_bytes > 1) ? 2 : 4;
 }
 __host__ __device__ constexpr int tiled_min_blocks(int elem_bytes, int interp, int teams) {
-    return R360_TILED_MINB > 0 ? R360_TILED_MINB : (tiled_default_blocks(elem_bytes, interp) + teams - 1) / teams;
+    return (tiled_default_blocks(elem_bytes, interp) + teams - 1) / teams;
 }
 constexpr int kModeExit = 255;                          // slot record that ends a team's stream
 
@@ -802,10 +791,6 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
         PatchRing ringst;                // identical in every lane
         int oldest = 0, k = 0;
         const uint64_t policy = l2_policy_by_kind(P.l2_policy);
-#if R360_TILED_STATS
-        const long long st_t0 = clock64();
-        long long st_wait = 0, st_slots = 0, st_multi = 0;
-#endif
         // Items are walked in the plan's source-row order (all views interleaved): the blocks of the grid then read
         // from one band of source rows at a time, so a frame's bytes come out of DRAM once and every view that
         // overlaps the band finds them in L2.  Item = (entry of the order list, frame block); the (view, tile) pair
@@ -870,17 +855,11 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
                 const int need = need1 * nf;
                 // ---- find room: wait for the oldest slots to be released until the patches fit ---------
                 int off = 0, charge = 0;
-#if R360_TILED_STATS
-                const long long st_w0 = clock64();
-#endif
                 while ((k - oldest) >= kSlots || !ringst.try_alloc(need, P.ring_bytes, off, charge)) {
                     mbar_wait_relaxed(&empty[oldest % kSlots], (oldest / kSlots) & 1);
                     ringst.release(slots[oldest % kSlots].size, P.ring_bytes);
                     ++oldest;
                 }
-#if R360_TILED_STATS
-                st_wait += clock64() - st_w0; ++st_slots; st_multi += nf > 1;
-#endif
                 unsigned char* patch = ring + off;
                 __syncwarp();                                              // slots[] reads above are done
                 if (lane == 0) {
@@ -957,14 +936,6 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
             }
             __syncwarp();
         }
-#if R360_TILED_STATS
-        if (lane == 0) {
-            atomicAdd(&g_tiled_stats[2], (unsigned long long)(clock64() - st_t0));
-            atomicAdd(&g_tiled_stats[3], (unsigned long long)st_wait);
-            atomicAdd(&g_tiled_stats[4], (unsigned long long)st_slots);
-            atomicAdd(&g_tiled_stats[5], (unsigned long long)st_multi);
-        }
-#endif
         return;
     }
 
@@ -998,19 +969,9 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
     const uint32_t col_tab = smem_u32(table);
     const float col_s = (float)(2 * lane - (kTile - 1)) * (1.0f / (kTile - 1));
     const double col_dlane = (double)lane, col_drow = (double)(warp * 4);
-#if R360_TILED_STATS
-    const long long st_c0 = clock64();
-    long long st_cwait = 0;
-#endif
     for (int k = team;; k += n_teams) {
         const int slot = k % kSlots;
-#if R360_TILED_STATS
-        const long long st_w0 = clock64();
-#endif
         mbar_wait_s(full_s + slot * 8, (k / kSlots) & 1);
-#if R360_TILED_STATS
-        st_cwait += clock64() - st_w0;
-#endif
         const SlotInfo* si = &slots[slot];
         const int mode = si->mode;
         if (mode == kModeExit) break;
@@ -1276,12 +1237,6 @@ __global__ void __launch_bounds__(tiled_threads(TEAMS), tiled_min_blocks((int)si
         }
         __syncwarp();                              // the stage rows are free again
     }
-#if R360_TILED_STATS
-    if (lane == 0) {
-        atomicAdd(&g_tiled_stats[0], (unsigned long long)(clock64() - st_c0));
-        atomicAdd(&g_tiled_stats[1], (unsigned long long)st_cwait);
-    }
-#endif
 }
 
 // Debug twin: what the tiled kernel samples at, written as maps (r360_plan_coords).  One block per

@@ -1253,20 +1253,6 @@ int r360_debug_weight_tables_lanczos4(int16_t* fixed_65536, float* one_d_256) {
     return R360_OK;
 }
 
-// Experiment hook: the wait-time counters of builds with -DR360_TILED_STATS=1 (zeros otherwise); `reset` clears them.
-int r360_debug_tiled_stats(uint64_t* out8, int reset) {
-    unsigned long long h[8] = {};
-    if (out8) {
-        R360_CUDA(cudaMemcpyFromSymbol(h, g_tiled_stats, sizeof(h)));
-        for (int q = 0; q < 8; ++q) out8[q] = h[q];
-    }
-    if (reset) {
-        unsigned long long z[8] = {};
-        R360_CUDA(cudaMemcpyToSymbol(g_tiled_stats, z, sizeof(z)));
-    }
-    return R360_OK;
-}
-
 // Test hook: drives the shared-memory ring allocator (PatchRing, r360_tiled.cuh) on the host with a
 // sequence of patch sizes and at most `slots` allocations in flight; returns -1 if no two live
 // allocations ever overlap and none leaves the ring, else the index of the offending request.

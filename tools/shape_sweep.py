@@ -31,7 +31,6 @@ def main():
     ap.add_argument("--teams", nargs="+", type=int, default=[0], help="consumer teams for four-frame items (0 = the library's choice)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--dtype", default="u8")
-    ap.add_argument("--stats", action="store_true", help="wait-time counters of a -DR360_TILED_STATS=1 build")
     ns = ap.parse_args()
     dev = torch.device("cuda")
     g = torch.Generator(device=dev)
@@ -84,24 +83,10 @@ def main():
                         print(json.dumps({"library": lib, "interp": interp, "fr": fr, "ctas": ctas, "pct": pct, "error": str(exc)}), flush=True)
                         continue
                     ms = e0.elapsed_time(e1) / ns.iters
-                    stats = None
-                    if ns.stats:
-                        import ctypes
-                        import numpy as np
-                        from remap360 import _lib
-                        L = _lib.load()
-                        buf = np.zeros(8, dtype=np.uint64)
-                        L.r360_debug_tiled_stats(ctypes.c_void_p(0), 1)
-                        fn()
-                        torch.cuda.synchronize()
-                        L.r360_debug_tiled_stats(ctypes.c_void_p(buf.ctypes.data), 0)
-                        c, cw, p, pw, sl, mu = (int(x) for x in buf[:6])
-                        stats = {"consumer_wait_frac": round(cw / max(c, 1), 4), "producer_wait_frac": round(pw / max(p, 1), 4),
-                                 "slots": sl, "multi_slots": mu}
                     sha = hashlib.sha256(out[:2].view(torch.uint8).cpu().numpy().tobytes()).hexdigest()[:12]
                     print(json.dumps({"library": os.path.basename(lib), "interp": interp, "dtype": ns.dtype, "fr": fr, "ctas": ctas, "teams": teams,
                                       "pct": pct, "ms": round(ms, 4), "Gpix_per_s": round(out.numel() / 3 / ms / 1e6, 1),
-                                      "sha": sha, "stats": stats}), flush=True)
+                                      "sha": sha}), flush=True)
 
 
 if __name__ == "__main__":
