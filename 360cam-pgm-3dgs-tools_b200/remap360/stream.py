@@ -45,21 +45,26 @@ class StreamingRemapper:
     def __init__(self, views: Sequence[PerspectiveView], size: Tuple[int, int], frame_shape: Tuple[int, int, int],
                  dtype: torch.dtype = torch.uint8, *, interp: str = "cubic", convention: str = "halfpixel",
                  out_dtype: Optional[torch.dtype] = None, device=None, depth: int = 4, batch: int = 2, path: str = "auto",
-                 frame_filter: Optional[Callable[[torch.Tensor, torch.cuda.Stream], None]] = None):
+                 frame_filter: Optional[Callable[[torch.Tensor, torch.cuda.Stream], None]] = None, hold: int = 0):
         if depth < 1 or batch < 1:
             raise ValueError("depth and batch must be >= 1")
+        if hold < 0 or hold > depth - 2 and hold > 0:
+            raise ValueError("hold must leave at least two slots of the ring in circulation")
         self.views = list(views)
         self.size = (int(size[0]), int(size[1]))
         self.interp, self.convention, self.path = interp, convention, path
         self.device = torch.device(device if device is not None else "cuda")
         self.out_dtype = out_dtype or dtype
         self.depth, self.batch = int(depth), int(batch)
+        # results stay valid until `hold` further batches have been handed out (0: until the generator is advanced):
+        # lets a caller copy / encode a result on other threads while it pulls the next ones
+        self.hold = int(hold)
         # in-place per-frame step on the uploaded frames [n, H, W, C], run on the kernel stream before the
         # remap (the cutter's video colour step, PC:299-309)
         self.frame_filter = frame_filter
         with torch.cuda.device(self.device):
-            self._free: List[_Slot] = [_Slot(self.batch, frame_shape, dtype, len(self.views), self.size, self.out_dtype, self.device)
-                                       for _ in range(self.depth)]
+            self._free: Deque[_Slot] = deque(_Slot(self.batch, frame_shape, dtype, len(self.views), self.size, self.out_dtype, self.device)
+                                       for _ in range(self.depth))
             self.s_h2d = torch.cuda.Stream(self.device)
             self.s_kernel = torch.cuda.Stream(self.device)
             self.s_d2h = torch.cuda.Stream(self.device)
@@ -108,13 +113,15 @@ class StreamingRemapper:
 
     def run(self, frames: Iterable[torch.Tensor]) -> Iterator[torch.Tensor]:
         """Generator over results, in order.  A yielded tensor is a view of a pinned ring buffer: it
-        stays valid until the generator is advanced again."""
+        stays valid until the generator is advanced again (with ``hold`` = h: until h more batches have been
+        handed out after the batch it belongs to)."""
         cur: Optional[_Slot] = None
         for frame in frames:
             if cur is None:
-                while not self._free:
+                # the oldest drained slot is reused, and only once `hold` younger ones lie between it and the caller
+                while len(self._free) <= self.hold and self._inflight:
                     yield from self._drain_one()
-                cur = self._free.pop()
+                cur = self._free.popleft()
                 cur.n = 0
             self._upload(cur, frame)
             if cur.n == self.batch:

@@ -112,7 +112,7 @@ class _MjpegGpuFrames:
     """Frames of a Motion-JPEG stream decoded on the device: raw packets from the container, nvJPEG on `workers`
     host threads (one codec + one CUDA stream each), results handed over in order as CUDA tensors [H, W, 3] BGR."""
 
-    def __init__(self, source, wanted: Sequence[int], device, workers: int = 4, ahead: int = 6):
+    def __init__(self, source, wanted: Sequence[int], device, workers: int = 6, ahead: int = 10):
         import cv2
         self.cv2, self.source, self.wanted, self.device = cv2, str(source), list(wanted), device
         self.workers, self.ahead = max(1, workers), max(2, ahead)
@@ -275,7 +275,7 @@ def _run_bucket(source, jobs, n_in, in_fps, stop_event, shard, device, pool, mjp
         from .executor import job_convention
         remapper = StreamingRemapper(views, (first.width, first.height), (h_in, w_in, 3), torch.uint8,
                                      interp=_INTERP[first.interp], convention=job_convention(), frame_filter=frame_filter,
-                                     device=device)
+                                     device=device, depth=6, hold=2)
         source_frames = (_MjpegGpuFrames(source, wanted, device) if mjpeg_gpu else _OpenCvFrames(source, wanted))
 
         from .executor import _stage
@@ -289,34 +289,43 @@ def _run_bucket(source, jobs, n_in, in_fps, stop_event, shard, device, pool, mjp
                     return
                 yield fr
 
-        # A result is a view of a pinned ring slot that the remapper reuses once the loop moves on: every writer
-        # task first takes its own copy of its view (the copies of a frame run in parallel on the pool), the loop
-        # only waits for those copies, encoding and disk I/O continue behind it.
-        futures, produced = deque(), 0
-        copied = threading.Semaphore(0)
+        # A result is a view of a pinned ring slot.  The remapper keeps a handed-out batch untouched until two more
+        # batches have been handed out (hold=2), so the loop does not copy anything itself: a few dedicated threads
+        # copy the views of a frame out of the ring and pass each copy on to the writer pool (encoding, disk I/O);
+        # the loop only makes sure, before it advances, that the copies of the frame before last are done, and
+        # bounds the number of views waiting for a writer.
+        import numpy as np
+        futures, copying, produced = deque(), deque(), 0
+        copiers = ThreadPoolExecutor(max_workers=4)
 
-        def write_view(path, pinned_view, quality, pix_fmt):
-            try:
-                local = pinned_view.copy()
-            finally:
-                copied.release()
+        def write_view(path, local, quality, pix_fmt):
             with _stage("video_write"):
                 _write_image(path, local, quality, pix_fmt)
 
-        for n, out in enumerate(remapper.run(frames())):
-            views_host = out.numpy()
-            for col, job in enumerate(jobs):
-                path = str(job.output) % (lo + n) if "%" in str(job.output) else str(job.output)
-                futures.append(pool.submit(write_view, pathlib.Path(path), views_host[col], job.jpeg_quality, job.pix_fmt))
-            with _stage("video_copy_wait"):
-                for _ in jobs:
-                    copied.acquire()
-            produced += 1
-            with _stage("video_writer_backpressure"):
-                while len(futures) > 96:                    # bound the views waiting for a writer
-                    futures.popleft().result()
-        for f in futures:
-            f.result()
+        def copy_view(path, pinned_view, quality, pix_fmt):
+            return pool.submit(write_view, path, np.copy(pinned_view), quality, pix_fmt)
+
+        try:
+            for n, out in enumerate(remapper.run(frames())):
+                views_host = out.numpy()
+                batch = []
+                for col, job in enumerate(jobs):
+                    path = str(job.output) % (lo + n) if "%" in str(job.output) else str(job.output)
+                    batch.append(copiers.submit(copy_view, pathlib.Path(path), views_host[col], job.jpeg_quality, job.pix_fmt))
+                copying.append(batch)
+                produced += 1
+                with _stage("video_copy_wait"):
+                    while len(copying) > 2:                 # frames n - 2 and older: out of the ring before it turns
+                        futures.extend(c.result() for c in copying.popleft())
+                with _stage("video_writer_backpressure"):
+                    while len(futures) > 96:                # bound the views waiting for a writer
+                        futures.popleft().result()
+            for batch in copying:
+                futures.extend(c.result() for c in batch)
+            for f in futures:
+                f.result()
+        finally:
+            copiers.shutdown(wait=True)
     if stop_event is not None and stop_event.is_set():
         return 130, ""
     if produced == 0:
