@@ -39,13 +39,19 @@ class StreamingRemapper:
             ...                                       # [V, h, w, C] pinned; valid until the next item
     Frames may also be CUDA tensors that are complete on their producer's stream (frames decoded on the device).
 
-    ``depth`` batches of ``batch`` frames are in flight at once (default 4 x 2: one filling / uploading, one in
-    the kernel, one downloading, one being read by the caller)."""
+    ``depth`` batches of ``batch`` frames are in flight at once.  Default 6 x 1: the host link, not the kernel, bounds
+    this path (the kernel is ten times faster), and single-frame batches interleave the two copy directions most
+    finely -- measured on B200, 16 x 8K frames per call -> 12 views: 15.87 Gpix/s = 0.96 of the link with 6 x 1, 15.18
+    with 4 x 2, 13.2 with 4 x 4, 11.5 with 4 x 8 (profiles/README.md).  Callers whose frames share a long stream and
+    who want the kernel's multi-frame items pass batch=2."""
 
     def __init__(self, views: Sequence[PerspectiveView], size: Tuple[int, int], frame_shape: Tuple[int, int, int],
                  dtype: torch.dtype = torch.uint8, *, interp: str = "cubic", convention: str = "halfpixel",
-                 out_dtype: Optional[torch.dtype] = None, device=None, depth: int = 4, batch: int = 2, path: str = "auto",
+                 out_dtype: Optional[torch.dtype] = None, device=None, depth: int = 6, batch: int = 1, path: str = "auto",
                  frame_filter: Optional[Callable[[torch.Tensor, torch.cuda.Stream], None]] = None, hold: int = 0):
+        import os
+        depth = int(os.environ.get("R360_STREAM_DEPTH", depth))      # experiments: ring shape without code changes
+        batch = int(os.environ.get("R360_STREAM_BATCH", batch))
         if depth < 1 or batch < 1:
             raise ValueError("depth and batch must be >= 1")
         if hold < 0 or hold > depth - 2 and hold > 0:

@@ -275,7 +275,7 @@ def _run_bucket(source, jobs, n_in, in_fps, stop_event, shard, device, pool, mjp
         from .executor import job_convention
         remapper = StreamingRemapper(views, (first.width, first.height), (h_in, w_in, 3), torch.uint8,
                                      interp=_INTERP[first.interp], convention=job_convention(), frame_filter=frame_filter,
-                                     device=device, depth=6, hold=2)
+                                     device=device, depth=6, batch=2, hold=2)
         source_frames = (_MjpegGpuFrames(source, wanted, device) if mjpeg_gpu else _OpenCvFrames(source, wanted))
 
         from .executor import _stage
