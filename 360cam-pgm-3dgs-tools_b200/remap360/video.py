@@ -298,8 +298,38 @@ def _run_bucket(source, jobs, n_in, in_fps, stop_event, shard, device, pool, mjp
         futures, copying, produced = deque(), deque(), 0
         copiers = ThreadPoolExecutor(max_workers=4)
 
+        # JPEG views are encoded by the writer threads' cv2.imwrite -- and, while one of a few permits is free, by
+        # nvJPEG on the device instead (the view goes back up, 7.7 MB; the encoder is ~5 x a host thread).  The two
+        # encoders write the same format (4:4:4, the job's quality); R360_VIDEO_GPU_ENCODERS=0 leaves all to the host.
+        gpu_permits = threading.BoundedSemaphore(max(1, int(os.environ.get("R360_VIDEO_GPU_ENCODERS", "3"))))
+        gpu_state = {"on": int(os.environ.get("R360_VIDEO_GPU_ENCODERS", "3")) > 0 and not os.environ.get("R360_CPU_CODEC")}
+        tls = threading.local()
+
+        def encode_on_device(path, local, quality) -> bool:
+            try:
+                from . import codec
+                if getattr(tls, "jc", None) is None:
+                    with torch.cuda.device(device):
+                        tls.jc, tls.stream = codec.JpegCodec(device), torch.cuda.Stream(device)
+                with torch.cuda.device(device), torch.cuda.stream(tls.stream):
+                    dev_view = torch.from_numpy(local).to(device, non_blocking=False)
+                    data = tls.jc.encode(dev_view, quality, stream=tls.stream)
+                path.parent.mkdir(parents=True, exist_ok=True)
+                path.write_bytes(data)
+                return True
+            except Exception:
+                gpu_state["on"] = False                    # no codec library / not this kind of image: host encoder from now on
+                return False
+
         def write_view(path, local, quality, pix_fmt):
             with _stage("video_write"):
+                if (gpu_state["on"] and path.suffix.lower() in (".jpg", ".jpeg") and local.dtype == np.uint8
+                        and local.ndim == 3 and local.shape[2] == 3 and gpu_permits.acquire(blocking=False)):
+                    try:
+                        if encode_on_device(path, local, quality):
+                            return
+                    finally:
+                        gpu_permits.release()
                 _write_image(path, local, quality, pix_fmt)
 
         def copy_view(path, pinned_view, quality, pix_fmt):
