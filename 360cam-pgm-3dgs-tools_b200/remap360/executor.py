@@ -209,6 +209,27 @@ def _gpu_codec():
         return None
 
 
+_host_writer_pool = None
+_host_writer_lock = threading.Lock()
+
+
+def _host_writers() -> ThreadPoolExecutor:
+    """Host threads that encode and write the views the device encoder does not take."""
+    global _host_writer_pool
+    with _host_writer_lock:
+        if _host_writer_pool is None:
+            _host_writer_pool = ThreadPoolExecutor(max_workers=max(2, (os.cpu_count() or 4) * 3 // 4))
+        return _host_writer_pool
+
+
+def _host_encode_share() -> int:
+    """Per cent of a panorama's JPEG views encoded on the host instead of by nvJPEG (R360_STILL_HOST_ENCODE_PCT)."""
+    try:
+        return min(100, max(0, int(os.environ.get("R360_STILL_HOST_ENCODE_PCT", "40"))))
+    except ValueError:
+        return 40
+
+
 def _is_jpeg(path: pathlib.Path) -> bool:
     return path.suffix.lower() in (".jpg", ".jpeg")
 
@@ -279,15 +300,28 @@ def _run_still_group_on(worker, source: pathlib.Path, jobs: List[ParsedJob], sto
                 with _stage("remap", stream):
                     out = api.remap_erp(dev[None], views, (w, h), interp=interp, convention=job_convention(), stream=stream)[0]
                 encoded = {}
+                host_side = {}                                   # view index -> future of a host-encoded file
                 if jc is not None and out.dtype in (torch.uint8, torch.uint16) and out.shape[-1] in (1, 3):
+                    # a share of the JPEG views goes to host threads (cv2.imwrite) while this thread's nvJPEG
+                    # encoder takes the rest: the device encoder saturates at ~900 views/s whatever the number of
+                    # threads feeding it, and the host has idle cores beside the decoders
+                    share = _host_encode_share()
+                    if share > 0 and out.dtype == torch.uint8 and out.shape[-1] == 3:
+                        for n, k in enumerate(idxs):
+                            if _is_jpeg(jobs[k].output) and (n * share) % 100 + share > 99:
+                                with _stage("download", stream):
+                                    img = out[n].contiguous().cpu().numpy()
+                                host_side[n] = _host_writers().submit(_write_image, jobs[k].output, img, jobs[k].jpeg_quality)
                     with _stage("encode", stream):
                         for n, k in enumerate(idxs):
+                            if n in host_side:
+                                continue
                             if _is_jpeg(jobs[k].output):
                                 # 16-bit views are scaled to 8 bits on the device first (narrow_to_8bit)
                                 encoded[n] = jc.encode(narrow_to_8bit(out[n]).contiguous() if out.dtype == torch.uint16 else out[n],
                                                        jobs[k].jpeg_quality, stream=stream)
                 out_host = None
-                if len(encoded) < len(idxs):
+                if len(encoded) + len(host_side) < len(idxs):
                     with _stage("download", stream):
                         if out.dtype == torch.uint16:
                             out_host = out.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
@@ -296,6 +330,8 @@ def _run_still_group_on(worker, source: pathlib.Path, jobs: List[ParsedJob], sto
                 stream.synchronize()
             with _stage("write"):
                 for n, k in enumerate(idxs):
+                    if n in host_side:
+                        continue
                     if n in encoded:
                         jobs[k].output.parent.mkdir(parents=True, exist_ok=True)
                         jobs[k].output.write_bytes(encoded[n])
@@ -303,6 +339,10 @@ def _run_still_group_on(worker, source: pathlib.Path, jobs: List[ParsedJob], sto
                         img = out_host[n]
                         _write_image(jobs[k].output, img[..., 0] if img.shape[2] == 1 else img, jobs[k].jpeg_quality)
                     results[k] = (0, "")
+            with _stage("host_encode_wait"):
+                for n, fut in host_side.items():
+                    fut.result()
+                    results[idxs[n]] = (0, "")
         except Exception as exc:  # report per job, like a failing ffmpeg process would
             text = "%s: %s" % (type(exc).__name__, exc)
             for k in idxs:
