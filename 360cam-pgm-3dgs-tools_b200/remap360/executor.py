@@ -120,11 +120,23 @@ class _DeviceWorker:
             idle = _idle_workers.setdefault(self._dev, [])
             item = idle.pop() if idle else None
         if item is None:
-            item = (torch.cuda.Stream(), _gpu_codec())
+            item = (torch.cuda.Stream(), _gpu_codec(), {})
         self._item = item
         self.stream = item[0]
         self.codec = None if os.environ.get("R360_CPU_CODEC") else item[1]
+        self._pinned = item[2]                 # (slot, shape) -> pinned staging buffer for views encoded on the host
         return self
+
+    def pinned_view(self, slot: int, shape):
+        """A pinned uint8 buffer of `shape`, kept with the worker (views that leave for the host encoders)."""
+        import torch
+        key = (slot, tuple(shape))
+        buf = self._pinned.get(key)
+        if buf is None:
+            if len(self._pinned) >= 16:
+                self._pinned.clear()
+            buf = self._pinned[key] = torch.empty(tuple(shape), dtype=torch.uint8).pin_memory()
+        return buf
 
     def __exit__(self, *exc):
         with _pool_lock:
@@ -307,11 +319,21 @@ def _run_still_group_on(worker, source: pathlib.Path, jobs: List[ParsedJob], sto
                     # threads feeding it, and the host has idle cores beside the decoders
                     share = _host_encode_share()
                     if share > 0 and out.dtype == torch.uint8 and out.shape[-1] == 3:
-                        for n, k in enumerate(idxs):
-                            if _is_jpeg(jobs[k].output) and (n * share) % 100 + share > 99:
-                                with _stage("download", stream):
-                                    img = out[n].contiguous().cpu().numpy()
-                                host_side[n] = _host_writers().submit(_write_image, jobs[k].output, img, jobs[k].jpeg_quality)
+                        chosen = [n for n, k in enumerate(idxs) if _is_jpeg(jobs[k].output) and (n * share) % 100 + share > 99]
+                        with _stage("download", stream):
+                            # into pinned buffers of this worker, one synchronisation for all of them; the buffers
+                            # are free again when the host encoders' futures have been collected below
+                            staged = []
+                            if os.environ.get("R360_STILL_PINNED", "1") == "0":          # experiment: pageable copies
+                                staged = [out[n].contiguous().cpu() for n in chosen]
+                            else:
+                                for slot, n in enumerate(chosen):
+                                    buf = worker.pinned_view(slot, out[n].shape)
+                                    buf.copy_(out[n], non_blocking=True)
+                                    staged.append(buf)
+                                stream.synchronize()
+                        for n, buf in zip(chosen, staged):
+                            host_side[n] = _host_writers().submit(_write_image, jobs[idxs[n]].output, buf.numpy(), jobs[idxs[n]].jpeg_quality)
                     with _stage("encode", stream):
                         for n, k in enumerate(idxs):
                             if n in host_side:
