@@ -35,6 +35,9 @@ df_cli_outputs.npz      ``parse_arguments``; stdout / stderr / exit code of ``ma
                         usage errors (temp paths replaced by <TMP>); and one real run on two tiny
                         smooth X/Y pairs (LUT, undistorted fisheye, 10 views + masks as PNG) whose
                         input and output images are stored for the end-to-end parity test
+ms_export.json          the MS360xmlToPersCams pose exporters on a synthetic spherical project: view sets and intrinsics
+                        per preset, and whole ``main()`` runs (transforms.json, COLMAP text, RealityScan XMP, Metashape XML,
+                        rotated point cloud; stdout / stderr / exit codes)
 gui_geometry.npz        lon / lat and equirectangular pixel coordinates of 33 x 33 pixel centres of ten views,
                         computed by the reference's own ``direction_from_uv`` / ``lonlat_to_xy`` (gs360_GUI.py:342-424,
                         taken out of the file's syntax tree because the module needs tkinter to import)
@@ -572,6 +575,101 @@ def dump_df_metadata(df):
     (HERE / "df_metadata.json").write_text(json.dumps(out, indent=1) + "\n")
 
 
+def _ms_xml_text():
+    """A synthetic spherical Metashape project for the MS360xmlToPersCams tool: a sensor with data_type / black_level /
+    sensitivity, four cameras (a plain label, one that already carries a view suffix, one with a path separator, a
+    disabled one), a chunk similarity given as rotation / translation / scale children."""
+    rng = np.random.default_rng(4711)
+
+    def rot(ax, ay, az):
+        cx, sx, cy, sy, cz, sz = math.cos(ax), math.sin(ax), math.cos(ay), math.sin(ay), math.cos(az), math.sin(az)
+        rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+        return rz @ ry @ rx
+
+    cams = []
+    for cid, (label, extra) in enumerate((("IMG_0001", ""), ("IMG_0002_A", ""), ("sub/IMG_0003", ""), ("IMG_0004", " enabled=\"false\""))):
+        m = np.eye(4)
+        m[:3, :3] = rot(*(rng.random(3) * 2.0 - 1.0))
+        m[:3, 3] = rng.random(3) * 6.0 - 3.0
+        cams.append("<camera id=\"%d\" sensor_id=\"0\" component_id=\"0\" label=\"%s\"%s><transform>%s</transform></camera>"
+                    % (cid, label, extra, " ".join(repr(float(v)) for v in m.reshape(-1))))
+    r = rot(0.2, -0.35, 0.6)
+    chunk_tf = ("<transform><rotation locked=\"false\">%s</rotation><translation locked=\"false\">-1.5 0.25 2.0</translation>"
+                "<scale locked=\"true\">1.75</scale></transform>") % " ".join(repr(float(v)) for v in r.reshape(-1))
+    sensor = ("<sensor id=\"0\" label=\"spherical\" type=\"spherical\"><resolution width=\"7680\" height=\"3840\"/>"
+              "<data_type>uint16</data_type><black_level>1 2 3</black_level><sensitivity>1 0.5 0.25</sensitivity></sensor>")
+    return ("<?xml version=\"1.0\" encoding=\"UTF-8\"?>\n<document version=\"2.3.0\"><chunk label=\"Chunk 1\" enabled=\"true\">"
+            "<sensors next_id=\"1\">%s</sensors><cameras next_id=\"4\" next_group_id=\"0\">%s</cameras>%s</chunk></document>\n"
+            % (sensor, "".join(cams), chunk_tf))
+
+
+def _run_ms_main(ms, argv, tmp):
+    import contextlib
+    import io
+    out, err = io.StringIO(), io.StringIO()
+    old_argv, code = sys.argv, 0
+    sys.argv = ["gs360_MS360xmlToPersCams.py"] + argv
+    try:
+        with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+            try:
+                ms.main()
+            except SystemExit as exc:
+                code = exc.code if isinstance(exc.code, int) else 1
+    finally:
+        sys.argv = old_argv
+    norm = lambda t: t.replace(str(tmp), "<TMP>")
+    return {"argv": [norm(a) for a in argv], "stdout": norm(out.getvalue()), "stderr": norm(err.getvalue()), "exit": code}
+
+
+def dump_ms_export(ms):
+    """The MS360xmlToPersCams pose exporters (MS:592-720 view sets and intrinsics, :987-1250 writers, :2054-2177
+    main) on a synthetic spherical project: view sets / intrinsics per preset and whole ``main()`` runs -- stdout,
+    stderr, exit code and every written file (text as text, PLY as base64)."""
+    import base64
+    import tempfile
+    out = {"inputs": {}, "presets": {}, "runs": []}
+    for preset in ms.PRESET_CHOICES:
+        cfg = ms.preset_config(preset)
+        focal = cfg["focal_mm"] if cfg.get("hfov_deg") is None else ms.focal_from_hfov_deg(float(cfg["hfov_deg"]), ms.SENSOR_W_MM)
+        out["presets"][preset] = {"views": [list(v) for v in ms.build_views(preset)], "size": int(cfg["size"]), "focal_mm": focal,
+                                  "intrinsics": list(ms.compute_intrinsics(focal, int(cfg["size"]), int(cfg["size"])))}
+    with tempfile.TemporaryDirectory() as tmp_s:
+        tmp = pathlib.Path(tmp_s)
+        text = _ms_xml_text()
+        (tmp / "cameras.xml").write_text(text)
+        out["inputs"]["cameras.xml"] = text
+        for name, blob in (("binary_color.ply", _ply_bytes(True, True)), ("binary_plain.ply", _ply_bytes(True, False))):
+            (tmp / name).write_bytes(blob)
+            out["inputs"][name] = base64.b64encode(blob).decode("ascii")
+        xml = str(tmp / "cameras.xml")
+        runs = [
+            [xml, "--format", "all", "--points-ply", str(tmp / "binary_color.ply")],
+            [xml, "--format", "all", "--preset", "cube105", "--scale", "100", "--world-rot-axis", "1 0 0", "--world-rot-deg", "90",
+             "--points-ply", str(tmp / "binary_plain.ply"), "--pc-rotate-x-plus180", "--ext", ".png", "-o", str(tmp / "out_cube")],
+            [xml, "--preset", "fisheyelike", "-o", str(tmp / "out_fl")],
+            [xml, "--format", "transforms", "--preset", "evenMinus30", "-o", str(tmp / "out_even")],
+            [xml, "--format", "realityscan", "--preset", "2views", "--world-rot-axis", "0,0,1", "--world-rot-deg", "-30", "-o", str(tmp / "out_rs")],
+            [xml, "--format", "colmap", "--preset", "default", "--points-ply", str(tmp / "binary_color.ply"), "--pc-rotate-x-minus90",
+             "-o", str(tmp / "out_colmap")],
+            [xml, "--format", "colmap", "-o", str(tmp / "out_err1")],
+            [str(tmp / "missing.xml")],
+            [xml, "--format", "metashape-multi-camera-system", "--preset", "default"],
+            [xml, "--format", "all", "--points-ply", str(tmp / "nope.ply"), "-o", str(tmp / "out_err2")],
+        ]
+        for argv in runs:
+            before = {f for f in tmp.rglob("*") if f.is_file()}
+            run = _run_ms_main(ms, argv, tmp)
+            run["files"] = {}
+            for f in sorted(set(f for f in tmp.rglob("*") if f.is_file()) - before):
+                rel = str(f.relative_to(tmp))
+                run["files"][rel] = ("base64:" + base64.b64encode(f.read_bytes()).decode("ascii")) if f.suffix == ".ply" else f.read_text()
+                f.unlink()
+            out["runs"].append(run)
+    (HERE / "ms_export.json").write_text(json.dumps(out, indent=1) + "\n")
+
+
 def dump_gui_geometry(reference_dir):
     """The in-repo float64 statement of the view geometry (gs360_GUI.py:342-395, :419-424), evaluated by the
     reference's OWN functions.  gs360_GUI.py cannot be imported here (it needs tkinter), so the five pure functions
@@ -640,11 +738,14 @@ def main():
     if ns.only == "gui_geometry":
         dump_gui_geometry(ns.reference)
         return
-    if ns.only in ("v2f", "df_metadata"):
+    if ns.only in ("v2f", "df_metadata", "ms_export"):
         sys.dont_write_bytecode = True
         sys.path.insert(0, str(pathlib.Path(ns.reference) / "cli_tools"))
         if ns.only == "v2f":
             dump_v2f(ns.reference)
+        elif ns.only == "ms_export":
+            import gs360_MS360xmlToPersCams as ms
+            dump_ms_export(ms)
         else:
             import gs360_DualFisheyeDistortionCalibration as df
             dump_df_metadata(df)
@@ -662,6 +763,8 @@ def main():
     dump_v2f(ns.reference)
     dump_gui_geometry(ns.reference)
     dump_df_metadata(df)
+    import gs360_MS360xmlToPersCams as ms
+    dump_ms_export(ms)
     for p in sorted(HERE.glob("*.json")) + sorted(HERE.glob("*.npz")):
         print("%9d  %s" % (p.stat().st_size, p.name))
 

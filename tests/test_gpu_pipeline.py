@@ -262,3 +262,29 @@ def test_two_worker_processes_write_what_one_process_writes(r360, tmp_path):
         assert len(done) == len(res.jobs) and all(rc == 0 for _j, (rc, _e) in done), done
         outs[world] = {p.name: p.read_bytes() for p in sorted(out_dir.iterdir())}
     assert len(outs[1]) == 10 and outs[1] == outs[2]
+
+
+def test_ms_tool_persp_cut_runs_the_cuda_cutter(tmp_path):
+    """gs360_MS360xmlToPersCams --persp-cut (MS:2019-2051): poses are exported, then the cutter next to the tool is
+    spawned on <xml_dir>/360imgs -- here that cutter is the CUDA one; the cut files carry the names the poses refer to."""
+    import json
+    import subprocess
+    import sys
+    cv2 = pytest.importorskip("cv2")
+    golden = json.loads((pathlib.Path(__file__).parent / "golden" / "ms_export.json").read_text())
+    (tmp_path / "cameras.xml").write_text(golden["inputs"]["cameras.xml"])
+    (tmp_path / "360imgs").mkdir()
+    yy, xx = np.mgrid[0:256, 0:512].astype(np.float32)
+    pano = np.stack([127 + 100 * np.sin(xx / 512 * 6.2832 * (k + 1)) * np.cos(yy / 256 * 3.1416) for k in range(3)], axis=-1).astype(np.uint8)
+    cv2.imwrite(str(tmp_path / "360imgs" / "IMG_0001.jpg"), pano)
+    tool = pathlib.Path(__file__).resolve().parent.parent / "360cam-pgm-3dgs-tools_b200" / "gs360_MS360xmlToPersCams.py"
+    proc = subprocess.run([sys.executable, str(tool), str(tmp_path / "cameras.xml"), "--preset", "default", "--format", "transforms",
+                           "--persp-cut", "--cut-out", str(tmp_path / "cut")], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert "[INFO] Running cut:" in proc.stdout
+    frames = json.loads((tmp_path / "perspective_cams" / "transforms.json").read_text())["frames"]
+    names = {f["file_path"] for f in frames if f["file_path"].startswith("IMG_0001_")}
+    cut = {p.name for p in (tmp_path / "cut").glob("*.jpg")}
+    assert len(cut) == 8 and cut == names
+    img = cv2.imread(str(tmp_path / "cut" / "IMG_0001_A.jpg"))
+    assert img is not None and img.shape == (1600, 1600, 3)
